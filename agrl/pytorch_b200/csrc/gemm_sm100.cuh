@@ -1,0 +1,352 @@
+// gemm_sm100.cuh -- split-bf16 GEMM on tcgen05 tensor cores (sm_100a), shared by the distance matrix
+// (distance.cu) and the graph layers' X.W^T (head.cu).
+//
+//   D[M,N] = sum over plane pairs (pa,pb) of  A_pa[M,K] . B_pb[N,K]^T        (both operands K-major)
+//
+// fp32 operands are pre-split into P bf16 planes (x = x0 + x1 (+ x2), each the bf16 rounding of the
+// remaining residual), laid out [P][rows][K_pad] so ONE 3-D TMA descriptor per operand serves every
+// plane.  P = 3 keeps the six products whose weight is >= 2^-16 of the leading one (fp32-accurate,
+// 24 operand bits); P = 2 keeps three (about 16 operand bits).  Products are exact in the tensor
+// core; accumulation is fp32 in TMEM.
+//
+// Kernel anatomy (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the A and B plane tiles into a
+//               ring of shared-memory stages, completion on mbarriers
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (cta_group::1, 128 x 128 x 16, kind::f16),
+//               tcgen05.commit frees the smem stage / publishes the accumulator
+//   warp 2      TMEM allocator (2 accumulator stages x 128 columns)
+//   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns), transpose through padded smem so that
+//               global stores are full 128 B lines, fused element-wise epilogue functor
+// The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace agrl {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 64;           // CTA tile; BK bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kPlaneTileBytes = BM * BK * 2;         // 16 KiB: one plane of an A (or B) tile
+constexpr int kThreads = 256;
+constexpr int kEpiWarps = 4;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * BN;           // 256 columns (power of two >= 32)
+constexpr int kEpiPad = 33;
+constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPad * 4;
+static_assert(BM == BN, "A and B tiles share one TMA box shape");
+
+template <int P> struct Config {
+    static constexpr int kStages = (P == 3) ? 2 : 3;
+    static constexpr int kStageBytes = 2 * P * kPlaneTileBytes;
+    static constexpr int kNumPairs = (P == 3) ? 6 : (P == 2 ? 3 : 1);
+    // dynamic smem: stages | epilogue staging | barriers ; +1024 for manual alignment
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 1024;
+};
+
+// plane pairs, least significant products first
+__device__ __forceinline__ void pair_of(int P, int i, int &pa, int &pb) {
+    if (P == 3) {
+        const int A[6] = {2, 0, 1, 1, 0, 0}, B[6] = {0, 2, 1, 0, 1, 0};
+        pa = A[i]; pb = B[i];
+    } else if (P == 2) {
+        const int A[3] = {1, 0, 0}, B[3] = {0, 1, 0};
+        pa = A[i]; pb = B[i];
+    } else { pa = 0; pb = 0; }
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);      // start address, 16-byte units
+    d |= static_cast<uint64_t>(1) << 16;                          // leading byte offset (unused when swizzled)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // stride byte offset
+    d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, dense
+constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ---- epilogue functors: value for output element (row, col) given the accumulator -------------
+struct EpiDistance {            // distance.py:59-73 / :76-89
+    const float *qn, *gn;       // squared norms (euclidean); unused for cosine
+    float *out;
+    int64_t ld;
+    int metric;
+    struct Col { float gn; };
+    __device__ __forceinline__ Col col_state(int col) const {
+        Col c; c.gn = (metric == AGRL_METRIC_EUCLIDEAN) ? __ldg(gn + col) : 0.f; return c;
+    }
+    __device__ __forceinline__ void store(int row, int col, float acc, const Col &c) const {
+        float v;
+        if (metric == AGRL_METRIC_EUCLIDEAN) v = fmaf(-2.0f, acc, __fadd_rn(__ldg(qn + row), c.gn));
+        else v = 1.0f - acc;
+        out[static_cast<size_t>(row) * ld + col] = v;
+    }
+};
+
+struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) + (1-gamma) * x
+    const float *x;             // layer input (M, ldx)
+    const float *scale, *shift; // folded eval-mode BatchNorm1d per output channel
+    float *out;
+    int64_t ldx, ldo;
+    float gamma, slope;
+    struct Col { float scale, shift; };
+    __device__ __forceinline__ Col col_state(int col) const {
+        Col c; c.scale = __ldg(scale + col); c.shift = __ldg(shift + col); return c;
+    }
+    __device__ __forceinline__ void store(int row, int col, float acc, const Col &c) const {
+        float h = fmaf(acc, c.scale, c.shift);
+        h = h >= 0.f ? h : h * slope;
+        const float xin = __ldg(x + static_cast<size_t>(row) * ldx + col);
+        out[static_cast<size_t>(row) * ldo + col] = fmaf(gamma, h, (1.0f - gamma) * xin);
+    }
+};
+
+// ---- the kernel --------------------------------------------------------------------------------
+template <int P, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  int M, int N, int k_pad, Epi epi) {
+    using Cfg = Config<P>;
+    extern __shared__ unsigned char smem_dyn[];
+    // 128B-swizzled tiles need 1024-byte alignment
+    unsigned char *smem = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+    float *epi_buf = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes + kEpiBytes);
+    // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * Cfg::kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * Cfg::kStages;
+    const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::kStages + 2 * kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = k_pad / BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_a);
+        prefetch_tensormap(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (lane == 0) {
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + P * kPlaneTileBytes;
+                    mbar_arrive_expect_tx(full, Cfg::kStageBytes);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kPlaneTileBytes, &map_a, full, kb * BK, m0, p);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) tma_load_3d(sb + p * kPlaneTileBytes, &map_b, full, kb * BK, n0, p);
+                }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc(BM, BN);
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);        // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(bar_full + 8 * stage, phase);            // TMA bytes have landed
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + P * kPlaneTileBytes;
+#pragma unroll
+                    for (int i = 0; i < Cfg::kNumPairs; ++i) {
+                        int pa, pb;
+                        pair_of(P, i, pa, pb);
+                        const uint64_t da = make_smem_desc(sa + pa * kPlaneTileBytes);
+                        const uint64_t db = make_smem_desc(sb + pb * kPlaneTileBytes);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
+                            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(bar_empty + 8 * stage);               // frees the smem stage when the MMAs retire
+                    if (kb == num_kb - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;                                   // == warp % 4: the TMEM lane quarter
+        float *buf = epi_buf + ew * 32 * kEpiPad;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int row_base = m0 + ew * 32;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) buf[lane * kEpiPad + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                const int col = n0 + c * 32 + lane;
+                if (col < N) {
+                    const typename Epi::Col cs = epi.col_state(col);
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = row_base + rr;
+                        if (row < M) epi.store(row, col, buf[rr * kEpiPad + lane], cs);
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+// 3-D tensor map over planes [P][rows][k_pad] of bf16: box = (BK, BM, 1), 128-byte swizzle
+int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P);
+
+template <int P, class Epi>
+int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,
+                      const Epi &epi, cudaStream_t st) {
+    using Cfg = Config<P>;
+    auto kern = split_gemm_kernel<P, Epi>;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}
+
+// fp32 rows -> bf16 planes (+ optional squared norms / L2 normalisation); see split.cu
+struct SplitArgs {
+    const float *src; int64_t ld;      // (rows, dim) fp32
+    __nv_bfloat16 *planes;             // [P][rows][k_pad]
+    float *sumsq;                      // optional: per-row sum of squares (of the un-normalised row)
+    int64_t rows; int dim; int k_pad; int P;
+    int normalize;                     // 1: split x / max(||x||, 1e-12) instead of x (cosine_distance)
+};
+int launch_split_planes(const SplitArgs &a, cudaStream_t st);
+
+static inline int64_t pad_k(int64_t dim) { return (dim + BK - 1) / BK * BK; }
+
+}  // namespace gemm
+}  // namespace agrl

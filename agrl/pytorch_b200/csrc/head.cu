@@ -1,0 +1,509 @@
+// head.cu -- the VMGN adaptive graph head, eval mode (torchreid/models/vmgn.py:296-321).
+//
+// Per batch of B tracklets (S frames, P = 7 pyramid strips, V = S*P region nodes, C channels):
+//
+//   pool_kernel        one pass over both layer4 maps (the only HBM-heavy step, 2 x S*C*h*w*4 B per
+//                      tracklet): strip means -> node tensor X0 (B,V,C) written directly in node order
+//                      (vmgn.py:304-308, no cat / transpose copies, x4_2 read once instead of three
+//                      times) and the global mean -> BN neck -> out[:, :C] (vmgn.py:299-301).
+//   graph_kernel       one CTA per tracklet: Gram matrix on CUDA cores in fp32 (the cancellation in
+//                      |xi|^2+|xj|^2-2xi.xj needs it), affinity 2/(exp(d)+1) (vmgn.py:114-120), L1 row
+//                      normalisation of affinity and pose graph with warp shuffles (:157,:162), average
+//                      (:164), then Y = G.X (the message passing, :168, re-associated as (G.X).W^T)
+//                      emitted straight as bf16 operand planes for the tensor-core GEMM.
+//   split_gemm_kernel  (gemm_sm100.cuh) Y.W^T on tcgen05 with the layer's epilogue fused:
+//                      0.9*X + 0.1*LeakyReLU(BN(.)) (vmgn.py:169-172).
+//   attn_kernel        temporal attention (vmgn.py:276-277), part mean, BN neck -> out[:, C:] (:317-321).
+#include "gemm_sm100.cuh"
+
+namespace agrl {
+
+constexpr int kParts = 7;              // calc_splits(4) = [4,2,1] (utils/reidtools.py:13-15)
+constexpr int kMaxNodes = 64;
+constexpr int kHeadThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: folded BN vectors
+// ------------------------------------------------------------------------------------------------
+struct FoldArgs {
+    const float *w[AGRL_HEAD_MAX_LAYERS + 2], *b[AGRL_HEAD_MAX_LAYERS + 2];
+    const float *mean[AGRL_HEAD_MAX_LAYERS + 2], *var[AGRL_HEAD_MAX_LAYERS + 2];
+    float *scale[AGRL_HEAD_MAX_LAYERS + 2], *shift[AGRL_HEAD_MAX_LAYERS + 2];
+    int channels;
+    float eps;
+};
+
+__global__ void fold_bn_kernel(FoldArgs a) {
+    const int which = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.channels; c += gridDim.x * blockDim.x) {
+        const float s = __fdiv_rn(a.w[which][c], sqrtf(a.var[which][c] + a.eps));
+        a.scale[which][c] = s;
+        a.shift[which][c] = fmaf(-a.mean[which][c], s, a.b[which][c]);
+    }
+}
+
+struct Prepared {                       // layout of the caller-owned "prepared" buffer
+    __nv_bfloat16 *w_planes[AGRL_HEAD_MAX_LAYERS];     // [P][C][C]
+    float *scale[AGRL_HEAD_MAX_LAYERS + 2], *shift[AGRL_HEAD_MAX_LAYERS + 2];   // layers.., global, att
+    size_t bytes;
+};
+
+static Prepared carve_prepared(const agrl_head_params *p, void *buf) {
+    Carver c(buf);
+    Prepared r;
+    const size_t C = static_cast<size_t>(p->channels);
+    for (int l = 0; l < p->num_layers; ++l) r.w_planes[l] = c.take<__nv_bfloat16>(p->split * C * C);
+    for (int l = 0; l < p->num_layers + 2; ++l) { r.scale[l] = c.take<float>(C); r.shift[l] = c.take<float>(C); }
+    r.bytes = c.total();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling: grid (C/64, B), 8 warps x 8 channels, loop over the S frames
+// ------------------------------------------------------------------------------------------------
+struct PoolArgs {
+    const float *x41, *x42;            // (B*S, C, hw)
+    float *nodes;                      // (B, V, C)
+    float *out; int64_t ld_out;        // (B, 2C): global branch -> [:, :C]
+    const float *g_scale, *g_shift;    // folded global_bottleneck
+    int S, C, hw;
+};
+
+constexpr int kPoolCh = 64;            // channels per CTA
+
+template <bool kVec>
+__global__ void __launch_bounds__(kHeadThreads)
+pool_kernel(PoolArgs a) {
+    extern __shared__ float s_nodes[];                 // [S][7][kPoolCh]
+    const int b = blockIdx.y, c0 = blockIdx.x * kPoolCh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, sub = lane & 7;         // 8-lane group <-> quarter strip
+    const int hw = a.hw, qlen = hw >> 2;
+    const float inv_q = 1.0f / static_cast<float>(qlen), inv_h = 1.0f / static_cast<float>(2 * qlen);
+    const float inv_w = 1.0f / static_cast<float>(hw);
+
+    float gsum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gsum[i] = 0.f;
+
+    for (int s = 0; s < a.S; ++s) {
+        const size_t frame = (static_cast<size_t>(b) * a.S + s) * a.C;
+        float q1[8], q2[8];
+        if (kVec) {
+            // hw == 128: one float4 per lane covers a (frame, channel) plane; 16 loads in flight per lane
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const size_t off = (frame + c0 + warp * 8 + i) * hw + lane * 4;
+                const float4 v1 = __ldcs(reinterpret_cast<const float4 *>(a.x41 + off));
+                const float4 v2 = __ldcs(reinterpret_cast<const float4 *>(a.x42 + off));
+                q1[i] = (v1.x + v1.y) + (v1.z + v1.w);
+                q2[i] = (v2.x + v2.y) + (v2.z + v2.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const size_t off = (frame + c0 + warp * 8 + i) * hw + grp * qlen;
+                float s1 = 0.f, s2 = 0.f;
+                for (int e = sub; e < qlen; e += 8) { s1 += a.x41[off + e]; s2 += a.x42[off + e]; }
+                q1[i] = s1; q2[i] = s2;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v1 = q1[i], v2 = q2[i];
+            // quarter sums: reduce inside each 8-lane group
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 4); v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 2); v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1); v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+            const float h2 = v2 + __shfl_xor_sync(0xffffffffu, v2, 8);       // half strips
+            const float w2 = h2 + __shfl_xor_sync(0xffffffffu, h2, 16);      // whole map
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
+            gsum[i] += v1;
+            float *dst = s_nodes + (s * kParts) * kPoolCh + warp * 8 + i;
+            if (sub == 0) dst[grp * kPoolCh] = v2 * inv_q;                   // parts 0..3
+            if (lane == 0) { dst[4 * kPoolCh] = h2 * inv_h; dst[6 * kPoolCh] = w2 * inv_w; }
+            if (lane == 16) dst[5 * kPoolCh] = h2 * inv_h;
+        }
+    }
+    // global branch: mean over (S, h, w), BN neck
+    if (lane == 0) {
+        const float inv_all = 1.0f / (static_cast<float>(a.S) * static_cast<float>(hw));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + warp * 8 + i;
+            a.out[static_cast<size_t>(b) * a.ld_out + c] = fmaf(gsum[i] * inv_all, a.g_scale[c], a.g_shift[c]);
+        }
+    }
+    __syncthreads();
+    // node rows: V rows of kPoolCh contiguous floats
+    const int V = a.S * kParts;
+    float *nodes = a.nodes + static_cast<size_t>(b) * V * a.C + c0;
+    for (int i = threadIdx.x; i < V * kPoolCh; i += kHeadThreads) {
+        const int v = i / kPoolCh, c = i % kPoolCh;
+        nodes[static_cast<size_t>(v) * a.C + c] = s_nodes[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph kernel: one CTA per tracklet
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunk = 256;                 // channels staged per step
+constexpr int kXsLd = kChunk + 4;           // padded row stride (floats), keeps float4 alignment
+constexpr int kGLd = kMaxNodes + 1;
+
+struct GraphArgs {
+    const float *x;                    // (B, V, C) layer input
+    const float *adj;                  // (B, V, V) or null
+    __nv_bfloat16 *y_planes;           // [P][B*V][C]
+    int64_t plane_stride;              // B*V*C
+    int V, C, P;
+    int use_pose, learn_graph;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// stage X[:, c0:c0+kChunk] (V rows; rows V..NT*4-1 stay zero) into shared memory
+__device__ __forceinline__ void stage_chunk(float *xs, const float *x, int V, int C, int c0, int tid) {
+    const int per_row = kChunk / 4;
+    for (int i = tid; i < V * per_row; i += kHeadThreads) {
+        const int r = i / per_row, q = i % per_row;
+        cp_async16(xs + r * kXsLd + q * 4, x + static_cast<size_t>(r) * C + c0 + q * 4);
+    }
+    cp_async_wait_all();
+}
+
+template <int NT>                            // NT = ceil(V/4): 14 for the canonical V = 56
+__global__ void __launch_bounds__(kHeadThreads)
+graph_kernel(GraphArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    float *xs = smem_f;                                // [4*NT][kXsLd]
+    float *g = xs + 4 * NT * kXsLd;                    // [64][65]: Gram, then the mixed graph
+    float *sq = g + kMaxNodes * kGLd;                  // [64]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.V, C = a.C;
+    const int b = blockIdx.x;
+    const float *x = a.x + static_cast<size_t>(b) * V * C;
+
+    for (int i = tid; i < 4 * NT * kXsLd; i += kHeadThreads) xs[i] = 0.f;     // pad rows stay zero
+    __syncthreads();
+
+    if (a.learn_graph) {
+        // ---- Gram matrix: thread (ti, tj) owns rows {ti + NT*e} x {tj + NT*f}, e,f < 4 ----
+        const bool active = tid < NT * NT;
+        const int ti = tid / NT, tj = tid % NT;
+        float acc[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[e][f] = 0.f;
+        for (int c0 = 0; c0 < C; c0 += kChunk) {
+            stage_chunk(xs, x, V, C, c0, tid);
+            __syncthreads();
+            if (active) {
+#pragma unroll 4
+                for (int k = 0; k < kChunk; k += 4) {
+                    float4 av[4], bv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        av[e] = *reinterpret_cast<const float4 *>(xs + (ti + NT * e) * kXsLd + k);
+                        bv[e] = *reinterpret_cast<const float4 *>(xs + (tj + NT * e) * kXsLd + k);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) {
+                            acc[e][f] = fmaf(av[e].x, bv[f].x, acc[e][f]);
+                            acc[e][f] = fmaf(av[e].y, bv[f].y, acc[e][f]);
+                            acc[e][f] = fmaf(av[e].z, bv[f].z, acc[e][f]);
+                            acc[e][f] = fmaf(av[e].w, bv[f].w, acc[e][f]);
+                        }
+                }
+            }
+            __syncthreads();
+        }
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int f = 0; f < 4; ++f) g[(ti + NT * e) * kGLd + (tj + NT * f)] = acc[e][f];
+        }
+        __syncthreads();
+        if (tid < V) sq[tid] = g[tid * kGLd + tid];
+        __syncthreads();
+        // ---- affinity 2 / (exp(sqrt(max(d2, 1e-12))) + 1)  (vmgn.py:116-120) ----
+        for (int i = tid; i < V * V; i += kHeadThreads) {
+            const int r = i / V, c = i % V;
+            float d2 = __fadd_rn(sq[c], sq[r]);
+            d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
+            const float d = sqrtf(fmaxf(d2, 1e-12f));
+            g[r * kGLd + c] = __fdiv_rn(2.0f, expf(d) + 1.0f);
+        }
+        __syncthreads();
+    }
+    // ---- L1 row normalisation + mixing: one warp per row ----
+    const float *adj = a.use_pose ? a.adj + static_cast<size_t>(b) * V * V : nullptr;
+    for (int r = warp; r < V; r += kHeadThreads / 32) {
+        float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
+        const int c1 = lane + 32;
+        if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
+        if (a.use_pose) { a0 = (lane < V) ? adj[r * V + lane] : 0.f; a1 = (c1 < V) ? adj[r * V + c1] : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
+        rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);              // F.normalize eps
+        float m0, m1;
+        if (a.learn_graph && a.use_pose) {
+            m0 = __fdiv_rn(__fdiv_rn(a0, ra) + __fdiv_rn(s0, rs), 2.0f);
+            m1 = __fdiv_rn(__fdiv_rn(a1, ra) + __fdiv_rn(s1, rs), 2.0f);
+        } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
+        else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
+        __syncwarp();
+        if (lane < V) g[r * kGLd + lane] = m0;
+        if (c1 < kMaxNodes) g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
+    }
+    // rows V..63 of the graph are never read; columns V..63 are zero
+    __syncthreads();
+
+    // ---- Y = G . X : thread (rg, cq) owns rows {rg*NT .. rg*NT+NT-1} x 4 channels ----
+    const int rg = tid >> 6, cq = tid & 63;
+    const size_t row0 = static_cast<size_t>(b) * V;
+    for (int c0 = 0; c0 < C; c0 += kChunk) {
+        stage_chunk(xs, x, V, C, c0, tid);
+        __syncthreads();
+        float acc[NT][4];
+#pragma unroll
+        for (int r = 0; r < NT; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+        for (int j = 0; j < V; ++j) {
+            const float4 xv = *reinterpret_cast<const float4 *>(xs + j * kXsLd + cq * 4);
+#pragma unroll
+            for (int r = 0; r < NT; ++r) {
+                const float w = g[(rg * NT + r) * kGLd + j];            // warp-uniform address: broadcast
+                acc[r][0] = fmaf(w, xv.x, acc[r][0]); acc[r][1] = fmaf(w, xv.y, acc[r][1]);
+                acc[r][2] = fmaf(w, xv.z, acc[r][2]); acc[r][3] = fmaf(w, xv.w, acc[r][3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NT; ++r) {
+            const int row = rg * NT + r;
+            if (row < V) {
+                float v0 = acc[r][0], v1 = acc[r][1], v2 = acc[r][2], v3 = acc[r][3];
+                __nv_bfloat16 *dst = a.y_planes + (row0 + row) * C + c0 + cq * 4;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    if (p < a.P) {
+                        const __nv_bfloat16 b0 = __float2bfloat16_rn(v0), b1 = __float2bfloat16_rn(v1);
+                        const __nv_bfloat16 b2 = __float2bfloat16_rn(v2), b3 = __float2bfloat16_rn(v3);
+                        __nv_bfloat162 lo = __halves2bfloat162(b0, b1), hi = __halves2bfloat162(b2, b3);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                        *reinterpret_cast<uint2 *>(dst + p * a.plane_stride) = pk;
+                        v0 = __fsub_rn(v0, __bfloat162float(b0)); v1 = __fsub_rn(v1, __bfloat162float(b1));
+                        v2 = __fsub_rn(v2, __bfloat162float(b2)); v3 = __fsub_rn(v3, __bfloat162float(b3));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// temporal attention + part mean + BN neck: one CTA per tracklet
+// ------------------------------------------------------------------------------------------------
+struct AttnArgs {
+    const float *x;                    // (B, V, C) output of the last graph layer
+    float *out; int64_t ld_out;        // (B, 2C): attention branch -> [:, C:]
+    const float *a_scale, *a_shift;    // folded att_bottleneck
+    int S, C;
+};
+
+__global__ void __launch_bounds__(kHeadThreads)
+attn_kernel(AttnArgs a) {
+    __shared__ float s_norm[kMaxNodes];
+    __shared__ float s_att[kMaxNodes];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.S * kParts, C = a.C, b = blockIdx.x;
+    const float *x = a.x + static_cast<size_t>(b) * V * C;
+    // a[s,p] = ||f[s,p,:]||_2
+    for (int r = warp; r < V; r += kHeadThreads / 32) {
+        const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
+        float s = 0.f;
+        for (int i = lane; i < C / 4; i += 32) {
+            const float4 v = __ldg(row + i);
+            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) s_norm[r] = sqrtf(s);
+    }
+    __syncthreads();
+    // att = a / max(sum_s |a|, 1e-12)   (F.normalize p=1 over the frame axis)
+    if (tid < V) {
+        const int p = tid % kParts;
+        float t = 0.f;
+        for (int s = 0; s < a.S; ++s) t += fabsf(s_norm[s * kParts + p]);
+        s_att[tid] = __fdiv_rn(s_norm[tid], fmaxf(t, 1e-12f));
+    }
+    __syncthreads();
+    // fused[p] = sum_s f * att ; mean over p ; BN
+    for (int c4 = tid; c4 < C / 4; c4 += kHeadThreads) {
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < kParts; ++p) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < a.S; ++s) {
+                const int r = s * kParts + p;
+                const float w = s_att[r];
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C) + c4);
+                acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y);
+                acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+            }
+            tot.x += acc.x; tot.y += acc.y; tot.z += acc.z; tot.w += acc.w;
+        }
+        const int c = c4 * 4;
+        float *o = a.out + static_cast<size_t>(b) * a.ld_out + C + c;
+        const float kP = static_cast<float>(kParts);
+        o[0] = fmaf(__fdiv_rn(tot.x, kP), a.a_scale[c], a.a_shift[c]);
+        o[1] = fmaf(__fdiv_rn(tot.y, kP), a.a_scale[c + 1], a.a_shift[c + 1]);
+        o[2] = fmaf(__fdiv_rn(tot.z, kP), a.a_scale[c + 2], a.a_shift[c + 2]);
+        o[3] = fmaf(__fdiv_rn(tot.w, kP), a.a_scale[c + 3], a.a_shift[c + 3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct HeadWorkspace {
+    float *x[2];
+    __nv_bfloat16 *y_planes;
+    size_t bytes;
+};
+
+static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t batch, int32_t S) {
+    Carver c(ws);
+    HeadWorkspace w;
+    const size_t n = static_cast<size_t>(batch) * S * kParts * p->channels;
+    w.x[0] = c.take<float>(n);
+    w.x[1] = c.take<float>(n);
+    w.y_planes = c.take<__nv_bfloat16>(static_cast<size_t>(p->split) * n);
+    w.bytes = c.total();
+    return w;
+}
+
+static int check_params(const agrl_head_params *p) {
+    if (!p) return AGRL_E_INVALID;
+    if (p->num_layers < 0 || p->num_layers > AGRL_HEAD_MAX_LAYERS) return AGRL_E_INVALID;
+    if (p->split != AGRL_SPLIT_BF16X2 && p->split != AGRL_SPLIT_BF16X3) return AGRL_E_INVALID;
+    if (p->channels < kChunk || p->channels % kChunk != 0) return AGRL_E_UNSUPPORTED;
+    if (!p->use_pose && !p->learn_graph) return AGRL_E_INVALID;            // vmgn.py:92 assert
+    return AGRL_OK;
+}
+
+template <int NT>
+static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
+    const size_t smem = (static_cast<size_t>(4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    graph_kernel<NT><<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}
+
+}  // namespace agrl
+
+using namespace agrl;
+
+extern "C" size_t agrl_head_prepared_bytes(const agrl_head_params *p) {
+    if (check_params(p)) return 0;
+    return carve_prepared(p, nullptr).bytes;
+}
+
+extern "C" int agrl_head_prepare_dev(const agrl_head_params *p, void *prepared, size_t prepared_bytes, void *stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if ((rc = agrl_device_ok())) return rc;
+    Prepared pr = carve_prepared(p, prepared);
+    if (!prepared || prepared_bytes < pr.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int C = p->channels;
+    FoldArgs fa;
+    fa.channels = C; fa.eps = p->bn_eps;
+    const int nvec = p->num_layers + 2;
+    for (int l = 0; l < p->num_layers; ++l) {
+        if (!p->linear_weight[l] || !p->bn_weight[l] || !p->bn_bias[l] || !p->bn_mean[l] || !p->bn_var[l]) return AGRL_E_INVALID;
+        fa.w[l] = p->bn_weight[l]; fa.b[l] = p->bn_bias[l]; fa.mean[l] = p->bn_mean[l]; fa.var[l] = p->bn_var[l];
+        gemm::SplitArgs sa{p->linear_weight[l], C, pr.w_planes[l], nullptr, C, C, C, p->split, 0};
+        if ((rc = gemm::launch_split_planes(sa, st))) return rc;
+    }
+    const float *const *extra[2] = {p->global_bn, p->att_bn};
+    for (int e = 0; e < 2; ++e) {
+        const int l = p->num_layers + e;
+        for (int k = 0; k < 4; ++k) if (!extra[e][k]) return AGRL_E_INVALID;
+        fa.w[l] = extra[e][0]; fa.b[l] = extra[e][1]; fa.mean[l] = extra[e][2]; fa.var[l] = extra[e][3];
+    }
+    for (int l = 0; l < nvec; ++l) { fa.scale[l] = pr.scale[l]; fa.shift[l] = pr.shift[l]; }
+    fold_bn_kernel<<<dim3((C + 255) / 256, nvec), 256, 0, st>>>(fa);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}
+
+extern "C" size_t agrl_head_workspace_bytes(const agrl_head_params *p, int64_t batch, int32_t seq_len) {
+    if (check_params(p) || batch < 0 || seq_len < 1) return 0;
+    return carve_head(p, nullptr, batch, seq_len).bytes;
+}
+
+extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prepared,
+                                     const float *x4_1, const float *x4_2, const float *adj,
+                                     float *out, int64_t ld_out, float *nodes_out,
+                                     int64_t batch, int32_t S, int32_t h, int32_t w,
+                                     void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!prepared || !x4_1 || !x4_2 || !out || batch < 0 || S < 1 || h < 1 || w < 1) return AGRL_E_INVALID;
+    if (p->use_pose && !adj) return AGRL_E_INVALID;
+    const int C = p->channels, V = S * kParts, hw = h * w;
+    if (ld_out < 2 * C) return AGRL_E_INVALID;
+    if (V > kMaxNodes || h % 4 != 0 || batch > 65535) return AGRL_E_UNSUPPORTED;
+    if ((rc = agrl_device_ok())) return rc;
+    if (batch == 0) return AGRL_OK;
+    HeadWorkspace hwk = carve_head(p, ws, batch, S);
+    if (!ws || ws_bytes < hwk.bytes) return AGRL_E_WORKSPACE;
+    Prepared pr = carve_prepared(p, const_cast<void *>(prepared));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int L = p->num_layers;
+
+    // 1. pooling (+ global branch)
+    PoolArgs pa{x4_1, x4_2, hwk.x[0], out, ld_out, pr.scale[L], pr.shift[L], S, C, hw};
+    const size_t pool_smem = static_cast<size_t>(S) * kParts * kPoolCh * sizeof(float);
+    const dim3 pgrid(C / kPoolCh, static_cast<unsigned>(batch));
+    const bool vec = (hw == 128) && ((reinterpret_cast<uintptr_t>(x4_1) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(x4_2) & 15u) == 0);
+    if (vec) pool_kernel<true><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
+    else pool_kernel<false><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
+    AGRL_LAUNCH_CHECK();
+
+    // 2. graph layers
+    const int64_t rows = batch * V;
+    CUtensorMap map_y, map_w;
+    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, hwk.y_planes, rows, C, p->split))) return rc;
+    int cur = 0;
+    for (int l = 0; l < L; ++l) {
+        GraphArgs ga{hwk.x[cur], adj, hwk.y_planes, rows * C, V, C, p->split, p->use_pose, p->learn_graph};
+        if (V == 56) rc = launch_graph<14>(ga, batch, st); else rc = launch_graph<16>(ga, batch, st);
+        if (rc) return rc;
+        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split))) return rc;
+        float *dst = (l == L - 1 && nodes_out) ? nodes_out : hwk.x[cur ^ 1];
+        gemm::EpiGraphLayer epi{hwk.x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope};
+        if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        else rc = gemm::launch_split_gemm<2>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        if (rc) return rc;
+        if (dst == nodes_out) { hwk.x[cur ^ 1] = nodes_out; }
+        cur ^= 1;
+    }
+    if (L == 0 && nodes_out)
+        AGRL_CUDA_TRY(cudaMemcpyAsync(nodes_out, hwk.x[0], sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
+
+    // 3. attention + neck
+    AttnArgs aa{hwk.x[cur], out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C};
+    attn_kernel<<<static_cast<unsigned>(batch), kHeadThreads, 0, st>>>(aa);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}

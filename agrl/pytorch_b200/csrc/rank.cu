@@ -1,0 +1,730 @@
+// rank.cu -- CMC / mAP on the GPU, bit-exact with the reference evaluators.
+//
+//   market1501 metric : torchreid/metrics/rank_cylib/rank_cy.pyx:154-241 (eval_market1501_cy)
+//   MARS metric       : torchreid/metrics/rank.py:160-212 (evaluate_mars, Compute_AP)
+//
+// Neither evaluator needs a sorted row.  With the row ordered by key (distance, gallery index):
+//
+//   market1501  AP and the CMC step only depend on the kept-rank of the query's POSITIVES
+//               (same pid, other camera).  One CTA per query gathers the few same-pid gallery items
+//               (positives + same-camera junk) into shared memory, sorts that short list, then
+//               streams the row ONCE, binning every element between the list's keys (upper bound
+//               by branch-free binary search, per-thread private histograms -> no atomics).  A
+//               prefix sum over the bins gives each positive's full rank; subtracting the junk
+//               items in front of it gives the kept rank.  HBM traffic = one read of the matrix.
+//   MARS        only the first max_rank entries of the ordered row are inspected.  One CTA per
+//               query keeps a candidate buffer in shared memory, filtered by a running threshold
+//               (k-th smallest key seen so far), re-compacted by a bitonic sort when it fills.
+//
+// The sequential floating-point recurrences of the reference (float accumulation with the term in
+// double for rank_cy; Python-double arithmetic and numpy's pairwise mean for evaluate_mars) are
+// reproduced with explicitly rounded intrinsics, so no FMA contraction can change a bit.
+#include "common.cuh"
+
+#include <limits.h>
+
+namespace agrl {
+
+constexpr int kRankThreads = 256;
+constexpr int kFastBins    = 64;     // fast path: same-pid list of <= 62 items, padded to 64
+constexpr int kListCap     = 2048;   // shared-histogram path: list of <= 2048 items
+constexpr int kOverflowCtas = 8;     // brute-force path for longer lists
+constexpr uint64_t kKeyMax = 0xFFFFFFFFFFFFFFFFull;
+
+// ------------------------------------------------------------------------------------------------
+// labels: int64 (ABI) -> int32 (kernels), flagging values that do not fit
+// ------------------------------------------------------------------------------------------------
+struct LabelArrays {
+    const int64_t *src[4];
+    int32_t       *dst[4];
+    int64_t        n[4];
+};
+
+__global__ void narrow_labels_kernel(LabelArrays a, uint32_t *status) {
+    const int which = blockIdx.y;
+    const int64_t *src = a.src[which];
+    int32_t *dst = a.dst[which];
+    const int64_t n = a.n[which];
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = src[i];
+        bad |= (v < INT32_MIN || v > INT32_MAX);
+        dst[i] = static_cast<int32_t>(v);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, AGRL_ST_LABEL_RANGE);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory bitonic sort of n2 (power of two) uint64 keys by `nthreads` cooperating threads
+// ------------------------------------------------------------------------------------------------
+template <bool kWarpOnly>
+__device__ __forceinline__ void bitonic_sort_u64(uint64_t *keys, int n2, int tid, int nthreads) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (n2 >> 1); t += nthreads) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const uint64_t a = keys[lo], b = keys[hi];
+                const bool up = ((lo & k) == 0);
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            if (kWarpOnly) __syncwarp(); else __syncthreads();
+        }
+    }
+}
+
+// visit every element of a row once, 16-byte vector loads over the aligned body
+template <class F>
+__device__ __forceinline__ void for_each_in_row(const float *__restrict__ row, int n, int tid,
+                                                int nthreads, F &&f) {
+    int head = static_cast<int>(((16u - (reinterpret_cast<uintptr_t>(row) & 15u)) & 15u) >> 2);
+    if (head > n) head = n;
+    if (tid < head) f(row[tid], tid);
+    const int nvec = (n - head) >> 2;
+    const float4 *v4 = reinterpret_cast<const float4 *>(row + head);
+#pragma unroll 2
+    for (int v = tid; v < nvec; v += nthreads) {
+        const float4 x = __ldg(v4 + v);
+        const int j = head + (v << 2);
+        f(x.x, j); f(x.y, j + 1); f(x.z, j + 2); f(x.w, j + 3);
+    }
+    const int tail0 = head + (nvec << 2);
+    if (tail0 + tid < n) f(row[tail0 + tid], tail0 + tid);     // < 4 leftovers
+}
+
+// ------------------------------------------------------------------------------------------------
+// market1501: one CTA per query
+// ------------------------------------------------------------------------------------------------
+struct MarketArgs {
+    const float   *dist;
+    int64_t        ld;
+    const int32_t *q_pid, *q_cam, *g_pid, *g_cam;
+    int            num_q, num_g, rank_len;        // rank_len = min(max_rank, num_g)
+    float         *ap;                             // [num_q]
+    int32_t       *first_hit;                      // [num_q] kept-rank of the best positive, INT_MAX if invalid
+    int32_t       *kept;                           // [num_q] gallery size after the junk filter
+    uint32_t      *flags;                          // bit0: some valid query has kept < rank_len (stale cmc tail)
+    int32_t       *overflow_list;                  // queries whose same-pid list exceeds kListCap
+    int32_t       *overflow_count;
+};
+
+// AP recurrence of rank_cy.pyx:219-225 over the positives in rank order: term = cum/(rank+1) in
+// double, accumulator rounded to float at each step.  terms[] already holds the double quotients.
+__device__ __forceinline__ float ap_from_terms(const double *terms, int npos) {
+    float acc = 0.f;
+    for (int i = 0; i < npos; ++i) acc = __double2float_rn(__dadd_rn(static_cast<double>(acc), terms[i]));
+    return __fdiv_rn(acc, static_cast<float>(npos));
+}
+
+__global__ void __launch_bounds__(kRankThreads)
+rank_market_kernel(MarketArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *list  = reinterpret_cast<uint64_t *>(smem_raw);                       // kListCap keys
+    uint16_t *hist16 = reinterpret_cast<uint16_t *>(smem_raw + kListCap * 8);       // [kFastBins][256]
+    uint32_t *hist32 = reinterpret_cast<uint32_t *>(smem_raw + kListCap * 8);       // [kListCap+1] (aliases)
+    __shared__ int s_m, s_njunk, s_npos;
+    __shared__ int s_cnt[kFastBins];
+
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int ng = a.num_g;
+    const int pid = a.q_pid[q], cam = a.q_cam[q];
+    const float *row = a.dist + static_cast<size_t>(q) * a.ld;
+
+    if (tid == 0) { s_m = 0; s_njunk = 0; s_npos = 0; }
+    __syncthreads();
+
+    // ---- phase A: gather the gallery items of the query's identity (labels only) ------------
+    {
+        const int nvec = ng >> 2;
+        const int4 *p4 = reinterpret_cast<const int4 *>(a.g_pid);
+        auto hit = [&](int j) {
+            const bool junk = (a.g_cam[j] == cam);
+            atomicAdd(junk ? &s_njunk : &s_npos, 1);
+            const int slot = atomicAdd(&s_m, 1);
+            if (slot < kListCap) list[slot] = rank_key(row[j], static_cast<uint32_t>(j));
+        };
+        for (int v = tid; v < nvec; v += kRankThreads) {
+            const int4 p = __ldg(p4 + v);
+            if (p.x == pid) hit(4 * v);
+            if (p.y == pid) hit(4 * v + 1);
+            if (p.z == pid) hit(4 * v + 2);
+            if (p.w == pid) hit(4 * v + 3);
+        }
+        const int j = (nvec << 2) + tid;
+        if (j < ng && a.g_pid[j] == pid) hit(j);
+    }
+    __syncthreads();
+    const int m = s_m, njunk = s_njunk, npos = s_npos;
+    const int kept = ng - njunk;
+    if (npos == 0) {                       // identity absent from the gallery: query skipped (pyx:203-205)
+        if (tid == 0) { a.ap[q] = 0.f; a.first_hit[q] = INT_MAX; a.kept[q] = kept; }
+        return;
+    }
+    if (m > kListCap) {                    // rare: handled by rank_market_overflow_kernel
+        if (tid == 0) {
+            a.overflow_list[atomicAdd(a.overflow_count, 1)] = q;
+            a.kept[q] = kept;
+            if (kept < a.rank_len) atomicOr(a.flags, 1u);
+        }
+        return;
+    }
+
+    // ---- phase B: sort the short list --------------------------------------------------------
+    const bool fast = (m <= kFastBins - 2) && (ng <= 65535 * kRankThreads);   // u16 private counters
+    int n2 = kFastBins;
+    while (n2 < m + 1) n2 <<= 1;           // at least one pad entry
+    for (int i = m + tid; i < n2; i += kRankThreads) list[i] = kKeyMax;
+    if (fast) {
+#pragma unroll 8
+        for (int t = 0; t < kFastBins; ++t) hist16[t * kRankThreads + tid] = 0;
+    } else {
+        for (int i = tid; i <= kListCap; i += kRankThreads) hist32[i] = 0;
+    }
+    __syncthreads();
+    if (fast) {
+        if (tid < 32) bitonic_sort_u64<true>(list, kFastBins, tid, 32);
+        __syncthreads();
+    } else {
+        bitonic_sort_u64<false>(list, n2, tid, kRankThreads);
+    }
+    const uint64_t key_max = list[m - 1];
+
+    // ---- phase C: one pass over the row, bin each element between the list keys ---------------
+    if (fast) {
+        uint16_t *mine = hist16 + tid;
+        for_each_in_row(row, ng, tid, kRankThreads, [&](float d, int j) {
+            const uint64_t key = rank_key(d, static_cast<uint32_t>(j));
+            if (key < key_max) {           // otherwise it precedes none of the list items
+                int t = 0;                 // t = #{i : list[i] <= key}
+#pragma unroll
+                for (int s = kFastBins / 2; s > 0; s >>= 1)
+                    if (list[t + s - 1] <= key) t += s;
+                mine[t * kRankThreads] += 1;
+            }
+        });
+    } else {
+        for_each_in_row(row, ng, tid, kRankThreads, [&](float d, int j) {
+            const uint64_t key = rank_key(d, static_cast<uint32_t>(j));
+            if (key < key_max) {
+                int t = 0;
+                for (int s = n2 >> 1; s > 0; s >>= 1)
+                    if (list[t + s - 1] <= key) t += s;
+                atomicAdd(&hist32[t], 1u);
+            }
+        });
+    }
+    __syncthreads();
+
+    // ---- phase D: bins -> ranks -> AP ----------------------------------------------------------
+    if (fast) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int t = warp; t < m; t += kRankThreads / 32) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(hist16 + t * kRankThreads + lane * 8);
+            int s = (v.x & 0xffff) + (v.x >> 16) + (v.y & 0xffff) + (v.y >> 16) +
+                    (v.z & 0xffff) + (v.z >> 16) + (v.w & 0xffff) + (v.w >> 16);
+            s = warp_sum(s);
+            if (lane == 0) s_cnt[t] = s;
+        }
+        __syncthreads();
+    }
+    if (tid >= 32) return;
+    {
+        const int lane = tid;
+        double *terms = reinterpret_cast<double *>(list);     // overwritten behind the read cursor
+        int carry_rank = 0, carry_junk = 0, carry_pos = 0;
+        int first_hit = INT_MAX;
+        for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            const bool in = i < m;
+            const int cnt = in ? (fast ? s_cnt[i] : static_cast<int>(hist32[i])) : 0;
+            const uint32_t idx = in ? static_cast<uint32_t>(list[i]) : 0u;
+            const bool is_junk = in && (a.g_cam[idx] == cam);
+            const bool is_pos = in && !is_junk;
+            // inclusive scan of cnt, exclusive counts of junk / positives in front of item i
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const uint32_t jm = __ballot_sync(0xffffffffu, is_junk);
+            const uint32_t pm = __ballot_sync(0xffffffffu, is_pos);
+            const uint32_t below = (1u << lane) - 1u;
+            const int full_rank = carry_rank + incl;                       // #{j : key_j < key_i}
+            const int kept_rank = full_rank - (carry_junk + __popc(jm & below));
+            const int pos_before = carry_pos + __popc(pm & below);
+            __syncwarp();
+            if (is_pos) {
+                terms[pos_before] = __ddiv_rn(static_cast<double>(pos_before + 1),
+                                              static_cast<double>(kept_rank + 1));
+                if (pos_before == 0) first_hit = kept_rank;
+            }
+            carry_rank += __shfl_sync(0xffffffffu, incl, 31);
+            carry_junk += __popc(jm);
+            carry_pos += __popc(pm);
+            __syncwarp();
+        }
+        first_hit = __reduce_min_sync(0xffffffffu, first_hit);
+        if (lane == 0) {
+            a.ap[q] = ap_from_terms(terms, npos);
+            a.first_hit[q] = first_hit;
+            a.kept[q] = kept;
+            if (kept < a.rank_len) atomicOr(a.flags, 1u);
+        }
+    }
+}
+
+// Brute-force path for identities with more than kListCap gallery items: O(m * (num_g + m)) per
+// query, a handful of CTAs, global-memory slabs (keys + terms).  Same arithmetic, same results.
+__global__ void __launch_bounds__(kRankThreads)
+rank_market_overflow_kernel(MarketArgs a, uint64_t *slab_keys, double *slab_terms) {
+    __shared__ int s_m;
+    __shared__ int s_first;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ng = a.num_g;
+    uint64_t *keys = slab_keys + static_cast<size_t>(blockIdx.x) * ng;
+    double *terms = slab_terms + static_cast<size_t>(blockIdx.x) * ng;
+    const int count = *a.overflow_count;
+    for (int o = blockIdx.x; o < count; o += gridDim.x) {
+        const int q = a.overflow_list[o];
+        const int pid = a.q_pid[q], cam = a.q_cam[q];
+        const float *row = a.dist + static_cast<size_t>(q) * a.ld;
+        if (tid == 0) { s_m = 0; s_first = INT_MAX; }
+        __syncthreads();
+        for (int j = tid; j < ng; j += kRankThreads)
+            if (a.g_pid[j] == pid) keys[atomicAdd(&s_m, 1)] = rank_key(row[j], static_cast<uint32_t>(j));
+        __syncthreads();
+        const int m = s_m;
+        int npos_total = 0;
+        for (int i = warp; i < m; i += kRankThreads / 32) {
+            const uint64_t key = keys[i];
+            const uint32_t idx = static_cast<uint32_t>(key);
+            const bool self_junk = (a.g_cam[idx] == cam);
+            if (self_junk) continue;                                   // warp-uniform
+            int full = 0, junk_before = 0, pos_before = 0;
+            for (int j = lane; j < ng; j += 32) full += (rank_key(row[j], static_cast<uint32_t>(j)) < key);
+            for (int j = lane; j < m; j += 32) {
+                const uint64_t kj = keys[j];
+                if (kj < key) {
+                    if (a.g_cam[static_cast<uint32_t>(kj)] == cam) ++junk_before; else ++pos_before;
+                }
+            }
+            full = warp_sum(full); junk_before = warp_sum(junk_before); pos_before = warp_sum(pos_before);
+            if (lane == 0) {
+                const int kept_rank = full - junk_before;
+                terms[pos_before] = __ddiv_rn(static_cast<double>(pos_before + 1),
+                                              static_cast<double>(kept_rank + 1));
+                if (pos_before == 0) s_first = kept_rank;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < m; ++i)
+                npos_total += (a.g_cam[static_cast<uint32_t>(keys[i])] != cam);
+            a.ap[q] = ap_from_terms(terms, npos_total);
+            a.first_hit[q] = s_first;
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA: averages in the reference's order (rank_cy.pyx:230-239).
+__global__ void __launch_bounds__(1024)
+rank_market_finish_kernel(MarketArgs a, int32_t *hist /*[rank_len+1], zeroed here*/,
+                          float *cmc_out, float *map_out, int64_t *num_valid_out, uint32_t *status) {
+    __shared__ int s_valid;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int nq = a.num_q, R = a.rank_len;
+    if (tid == 0) s_valid = 0;
+    for (int r = tid; r <= R; r += nthr) hist[r] = 0;
+    __syncthreads();
+    int v = 0;
+    for (int q = tid; q < nq; q += nthr) v += (a.first_hit[q] != INT_MAX);
+    v = warp_sum(v);
+    if ((tid & 31) == 0 && v) atomicAdd(&s_valid, v);
+    __syncthreads();
+    const int nvalid = s_valid;
+    if (nvalid == 0) {
+        if (tid == 0) { atomicOr(status, AGRL_ST_NO_VALID_QUERY); if (num_valid_out) *num_valid_out = 0; }
+        return;
+    }
+    const float fvalid = static_cast<float>(nvalid);     // exact: the reference counts in float by +1.
+    const bool stale = (*a.flags & 1u) != 0;
+    if (!stale) {
+        // every valid query has kept >= rank_len: cmc row = [r >= first_hit]
+        for (int q = tid; q < nq; q += nthr) {
+            const int fh = a.first_hit[q];
+            if (fh != INT_MAX) atomicAdd(&hist[fh < R ? fh : R], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {                                    // inclusive scan over r, chunks of 32
+            int carry = 0;
+            for (int base = 0; base < R; base += 32) {
+                const int r = base + tid;
+                int x = r < R ? hist[r] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, x, o);
+                    if (tid >= o) x += n;
+                }
+                if (r < R) cmc_out[r] = __fdiv_rn(static_cast<float>(carry + x), fvalid);
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+        }
+    } else {
+        // rank_cy never clears its `cmc` scratch (pyx:177): positions >= kept keep what the last
+        // valid query that reached them left there.  Replay that per rank position, in query order.
+        for (int r = tid; r < R; r += nthr) {
+            int last = 0, sum = 0;
+            for (int q = 0; q < nq; ++q) {
+                const int fh = a.first_hit[q];
+                if (fh == INT_MAX) continue;
+                if (r < a.kept[q]) last = (r >= fh);
+                sum += last;
+            }
+            cmc_out[r] = __fdiv_rn(static_cast<float>(sum), fvalid);
+        }
+    }
+    if (tid == 0) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < nq; ++q) acc = __fadd_rn(acc, a.ap[q]);     // invalid queries hold +0
+        *map_out = __fdiv_rn(acc, fvalid);
+        if (num_valid_out) *num_valid_out = nvalid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MARS metric: one CTA per query
+// ------------------------------------------------------------------------------------------------
+struct MarsArgs {
+    const float   *dist;
+    int64_t        ld;
+    const int32_t *q_pid, *q_cam, *g_pid, *g_cam;
+    int            num_q, num_g, max_rank;
+    int            buf_len;                         // power of two >= 2*max_rank and >= 2*tile
+    double        *ap;                              // [num_q]
+    int32_t       *first_pos;                       // [num_q] junk-compacted position of the first good hit
+    uint32_t      *status;
+};
+
+constexpr int kMarsTile = 1024;                     // elements examined between buffer checks
+
+__global__ void __launch_bounds__(kRankThreads)
+rank_mars_kernel(MarsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);                 // buf_len keys
+    uint8_t  *cls = reinterpret_cast<uint8_t *>(smem_raw + a.buf_len * 8);  // max_rank class bytes
+    __shared__ int s_cnt, s_ngood;
+    __shared__ unsigned long long s_thr;
+
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int ng = a.num_g, K = a.max_rank, L = a.buf_len;
+    const int pid = a.q_pid[q], cam = a.q_cam[q];
+    const float *row = a.dist + static_cast<size_t>(q) * a.ld;
+
+    if (tid == 0) { s_cnt = 0; s_ngood = 0; s_thr = kKeyMax; }
+    __syncthreads();
+
+    // number of good images: same pid, other camera (rank.py:166)
+    {
+        int good = 0;
+        const int nvec = ng >> 2;
+        const int4 *p4 = reinterpret_cast<const int4 *>(a.g_pid);
+        for (int v = tid; v < nvec; v += kRankThreads) {
+            const int4 p = __ldg(p4 + v);
+            if (p.x == pid) good += (a.g_cam[4 * v] != cam);
+            if (p.y == pid) good += (a.g_cam[4 * v + 1] != cam);
+            if (p.z == pid) good += (a.g_cam[4 * v + 2] != cam);
+            if (p.w == pid) good += (a.g_cam[4 * v + 3] != cam);
+        }
+        const int j = (nvec << 2) + tid;
+        if (j < ng && a.g_pid[j] == pid) good += (a.g_cam[j] != cam);
+        good = warp_sum(good);
+        if ((tid & 31) == 0 && good) atomicAdd(&s_ngood, good);
+    }
+
+    // running top-K: keep candidates below the threshold, compact when the buffer may overflow
+    for (int base = 0; base < ng; base += kMarsTile) {
+        const uint64_t thr = s_thr;
+        const int j = base + tid * 4;
+        // the tile is [base, base+1024): thread t owns 4 consecutive elements
+        float d[4];
+        int n_here = 0;
+        if (j + 3 < ng && ((reinterpret_cast<uintptr_t>(row + j) & 15u) == 0)) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(row + j));
+            d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w; n_here = 4;
+        } else {
+            for (int k = 0; k < 4; ++k) if (j + k < ng) { d[k] = row[j + k]; n_here = k + 1; }
+        }
+        for (int k = 0; k < n_here; ++k) {
+            const uint64_t key = rank_key(d[k], static_cast<uint32_t>(j + k));
+            if (key < thr) buf[atomicAdd(&s_cnt, 1)] = key;       // s_cnt <= L - tile before the tile
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        __syncthreads();                   // everyone holds the same cnt before anyone appends again
+        const bool last = (base + kMarsTile >= ng);
+        if (cnt > L - kMarsTile || last) {
+            for (int i = cnt + tid; i < L; i += kRankThreads) buf[i] = kKeyMax;
+            __syncthreads();
+            bitonic_sort_u64<false>(buf, L, tid, kRankThreads);
+            if (tid == 0) {
+                const int keep = cnt < K ? cnt : K;
+                s_cnt = keep;
+                if (keep == K) s_thr = buf[K - 1];     // later keys must beat the current K-th
+            }
+            __syncthreads();
+        }
+    }
+    // buf[0..K) = the K smallest keys in order (num_g >= K is checked by the host)
+
+    // classify the K ranked items: bit0 good, bit1 junk (rank.py:166-169)
+    for (int n = tid; n < K; n += kRankThreads) {
+        const uint32_t g = static_cast<uint32_t>(buf[n]);
+        const int gp = a.g_pid[g], gc = a.g_cam[g];
+        const bool good = (gp == pid) && (gc != cam);
+        const bool junk = (gp == -1) || ((gp == pid) && (gc == cam));
+        cls[n] = static_cast<uint8_t>((good ? 1 : 0) | (junk ? 2 : 0));
+    }
+    __syncthreads();
+    if (tid != 0) return;
+
+    // Compute_AP (rank.py:180-212) in Python-float (double) arithmetic, one rounding per operation
+    const int ngood = s_ngood;
+    double old_recall = 0.0, old_precision = 1.0, ap = 0.0;
+    int inter = 0, j_eff = 0, good_now = 0, njunk = 0, first_pos = INT_MAX;
+    bool zero_div = false;
+    for (int n = 0; n < K; ++n) {
+        const int c = cls[n];
+        if (c & 1) {
+            if (first_pos == INT_MAX) first_pos = n - njunk;         // cmc[n - njunk:] = 1
+            ++good_now;
+        }
+        if (c & 2) { ++njunk; continue; }
+        if (c & 1) ++inter;
+        if (ngood == 0) { zero_div = true; break; }                  // ZeroDivisionError (rank.py:203)
+        double recall = 0.0, precision = 0.0;
+        if (inter > 0) {
+            recall = __ddiv_rn(static_cast<double>(inter), static_cast<double>(ngood));
+            precision = __ddiv_rn(static_cast<double>(inter), static_cast<double>(j_eff + 1));
+        }
+        const double t = __ddiv_rn(__dmul_rn(__dsub_rn(recall, old_recall),
+                                             __dadd_rn(old_precision, precision)), 2.0);
+        ap = __dadd_rn(ap, t);
+        old_recall = recall;
+        old_precision = precision;
+        ++j_eff;
+        if (good_now == ngood) break;
+    }
+    if (zero_div) atomicOr(a.status, AGRL_ST_ZERO_DIVISION);
+    a.ap[q] = ap;
+    a.first_pos[q] = first_pos;
+}
+
+// numpy's pairwise float64 summation (what np.mean runs on the ap vector, rank.py:176)
+__device__ double pairwise_sum_f64(const double *x, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, x[i]);
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = x[k];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], x[i + k]);
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, x[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(pairwise_sum_f64(x, n2), pairwise_sum_f64(x + n2, n - n2));
+}
+
+__global__ void __launch_bounds__(1024)
+rank_mars_finish_kernel(MarsArgs a, int32_t *hist /*[max_rank+1]*/, double *cmc_out, double *map_out) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int nq = a.num_q, R = a.max_rank;
+    for (int r = tid; r <= R; r += nthr) hist[r] = 0;
+    __syncthreads();
+    for (int q = tid; q < nq; q += nthr) {
+        const int fp = a.first_pos[q];
+        atomicAdd(&hist[fp < R ? fp : R], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int carry = 0;
+        for (int base = 0; base < R; base += 32) {
+            const int r = base + tid;
+            int x = r < R ? hist[r] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, x, o);
+                if (tid >= o) x += n;
+            }
+            if (r < R) cmc_out[r] = __ddiv_rn(static_cast<double>(carry + x), static_cast<double>(nq));
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+    if (tid == 32) *map_out = __ddiv_rn(pairwise_sum_f64(a.ap, nq), static_cast<double>(nq));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct RankWorkspace {
+    int32_t *q_pid, *q_cam, *g_pid, *g_cam;
+    float   *ap_f32;
+    double  *ap_f64;
+    int32_t *first, *kept, *overflow_list, *hist;
+    int32_t *counters;       // [0] overflow_count, [1] flags
+    uint64_t *slab_keys;
+    double   *slab_terms;
+    size_t   bytes;
+};
+
+static RankWorkspace carve_rank(void *ws, int64_t nq, int64_t ng, int64_t max_rank) {
+    Carver c(ws);
+    RankWorkspace w;
+    w.q_pid = c.take<int32_t>(nq);  w.q_cam = c.take<int32_t>(nq);
+    w.g_pid = c.take<int32_t>(ng + 4);  w.g_cam = c.take<int32_t>(ng + 4);
+    w.ap_f32 = c.take<float>(nq);
+    w.ap_f64 = c.take<double>(nq);
+    w.first = c.take<int32_t>(nq);  w.kept = c.take<int32_t>(nq);
+    w.overflow_list = c.take<int32_t>(nq);
+    w.hist = c.take<int32_t>(max_rank + 1);
+    w.counters = c.take<int32_t>(4);
+    w.slab_keys = c.take<uint64_t>(static_cast<size_t>(kOverflowCtas) * ng);
+    w.slab_terms = c.take<double>(static_cast<size_t>(kOverflowCtas) * ng);
+    w.bytes = c.total();
+    return w;
+}
+
+static int narrow_labels(const RankWorkspace &w, const int64_t *qp, const int64_t *gp, const int64_t *qc,
+                         const int64_t *gc, int64_t nq, int64_t ng, uint32_t *status, cudaStream_t st) {
+    LabelArrays la;
+    la.src[0] = qp; la.dst[0] = w.q_pid; la.n[0] = nq;
+    la.src[1] = qc; la.dst[1] = w.q_cam; la.n[1] = nq;
+    la.src[2] = gp; la.dst[2] = w.g_pid; la.n[2] = ng;
+    la.src[3] = gc; la.dst[3] = w.g_cam; la.n[3] = ng;
+    const int64_t nmax = nq > ng ? nq : ng;
+    int blocks = static_cast<int>((nmax + 255) / 256);
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    narrow_labels_kernel<<<dim3(blocks, 4), 256, 0, st>>>(la, status);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}
+
+static int check_rank_args(const void *d, const void *a, const void *b, const void *c, const void *e,
+                           int64_t nq, int64_t ng, int64_t max_rank, int64_t ld) {
+    if (!d || !a || !b || !c || !e) return AGRL_E_INVALID;
+    if (nq < 0 || ng < 1 || max_rank < 1 || ld < ng) return AGRL_E_INVALID;
+    if (nq > INT32_MAX / 2 || ng > INT32_MAX / 2) return AGRL_E_UNSUPPORTED;
+    return AGRL_OK;
+}
+
+}  // namespace agrl
+
+using namespace agrl;
+
+extern "C" size_t agrl_rank_workspace_bytes(int64_t num_q, int64_t num_g, int64_t max_rank) {
+    if (num_q < 0 || num_g < 0 || max_rank < 0) return 0;
+    return carve_rank(nullptr, num_q, num_g, max_rank).bytes;
+}
+
+extern "C" int agrl_rank_market1501_dev(const float *distmat, int64_t ld,
+                                        const int64_t *q_pids, const int64_t *g_pids,
+                                        const int64_t *q_camids, const int64_t *g_camids,
+                                        int64_t num_q, int64_t num_g, int64_t max_rank,
+                                        float *cmc, float *map, float *all_ap, int64_t *num_valid,
+                                        uint32_t *status, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_rank_args(distmat, q_pids, g_pids, q_camids, g_camids, num_q, num_g, max_rank, ld);
+    if (rc) return rc;
+    if (!cmc || !map || !status) return AGRL_E_INVALID;
+    if ((rc = agrl_device_ok())) return rc;
+    const int64_t rank_len = max_rank < num_g ? max_rank : num_g;
+    RankWorkspace w = carve_rank(ws, num_q, num_g, rank_len);
+    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    AGRL_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(uint32_t), st));
+    AGRL_CUDA_TRY(cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), st));
+    if (num_q == 0) {                      // no query at all -> no valid query (pyx:227)
+        const uint32_t one = AGRL_ST_NO_VALID_QUERY;
+        AGRL_CUDA_TRY(cudaMemcpyAsync(status, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+        return AGRL_OK;
+    }
+    if ((rc = narrow_labels(w, q_pids, g_pids, q_camids, g_camids, num_q, num_g, status, st))) return rc;
+
+    MarketArgs a;
+    a.dist = distmat; a.ld = ld;
+    a.q_pid = w.q_pid; a.q_cam = w.q_cam; a.g_pid = w.g_pid; a.g_cam = w.g_cam;
+    a.num_q = static_cast<int>(num_q); a.num_g = static_cast<int>(num_g);
+    a.rank_len = static_cast<int>(rank_len);
+    a.ap = all_ap ? all_ap : w.ap_f32;
+    a.first_hit = w.first; a.kept = w.kept;
+    a.flags = reinterpret_cast<uint32_t *>(w.counters + 1);
+    a.overflow_list = w.overflow_list; a.overflow_count = w.counters;
+
+    const size_t smem = kListCap * 8 + kFastBins * kRankThreads * 2;
+    static_assert(kFastBins * kRankThreads * 2 >= (kListCap + 1) * 4, "hist32 must fit in the hist16 region");
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_market_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    rank_market_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
+    AGRL_LAUNCH_CHECK();
+    rank_market_overflow_kernel<<<kOverflowCtas, kRankThreads, 0, st>>>(a, w.slab_keys, w.slab_terms);
+    AGRL_LAUNCH_CHECK();
+    rank_market_finish_kernel<<<1, 1024, 0, st>>>(a, w.hist, cmc, map, num_valid, status);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}
+
+extern "C" int agrl_rank_mars_dev(const float *distmat, int64_t ld,
+                                  const int64_t *q_pids, const int64_t *g_pids,
+                                  const int64_t *q_camids, const int64_t *g_camids,
+                                  int64_t num_q, int64_t num_g, int64_t max_rank,
+                                  double *cmc, double *map, double *all_ap, uint32_t *status,
+                                  void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_rank_args(distmat, q_pids, g_pids, q_camids, g_camids, num_q, num_g, max_rank, ld);
+    if (rc) return rc;
+    if (!cmc || !map || !status || num_q < 1) return AGRL_E_INVALID;
+    if (max_rank > num_g || max_rank > 8192) return AGRL_E_UNSUPPORTED;
+    if ((rc = agrl_device_ok())) return rc;
+    RankWorkspace w = carve_rank(ws, num_q, num_g, max_rank);
+    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    AGRL_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(uint32_t), st));
+    if ((rc = narrow_labels(w, q_pids, g_pids, q_camids, g_camids, num_q, num_g, status, st))) return rc;
+
+    MarsArgs a;
+    a.dist = distmat; a.ld = ld;
+    a.q_pid = w.q_pid; a.q_cam = w.q_cam; a.g_pid = w.g_pid; a.g_cam = w.g_cam;
+    a.num_q = static_cast<int>(num_q); a.num_g = static_cast<int>(num_g);
+    a.max_rank = static_cast<int>(max_rank);
+    int L = 2 * kMarsTile;
+    while (L < 2 * max_rank) L <<= 1;
+    a.buf_len = L;
+    a.ap = all_ap ? all_ap : w.ap_f64;
+    a.first_pos = w.first;
+    a.status = status;
+
+    const size_t smem = static_cast<size_t>(L) * 8 + align_up(static_cast<size_t>(max_rank), 16);
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    rank_mars_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
+    AGRL_LAUNCH_CHECK();
+    rank_mars_finish_kernel<<<1, 1024, 0, st>>>(a, w.hist, cmc, map);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}

@@ -1,0 +1,118 @@
+// split.cu -- fp32 rows -> bf16 operand planes for the tcgen05 GEMMs, plus the TMA descriptors.
+//
+//   x = p0 + p1 (+ p2),  p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1)
+// The residuals are exact in fp32, so three planes carry all 24 significand bits of x.
+// The same pass produces what the distance epilogues need: the per-row sum of squares
+// (euclidean_squared_distance, distance.py:70-71) or the L2-normalised row x / max(||x||, 1e-12)
+// (cosine_distance, distance.py:86-87: F.normalize then mm).
+#include "gemm_sm100.cuh"
+
+#include <mutex>
+
+namespace agrl {
+namespace gemm {
+
+constexpr int kSplitThreads = 256;
+
+// one CTA per row; two passes over the row (the second one hits L1/L2)
+__global__ void __launch_bounds__(kSplitThreads)
+split_planes_kernel(SplitArgs a) {
+    __shared__ float s_part[kSplitThreads / 32];
+    __shared__ float s_inv;
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float *src = a.src + row * a.ld;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (a.dim % 4 == 0);
+
+    float inv = 1.0f;
+    if (a.sumsq != nullptr || a.normalize) {
+        float s = 0.f;
+        if (vec) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            for (int i = tid; i < a.dim / 4; i += kSplitThreads) {
+                const float4 v = __ldg(s4 + i);
+                s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+            }
+        } else {
+            for (int i = tid; i < a.dim; i += kSplitThreads) { const float v = src[i]; s = fmaf(v, v, s); }
+        }
+        s = warp_sum(s);
+        if ((tid & 31) == 0) s_part[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kSplitThreads / 32; ++w) t += s_part[w];
+            if (a.sumsq) a.sumsq[row] = t;
+            s_inv = fmaxf(sqrtf(t), 1e-12f);       // F.normalize: x / max(||x||_2, eps)
+        }
+        __syncthreads();
+        inv = s_inv;
+    }
+
+    const size_t plane_stride = static_cast<size_t>(a.rows) * a.k_pad;
+    __nv_bfloat16 *dst = a.planes + row * a.k_pad;
+    // pairs of elements -> one 32-bit store per plane
+    for (int i = 2 * tid; i < a.k_pad; i += 2 * kSplitThreads) {
+        float x0 = (i < a.dim) ? src[i] : 0.f;
+        float x1 = (i + 1 < a.dim) ? src[i + 1] : 0.f;
+        if (a.normalize) { x0 = __fdiv_rn(x0, inv); x1 = __fdiv_rn(x1, inv); }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            if (p < a.P) {
+                const __nv_bfloat16 b0 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
+                *reinterpret_cast<__nv_bfloat162 *>(dst + p * plane_stride + i) = __halves2bfloat162(b0, b1);
+                x0 = __fsub_rn(x0, __bfloat162float(b0));
+                x1 = __fsub_rn(x1, __bfloat162float(b1));
+            }
+        }
+    }
+}
+
+int launch_split_planes(const SplitArgs &a, cudaStream_t st) {
+    if (a.rows <= 0) return AGRL_OK;
+    split_planes_kernel<<<static_cast<unsigned>(a.rows), kSplitThreads, 0, st>>>(a);
+    AGRL_LAUNCH_CHECK();
+    return AGRL_OK;
+}
+
+// ---- TMA descriptors ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return AGRL_E_NO_DEVICE;
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(k_pad), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(P)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(k_pad) * 2, static_cast<cuuint64_t>(rows) * k_pad * 2};
+    const cuuint32_t box[3] = {BK, BM, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(planes), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled", __FILE__, __LINE__);
+        return AGRL_E_CUDA;
+    }
+    return AGRL_OK;
+}
+
+}  // namespace gemm
+}  // namespace agrl

@@ -1,0 +1,210 @@
+/*
+ * agrl_b200.h -- C ABI of libagrl_b200.so: AGRL's test-time hot path on one B200 (sm_100a).
+ *
+ * The reference (weleen/AGRL.pytorch) is Python; its only native component is the Cython evaluator
+ * torchreid/metrics/rank_cylib/rank_cy.pyx.  Each entry point below names the reference interface
+ * it replaces (file:line in the reference tree).  The reference-side bindings (ctypes stubs that a
+ * maintainer would drop into torchreid/) are shown in INTEGRATION.md and shipped, ready-made, as
+ * the Python package agrl.pytorch_b200.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - "dev" pointers are device memory of the CURRENT CUDA device, "host" pointers are ordinary
+ *     host memory (pageable or pinned);
+ *   - every *_dev entry point is asynchronous on `stream` (a cudaStream_t passed as void*), does
+ *     no allocation and no synchronisation, and needs a caller-owned workspace whose size comes
+ *     from the matching *_workspace_bytes(); it is re-entrant (no global mutable state), so one
+ *     host thread per GPU may call concurrently (nn.DataParallel, train_vidreid_xent_htri.py:318);
+ *   - every *_host entry point copies host->device, runs the same kernels, copies the result back
+ *     and synchronises before returning (this is the end-to-end path bench.py reports as `e2e`);
+ *   - return value: AGRL_OK (0) or a negative AGRL_E_* code; nothing throws across the boundary.
+ *     Data-dependent conditions the reference reports as Python exceptions are returned through
+ *     `status` words (see each function) so the async path needs no sync to detect them.
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x every compute
+ *     entry point returns AGRL_E_NO_DEVICE.
+ */
+#ifndef AGRL_B200_H_
+#define AGRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGRL_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define AGRL_API __attribute__((visibility("default")))
+#else
+#define AGRL_API
+#endif
+
+/* ---- return codes ------------------------------------------------------------------------- */
+#define AGRL_OK               0
+#define AGRL_E_INVALID       -1   /* bad argument (null pointer, negative size, unknown metric)   */
+#define AGRL_E_NO_DEVICE     -2   /* no CUDA device / not compute capability 10.x                  */
+#define AGRL_E_CUDA          -3   /* a CUDA runtime call failed; see agrl_last_cuda_error()        */
+#define AGRL_E_WORKSPACE     -4   /* workspace missing or smaller than *_workspace_bytes()         */
+#define AGRL_E_UNSUPPORTED   -5   /* shape outside what the kernels handle (documented per call)   */
+#define AGRL_E_NO_VALID_QUERY  -6 /* rank_cy.pyx:227 AssertionError "all query identities do not
+                                     appear in gallery" (host entry points only)                  */
+#define AGRL_E_ZERO_DIVISION -7   /* rank.py:203 ZeroDivisionError: a query has no cross-camera
+                                     match under the MARS metric (host entry points only)          */
+#define AGRL_E_LABEL_RANGE   -8   /* a pid / camid does not fit in int32 (host entry points only)  */
+
+/* ---- bits of the device-side `status` word written by the *_dev ranking calls -------------- */
+#define AGRL_ST_NO_VALID_QUERY  1u
+#define AGRL_ST_ZERO_DIVISION   2u
+#define AGRL_ST_LABEL_RANGE     4u
+
+/* ---- distance metrics (torchreid/metrics/distance.py:46-54) -------------------------------- */
+#define AGRL_METRIC_EUCLIDEAN 0   /* squared euclidean, no clamp, no sqrt (distance.py:59-73)     */
+#define AGRL_METRIC_COSINE    1   /* 1 - cos, rows L2-normalised with eps 1e-12 (distance.py:76-89) */
+
+/* ---- operand split of the tensor-core GEMMs ------------------------------------------------- */
+#define AGRL_SPLIT_BF16X3     3   /* fp32 = 3 bf16 planes, 6 products: fp32-accurate (default for
+                                     the distance matrix)                                          */
+#define AGRL_SPLIT_BF16X2     2   /* 2 planes, 3 products: ~2^-17 relative per product (default for
+                                     the graph layers, whose output enters with gamma = 0.1)       */
+
+AGRL_API int         agrl_abi_version(void);
+AGRL_API const char *agrl_status_string(int code);
+AGRL_API const char *agrl_last_cuda_error(void);           /* thread-local text of the last CUDA failure   */
+/* 0 when the current device can run this library (compute capability 10.x), else AGRL_E_NO_DEVICE */
+AGRL_API int         agrl_device_ok(void);
+/* number of kernels this library has launched from the calling thread (bench.py `gpu_launches`)   */
+AGRL_API uint64_t    agrl_launch_count(void);
+
+/* =============================================================================================
+ * (3) Ranking -- replaces rank_cy.evaluate_cy (torchreid/metrics/rank_cylib/rank_cy.pyx:24-32,
+ *     eval_market1501_cy :154-241) and evaluate_mars / Compute_AP (torchreid/metrics/rank.py:160-212),
+ *     both reached through evaluate_rank (rank.py:215-238).
+ *
+ *     Ordering: each row is ranked by (distance, gallery index) ascending, NaN last, -0 == +0,
+ *     i.e. numpy.argsort(kind='stable'); the reference's default argsort leaves ties undefined.
+ *     Labels are int64 in the ABI (rank_cy.pyx:26-29 casts to int64) but must fit in int32.
+ * ============================================================================================= */
+
+AGRL_API size_t agrl_rank_workspace_bytes(int64_t num_q, int64_t num_g, int64_t max_rank);
+
+/*
+ * market1501 metric, fp32 semantics of rank_cy (float accumulators, AP term in double rounded to
+ * float at every step, stale `cmc` scratch tail when the kept gallery is shorter than max_rank).
+ *   distmat_dev   (num_q, num_g) fp32, row stride ld_dist elements
+ *   cmc_dev       out, min(max_rank, num_g) floats      all_ap_dev  out, num_q floats (may be NULL)
+ *   map_dev       out, 1 float                          num_valid_dev out, 1 int64 (may be NULL)
+ *   status_dev    out, 1 uint32: AGRL_ST_NO_VALID_QUERY | AGRL_ST_LABEL_RANGE (outputs then undefined)
+ */
+AGRL_API int agrl_rank_market1501_dev(const float *distmat_dev, int64_t ld_dist,
+                             const int64_t *q_pids_dev, const int64_t *g_pids_dev,
+                             const int64_t *q_camids_dev, const int64_t *g_camids_dev,
+                             int64_t num_q, int64_t num_g, int64_t max_rank,
+                             float *cmc_dev, float *map_dev, float *all_ap_dev,
+                             int64_t *num_valid_dev, uint32_t *status_dev,
+                             void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/*
+ * MARS metric, float64 semantics of evaluate_mars: only the top max_rank of each row is inspected,
+ * junk = pid == -1 or same pid & same camera, trapezoid AP, CMC/mAP are means over ALL queries
+ * (np.mean: pairwise summation for mAP).  Needs 1 <= max_rank <= min(num_g, 8192).
+ *   cmc_dev  out, max_rank doubles     map_dev out, 1 double     all_ap_dev out, num_q doubles (may be NULL)
+ *   status_dev out: AGRL_ST_ZERO_DIVISION | AGRL_ST_LABEL_RANGE
+ */
+AGRL_API int agrl_rank_mars_dev(const float *distmat_dev, int64_t ld_dist,
+                       const int64_t *q_pids_dev, const int64_t *g_pids_dev,
+                       const int64_t *q_camids_dev, const int64_t *g_camids_dev,
+                       int64_t num_q, int64_t num_g, int64_t max_rank,
+                       double *cmc_dev, double *map_dev, double *all_ap_dev,
+                       uint32_t *status_dev,
+                       void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Host-buffer forms (numpy in / numpy out like the reference).  cmc_host must hold max_rank
+ * entries; *rank_len_out receives min(max_rank, num_g) for the market1501 metric. */
+AGRL_API int agrl_rank_market1501_host(const float *distmat_host,
+                              const int64_t *q_pids, const int64_t *g_pids,
+                              const int64_t *q_camids, const int64_t *g_camids,
+                              int64_t num_q, int64_t num_g, int64_t max_rank,
+                              float *cmc_host, float *map_host, float *all_ap_host,
+                              int64_t *rank_len_out, int64_t *num_valid_out);
+AGRL_API int agrl_rank_mars_host(const float *distmat_host,
+                        const int64_t *q_pids, const int64_t *g_pids,
+                        const int64_t *q_camids, const int64_t *g_camids,
+                        int64_t num_q, int64_t num_g, int64_t max_rank,
+                        double *cmc_host, double *map_host, double *all_ap_host);
+
+/* =============================================================================================
+ * (2) Distance matrix -- replaces compute_distance_matrix (torchreid/metrics/distance.py:11-56):
+ *     euclidean_squared_distance :59-73 and cosine_distance :76-89.
+ *     out[i,j] = (|q_i|^2 + |g_j|^2) - 2 q_i.g_j     or     1 - q^_i.g^_j
+ *     The contraction runs on tcgen05 tensor cores with bf16 operand planes (AGRL_SPLIT_*),
+ *     fp32 accumulation in TMEM; norms and the epilogue are fp32.
+ * ============================================================================================= */
+AGRL_API size_t agrl_distance_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int split);
+
+AGRL_API int agrl_distance_dev(const float *q_dev, int64_t ld_q, const float *g_dev, int64_t ld_g,
+                      float *out_dev, int64_t ld_out,
+                      int64_t num_q, int64_t num_g, int64_t dim, int metric, int split,
+                      void *workspace_dev, size_t workspace_bytes, void *stream);
+
+AGRL_API int agrl_distance_host(const float *q_host, const float *g_host, float *out_host,
+                       int64_t num_q, int64_t num_g, int64_t dim, int metric, int split);
+
+/* =============================================================================================
+ * (1) Graph head -- replaces the eval-mode tail of GSTA.forward (torchreid/models/vmgn.py:296-321):
+ *     global pooling + BN neck (:299-301), pyramid part pooling into S*P region nodes (:304-308),
+ *     num_gb x GraphLayer.forward (:142-172, affinity :104-123), temporal attention (:270-278),
+ *     part mean + BN neck + concat (:317-321).  The ResNet-50 backbone (featuremaps, :280-290)
+ *     stays on stock cuDNN in the caller.
+ *
+ *     Canonical geometry only: pyramid strips of num_split = 4 ([4,2,1] -> P = 7 parts,
+ *     utils/reidtools.py:13-15), feature-map height h divisible by 4, C divisible by 64,
+ *     S*P <= 64 nodes per tracklet.  Anything else returns AGRL_E_UNSUPPORTED.
+ * ============================================================================================= */
+#define AGRL_HEAD_MAX_LAYERS 4
+
+typedef struct agrl_head_params {
+    int32_t channels;             /* C = 2048 (vmgn.py:221)                                        */
+    int32_t num_layers;           /* num_gb (vmgn.py:254-260)                                      */
+    int32_t use_pose;             /* GraphLayer.use_pose  (vmgn.py:155)                            */
+    int32_t learn_graph;          /* GraphLayer.learn_graph (vmgn.py:159)                          */
+    float   gamma;                /* 0.1 (vmgn.py:74,172)                                          */
+    float   leaky_slope;          /* 0.1 (vmgn.py:95)                                              */
+    float   bn_eps;               /* 1e-5                                                          */
+    int32_t split;                /* AGRL_SPLIT_BF16X2 (default) or AGRL_SPLIT_BF16X3              */
+    /* device pointers, fp32; BN vectors have C entries, linear weights are (C, C) row-major [out,in] */
+    const float *linear_weight[AGRL_HEAD_MAX_LAYERS];      /* graph_layers.i.linear.weight          */
+    const float *bn_weight[AGRL_HEAD_MAX_LAYERS];          /* graph_layers.i.bn.{weight,bias,...}    */
+    const float *bn_bias[AGRL_HEAD_MAX_LAYERS];
+    const float *bn_mean[AGRL_HEAD_MAX_LAYERS];
+    const float *bn_var[AGRL_HEAD_MAX_LAYERS];
+    const float *global_bn[4];    /* global_bottleneck.{weight,bias,running_mean,running_var}      */
+    const float *att_bn[4];       /* att_bottleneck.{weight,bias,running_mean,running_var}         */
+} agrl_head_params;
+
+/* bytes of the persistent, weight-derived buffer (bf16 planes of W, folded BN scale/shift) */
+AGRL_API size_t agrl_head_prepared_bytes(const agrl_head_params *p);
+/* fills `prepared_dev`; call once per weight load, asynchronous on stream */
+AGRL_API int    agrl_head_prepare_dev(const agrl_head_params *p, void *prepared_dev, size_t prepared_bytes,
+                             void *stream);
+AGRL_API size_t agrl_head_workspace_bytes(const agrl_head_params *p, int64_t batch, int32_t seq_len);
+
+/*
+ *   x4_1_dev, x4_2_dev  (batch*seq_len, C, h, w) fp32 NCHW contiguous (layer4_1 / layer4_2 outputs)
+ *   adj_dev             (batch, V, V) fp32, V = seq_len * 7 (dataset_loader.py:345-388); may be NULL
+ *                       when use_pose == 0
+ *   out_dev             (batch, 2*C) fp32, row stride ld_out: [BN(global mean) | BN(attention feature)]
+ *   nodes_out_dev       optional (batch, V, C) fp32 copy of the node features after the last graph
+ *                       layer (for tests); NULL in production
+ */
+AGRL_API int agrl_head_forward_dev(const agrl_head_params *p, const void *prepared_dev,
+                          const float *x4_1_dev, const float *x4_2_dev, const float *adj_dev,
+                          float *out_dev, int64_t ld_out, float *nodes_out_dev,
+                          int64_t batch, int32_t seq_len, int32_t h, int32_t w,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGRL_B200_H_ */

@@ -187,3 +187,32 @@ if __name__ == '__main__':
         make_distance()
     if 'head' in which:
         make_head()
+
+
+# ------------------------------------------------------------------------------------ full model
+def make_full_model():
+    """Whole reference VMGN (random-init ResNet-50 under seed 0, eval) on one synthetic tracklet,
+    CPU fp32 -- used for the end-to-end check through the stock cuDNN backbone -- and the list of
+    state_dict keys/shapes the drop-in module must reproduce (checkpoint row)."""
+    import json
+    torch.manual_seed(0)
+    model = quiet(ref_vmgn, num_classes=625, loss={'xent', 'htri'}, last_stride=1, num_split=4,
+                  num_gb=2, num_scale=1, pyramid_part=True, use_pose=True, learn_graph=True).eval()
+    sd = model.state_dict()
+    with open(os.path.join(HERE, 'vmgn_state_dict_keys.json'), 'w') as f:
+        json.dump([[k, list(v.shape)] for k, v in sd.items()], f)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 8, 3, 256, 128, generator=g)
+    adj = synth.pose_adjacency(2, 8, 7, seed=77)
+    with torch.no_grad():
+        out = model(x, adj)
+        x4_1, x4_2 = model.featuremaps(x.view(16, 3, 256, 128))
+    np.savez_compressed(os.path.join(HERE, 'full_model.npz'), out=out.numpy(), input_seed=np.int64(77),
+                        model_seed=np.int64(0), x_checksum=np.float64(x.double().sum()),
+                        map_absmax=np.float64(max(x4_1.abs().max(), x4_2.abs().max())),
+                        conv1_checksum=np.float64(sd['conv1.weight'].double().sum()))
+    print('full_model', out.shape, float(out.abs().max()), float(x4_1.abs().max()))
+
+
+if __name__ == '__main__' and ('full' in sys.argv[1:] or not sys.argv[1:]):
+    make_full_model()

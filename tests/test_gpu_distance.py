@@ -1,0 +1,103 @@
+"""GPU parity of the tcgen05 distance matrix (csrc/distance.cu, gemm_sm100.cuh, split.cu) through
+compute_distance_matrix: reference golden vectors, oracle (fp32 and fp64) on larger seeded inputs,
+ragged shapes, argument checks.  Tolerance (north star): 1e-4 relative; the 3-plane split is held
+to fp32-level accuracy (2e-6 of the matrix scale) on top of that."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_files
+from oracle import distance as odist
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4           # the north-star bar
+FP32_TOL = 2e-6          # what the fp32-accurate split actually has to deliver
+
+
+@pytest.fixture(scope='module')
+def cdm():
+    from agrl.pytorch_b200.metrics import compute_distance_matrix
+    return compute_distance_matrix
+
+
+def _err(got, ref):
+    scale = np.abs(ref).max()
+    return np.abs(got - ref).max() / scale, np.linalg.norm(got - ref) / np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize('fname', golden_files('distance_'))
+@pytest.mark.parametrize('metric', ['euclidean', 'cosine'])
+@pytest.mark.parametrize('where', ['cpu', 'cuda'])
+def test_distance_golden(cdm, fname, metric, where):
+    g = np.load(os.path.join(GOLDEN, fname))
+    a, b = torch.from_numpy(g['a']), torch.from_numpy(g['b'])
+    if where == 'cuda':
+        a, b = a.cuda(), b.cuda()
+    out = cdm(a, b, metric)
+    assert out.shape == (a.size(0), b.size(0)) and out.dtype == torch.float32
+    assert out.device.type == where
+    emax, enrm = _err(out.cpu().numpy(), g[metric])
+    assert emax < FP32_TOL and enrm < FP32_TOL, (emax, enrm)
+
+
+@pytest.mark.parametrize('m,n,d', [(300, 1000, 2048), (129, 257, 4096), (1, 1, 1), (7, 130, 63), (128, 128, 64),
+                                   (255, 383, 200), (702, 2636, 4096)])
+@pytest.mark.parametrize('metric', ['euclidean', 'cosine'])
+def test_distance_vs_oracle(cdm, m, n, d, metric):
+    g = torch.Generator().manual_seed(m * 7 + n)
+    a, b = torch.randn(m, d, generator=g), torch.randn(n, d, generator=g)
+    ref32 = odist.distance_matrix(a, b, metric).numpy()
+    ref64 = odist.distance_matrix(a, b, metric, dtype=torch.float64).numpy()
+    out = cdm(a.cuda(), b.cuda(), metric).cpu().numpy()
+    emax, enrm = _err(out, ref32)
+    assert emax < REL_TOL and enrm < REL_TOL
+    # against the exact value we must be about as good as the reference's own fp32 arithmetic
+    e_ours = np.abs(out - ref64).max()
+    e_ref = np.abs(ref32 - ref64).max()
+    assert e_ours <= max(4 * e_ref, FP32_TOL * np.abs(ref64).max()), (e_ours, e_ref)
+
+
+def test_two_plane_split_meets_the_bar(cdm):
+    from agrl.pytorch_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.randn(200, 2048, generator=g), torch.randn(300, 2048, generator=g)
+    for metric in ('euclidean', 'cosine'):
+        ref = odist.distance_matrix(a, b, metric).numpy()
+        out = cdm(a.cuda(), b.cuda(), metric, split=_lib.SPLIT_BF16X2).cpu().numpy()
+        emax, enrm = _err(out, ref)
+        assert emax < REL_TOL and enrm < REL_TOL
+
+
+def test_clustered_small_distances(cdm):
+    """near-duplicate rows: the Gram form cancels; error must stay at fp32 level relative to the norms"""
+    g = torch.Generator().manual_seed(9)
+    base = torch.randn(64, 1024, generator=g)
+    a = base + 1e-3 * torch.randn(64, 1024, generator=g)
+    ref64 = odist.distance_matrix(a, base, 'euclidean', dtype=torch.float64).numpy()
+    ref32 = odist.distance_matrix(a, base, 'euclidean').numpy()
+    out = cdm(a.cuda(), base.cuda(), 'euclidean').cpu().numpy()
+    assert np.abs(out - ref64).max() <= 4 * np.abs(ref32 - ref64).max() + 1e-3
+
+
+def test_non_contiguous_and_strided_inputs(cdm):
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(50, 300, generator=g).cuda()
+    a, b = big[:20, 10:210], big[20:, 10:210]            # row stride 300, offset start
+    ref = odist.distance_matrix(a.cpu(), b.cpu(), 'euclidean').numpy()
+    out = cdm(a, b, 'euclidean').cpu().numpy()
+    assert _err(out, ref)[0] < FP32_TOL
+
+
+def test_argument_checks(cdm):
+    a = torch.zeros(3, 4).cuda()
+    with pytest.raises(AssertionError):
+        cdm(a, torch.zeros(4, 5).cuda())
+    with pytest.raises(AssertionError):
+        cdm(a[0], a)
+    with pytest.raises(AssertionError):
+        cdm(a.cpu().numpy(), a)
+    with pytest.raises(ValueError, match='Unknown distance metric'):
+        cdm(a, a, 'manhattan')
+    assert cdm(a[:0], a).shape == (0, 3)

@@ -1,0 +1,117 @@
+"""GPU parity of the graph head (csrc/head.cu + the tcgen05 GEMM) through the VMGN module mirror:
+reference golden outputs (GSTA.forward lines 296-321 on seeded maps), the oracle on further cases,
+and the whole model through the stock cuDNN backbone.  Bar (north star): 1e-4 relative, judged
+max-scaled and norm-relative on the (B, 4096) output."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_files
+from oracle import head as ohead
+from oracle import synth
+from test_oracle_head import regenerate
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def make_model(wts, use_pose=True, learn_graph=True, split=None, num_gb=2):
+    from agrl.pytorch_b200 import models, _lib
+    kw = {} if split is None else {'head_split': split}
+    m = models.init_model('vmgn', num_classes=8, loss={'xent', 'htri'}, last_stride=1, num_split=4, num_gb=num_gb,
+                          num_scale=1, pyramid_part=True, use_pose=use_pose, learn_graph=learn_graph,
+                          pretrained=False, **kw)
+    sd = m.state_dict()
+    for k, v in wts.items():
+        sd[k].copy_(v)
+    return m.cuda().eval()
+
+
+def rel_err(got, ref):
+    got, ref = got.double(), ref.double()
+    return float((got - ref).abs().max() / ref.abs().max()), float((got - ref).norm() / ref.norm())
+
+
+@pytest.mark.parametrize('fname', golden_files('head_'))
+@pytest.mark.parametrize('split', [2, 3])
+def test_head_golden(fname, split):
+    g = np.load(os.path.join(GOLDEN, fname))
+    x1, x2, adj, wts = regenerate(g)
+    model = make_model(wts, split=split)
+    with torch.no_grad():
+        out = model.head(x1.cuda(), x2.cuda(), adj.cuda(), 8).cpu()
+    ref = torch.from_numpy(g['out'])
+    emax, enrm = rel_err(out, ref)
+    assert out.shape == ref.shape
+    assert emax < TOL and enrm < TOL, (fname, split, emax, enrm)
+
+
+@pytest.mark.parametrize('use_pose,learn_graph', [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize('B,w', [(3, 8), (5, 2)])
+def test_head_vs_oracle(use_pose, learn_graph, B, w):
+    """canonical 16x8 maps (vector pooling path) and narrow maps; all GraphLayer flag combinations"""
+    S = 8
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, w, seed=40 + B, scale=3.0)
+    adj = synth.pose_adjacency(B, S, 7, seed=41 + B)
+    wts = synth.head_weights(2048, 2, seed=42, randomise_bn=True)
+    model = make_model(wts, use_pose, learn_graph)
+    ref, nodes0, nodes_ref = ohead.head_forward(x1, x2, adj, wts, use_pose=use_pose, learn_graph=learn_graph,
+                                                dtype=torch.float64, return_nodes=True)
+    with torch.no_grad():
+        out, nodes = model.head(x1.cuda(), x2.cuda(), adj.cuda() if use_pose else None, S, return_nodes=True)
+    emax, enrm = rel_err(out.cpu(), ref)
+    nmax, nnrm = rel_err(nodes.cpu(), nodes_ref)
+    assert emax < TOL and enrm < TOL, (emax, enrm)
+    assert nmax < TOL and nnrm < TOL, (nmax, nnrm)
+
+
+def test_head_single_layer_and_no_layer():
+    S, B = 8, 2
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=50)
+    adj = synth.pose_adjacency(B, S, 7, seed=51)
+    for num_gb in (0, 1):
+        wts = synth.head_weights(2048, num_gb, seed=52)
+        model = make_model(wts, num_gb=num_gb)
+        ref = ohead.head_forward(x1, x2, adj, wts, num_gb=num_gb, dtype=torch.float64)
+        with torch.no_grad():
+            out = model.head(x1.cuda(), x2.cuda(), adj.cuda(), S)
+        emax, enrm = rel_err(out.cpu(), ref)
+        assert emax < TOL and enrm < TOL, (num_gb, emax, enrm)
+
+
+def test_full_model_through_cudnn_backbone():
+    """random-init ResNet-50 (seed 0) + head on one synthetic tracklet batch vs the reference on CPU.
+    cuDNN and MKL-DNN convolutions differ in rounding, so the bar here is 1e-3 (stage-wise parity is
+    what the 1e-4 bar applies to)."""
+    from agrl.pytorch_b200 import models
+    g = np.load(os.path.join(GOLDEN, 'full_model.npz'))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(int(g['model_seed']))
+    model = models.init_model('vmgn', num_classes=625, loss={'xent', 'htri'}, last_stride=1, num_split=4,
+                              num_gb=2, num_scale=1, pyramid_part=True, use_pose=True, learn_graph=True,
+                              pretrained=False)
+    assert float(model.state_dict()['conv1.weight'].double().sum()) == float(g['conv1_checksum'])
+    gen = torch.Generator().manual_seed(int(g['input_seed']))
+    x = torch.randn(2, 8, 3, 256, 128, generator=gen)
+    assert float(x.double().sum()) == float(g['x_checksum'])
+    adj = synth.pose_adjacency(2, 8, 7, seed=int(g['input_seed']))
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model(x.cuda(), adj.cuda()).cpu()
+    emax, enrm = rel_err(out, torch.from_numpy(g['out']))
+    assert out.shape == (2, 4096)
+    assert emax < 1e-3 and enrm < 1e-3, (emax, enrm)
+
+
+def test_training_mode_and_cpu_inputs_fail_loudly():
+    wts = synth.head_weights(2048, 2, seed=1)
+    model = make_model(wts)
+    x = torch.zeros(1, 8, 3, 32, 16)
+    adj = torch.zeros(1, 56, 56)
+    with pytest.raises(NotImplementedError):
+        model.train()(x.cuda(), adj.cuda())
+    with pytest.raises(RuntimeError):
+        model.eval().cpu()(x, adj)
