@@ -40,11 +40,17 @@ _SIGNATURES = {
     'agrl_last_cuda_error': (ctypes.c_char_p, []),
     'agrl_device_ok': (c_int, []),
     'agrl_launch_count': (ctypes.c_uint64, []),
+    'agrl_profile_begin': (c_int, [c_vp]),
+    'agrl_profile_end': (c_int, [ctypes.c_char_p, c_sz]),
     'agrl_rank_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64]),
     'agrl_rank_market1501_dev': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'agrl_rank_mars_dev': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'agrl_rank_mars_partial_dev': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64,
+                                           c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'agrl_rank_mars_merge_dev': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                         c_vp, c_sz, c_vp]),
     'agrl_rank_market1501_host': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                           c_vp, c_vp, c_vp, c_vp, c_vp]),
     'agrl_rank_mars_host': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
@@ -121,3 +127,30 @@ def require_device():
 
 def launch_count():
     return int(load().agrl_launch_count())
+
+
+class profile(object):
+    """Context manager around agrl_profile_begin/_end: ``with profile(stream) as p: ...`` then
+    ``p.kernels`` is a list of (kernel name, milliseconds) in launch order."""
+
+    def __init__(self, stream=None):
+        self.stream, self.kernels = stream, []
+
+    def __enter__(self):
+        check(load().agrl_profile_begin(self.stream))
+        return self
+
+    def __exit__(self, *exc):
+        buf = ctypes.create_string_buffer(1 << 20)
+        rc = load().agrl_profile_end(buf, len(buf))
+        if exc[0] is None:
+            check(rc)
+        self.kernels = [(k, float(v)) for k, v in (item.split(':') for item in buf.value.decode().split(';') if item)]
+        return False
+
+    def totals(self):
+        out = {}
+        for k, ms in self.kernels:
+            n, t = out.get(k, (0, 0.0))
+            out[k] = (n + 1, t + ms)
+        return out

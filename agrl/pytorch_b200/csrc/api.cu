@@ -14,7 +14,29 @@ void set_cuda_error(cudaError_t e, const char *what, const char *file, int line)
              cudaGetErrorString(e));
     (void)cudaGetLastError();          // clear the sticky-less error so later calls start clean
 }
-void count_launch(int n) { tl_launches += static_cast<uint64_t>(n); }
+// Optional per-thread kernel timeline: one CUDA event after every launch, on the launching stream.
+struct Profiler {
+    static constexpr int kMax = 4096;
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[kMax + 1];
+    const char *name[kMax + 1];
+};
+static thread_local Profiler tl_prof;
+
+void after_launch(cudaStream_t st, const char *name) {
+    ++tl_launches;
+    Profiler &p = tl_prof;
+    if (p.on && p.n < Profiler::kMax) {
+        ++p.n;
+        if (cudaEventCreate(&p.ev[p.n]) != cudaSuccess || cudaEventRecord(p.ev[p.n], st) != cudaSuccess) {
+            (void)cudaGetLastError();
+            --p.n;
+            return;
+        }
+        p.name[p.n] = name;
+    }
+}
 
 // per-thread stream + stream-ordered scratch for the *_host entry points
 struct HostCtx {
@@ -219,4 +241,37 @@ extern "C" int agrl_distance_host(const float *q_host, const float *g_host, floa
     AGRL_CUDA_TRY(cudaMemcpyAsync(out_host, d_out, sizeof(float) * num_q * num_g, cudaMemcpyDeviceToHost, st));
     AGRL_CUDA_TRY(cudaStreamSynchronize(st));
     return AGRL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel timeline (bench.py's roofline numbers come from here: CUDA events on the launching stream)
+// ------------------------------------------------------------------------------------------------
+extern "C" int agrl_profile_begin(void *stream) {
+    Profiler &p = tl_prof;
+    if (p.on) return AGRL_E_INVALID;
+    p.n = 0;
+    AGRL_CUDA_TRY(cudaEventCreate(&p.ev[0]));
+    AGRL_CUDA_TRY(cudaEventRecord(p.ev[0], static_cast<cudaStream_t>(stream)));
+    p.name[0] = "begin";
+    p.on = true;
+    return AGRL_OK;
+}
+
+extern "C" int agrl_profile_end(char *text, size_t cap) {
+    Profiler &p = tl_prof;
+    if (!p.on) return AGRL_E_INVALID;
+    p.on = false;
+    size_t off = 0;
+    if (text && cap) text[0] = 0;
+    int rc = AGRL_OK;
+    if (p.n > 0 && cudaEventSynchronize(p.ev[p.n]) != cudaSuccess) rc = AGRL_E_CUDA;
+    for (int i = 1; i <= p.n && rc == AGRL_OK; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.ev[i - 1], p.ev[i]) != cudaSuccess) { rc = AGRL_E_CUDA; break; }
+        if (text && off + 64 < cap) off += snprintf(text + off, cap - off, "%s:%.6f;", p.name[i], ms);
+    }
+    for (int i = 0; i <= p.n; ++i) cudaEventDestroy(p.ev[i]);
+    p.n = 0;
+    if (rc != AGRL_OK) (void)cudaGetLastError();
+    return rc;
 }

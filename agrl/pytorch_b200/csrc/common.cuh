@@ -14,7 +14,7 @@ namespace agrl {
 
 // ---- host-side error plumbing --------------------------------------------------------------
 void        set_cuda_error(cudaError_t e, const char *what, const char *file, int line);
-void        count_launch(int n = 1);
+void        after_launch(cudaStream_t st, const char *name);   // counts; records a profiling event when enabled
 
 #define AGRL_CUDA_TRY(expr)                                                            \
     do {                                                                               \
@@ -26,10 +26,10 @@ void        count_launch(int n = 1);
     } while (0)
 
 // check the launch that just happened (configuration errors surface here without a sync)
-#define AGRL_LAUNCH_CHECK()                                                            \
+#define AGRL_LAUNCH_CHECK(stream, name)                                                \
     do {                                                                               \
-        ::agrl::count_launch();                                                        \
         AGRL_CUDA_TRY(cudaGetLastError());                                             \
+        ::agrl::after_launch(stream, name);                                            \
     } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -14,7 +14,7 @@
 //               ring of shared-memory stages, completion on mbarriers
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (cta_group::1, 128 x 128 x 16, kind::f16),
 //               tcgen05.commit frees the smem stage / publishes the accumulator
-//   warp 2      TMEM allocator (2 accumulator stages x 128 columns)
+//   warp 2      TMEM allocator (2 stages x [main | correction] x 128 columns = all 512 columns)
 //   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns), transpose through padded smem so that
 //               global stores are full 128 B lines, fused element-wise epilogue functor
 // The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -33,7 +33,8 @@ constexpr int kPlaneTileBytes = BM * BK * 2;         // 16 KiB: one plane of an 
 constexpr int kThreads = 256;
 constexpr int kEpiWarps = 4;
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * BN;           // 256 columns (power of two >= 32)
+constexpr int kAccCols = 2 * BN;                     // per stage: [main a0.b0 | correction products]
+constexpr int kTmemCols = kAccStages * kAccCols;     // 512 columns: all of TMEM
 constexpr int kEpiPad = 33;
 constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPad * 4;
 static_assert(BM == BN, "A and B tiles share one TMA box shape");
@@ -145,6 +146,7 @@ constexpr uint32_t make_idesc(int m, int n) {
 
 // ---- epilogue functors: value for output element (row, col) given the accumulator -------------
 struct EpiDistance {            // distance.py:59-73 / :76-89
+    static constexpr const char *kName = "gemm_distance";
     const float *qn, *gn;       // squared norms (euclidean); unused for cosine
     float *out;
     int64_t ld;
@@ -162,6 +164,7 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
 };
 
 struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) + (1-gamma) * x
+    static constexpr const char *kName = "gemm_graph_layer";
     const float *x;             // layer input (M, ldx)
     const float *scale, *shift; // folded eval-mode BatchNorm1d per output channel
     float *out;
@@ -252,7 +255,12 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);        // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
+            // Two accumulators per stage.  The tensor core truncates (round-toward-zero) on every
+            // accumulate, at the ulp of the running sum; keeping the small correction products out of
+            // the big a0.b0 sum spares it 5/6 (P=3) of those truncations, and the correction sum itself
+            // is ~2^-8 smaller, so its own truncation is negligible.
+            const uint32_t d_main = tmem_base + acc * kAccCols;
+            const uint32_t d_corr = d_main + BN;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(bar_full + 8 * stage, phase);            // TMA bytes have landed
                 tc_fence_after();
@@ -268,7 +276,10 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
-                            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
+                            if (i == Cfg::kNumPairs - 1)
+                                tc_mma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            else
+                                tc_mma_bf16(d_corr, da + 2 * k, db + 2 * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
                         }
                     }
                     tc_commit(bar_empty + 8 * stage);               // frees the smem stage when the MMAs retire
@@ -292,11 +303,14 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int row_base = m0 + ew * 32;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
+                uint32_t r[32], rc[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kAccCols + c * 32;
+                tmem_ld_32x32(taddr, r);
+                tmem_ld_32x32(taddr + BN, rc);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) buf[lane * kEpiPad + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j)
+                    buf[lane * kEpiPad + j] = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]));
                 __syncwarp();
                 const int col = n0 + c * 32 + lane;
                 if (col < N) {
@@ -332,7 +346,7 @@ int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M,
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;
 }
 

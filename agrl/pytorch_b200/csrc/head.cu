@@ -404,7 +404,7 @@ static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
     const size_t smem = (static_cast<size_t>(4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
     AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     graph_kernel<NT><<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "graph");
     return AGRL_OK;
 }
 
@@ -442,7 +442,7 @@ extern "C" int agrl_head_prepare_dev(const agrl_head_params *p, void *prepared, 
     }
     for (int l = 0; l < nvec; ++l) { fa.scale[l] = pr.scale[l]; fa.shift[l] = pr.shift[l]; }
     fold_bn_kernel<<<dim3((C + 255) / 256, nvec), 256, 0, st>>>(fa);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "fold_bn");
     return AGRL_OK;
 }
 
@@ -478,7 +478,7 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     const bool vec = (hw == 128) && ((reinterpret_cast<uintptr_t>(x4_1) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(x4_2) & 15u) == 0);
     if (vec) pool_kernel<true><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
     else pool_kernel<false><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "pool");
 
     // 2. graph layers
     const int64_t rows = batch * V;
@@ -504,6 +504,6 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     // 3. attention + neck
     AttnArgs aa{hwk.x[cur], out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C};
     attn_kernel<<<static_cast<unsigned>(batch), kHeadThreads, 0, st>>>(aa);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "attn");
     return AGRL_OK;
 }

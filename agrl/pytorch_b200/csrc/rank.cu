@@ -22,6 +22,7 @@
 #include "common.cuh"
 
 #include <limits.h>
+#include <string.h>
 
 namespace agrl {
 
@@ -408,49 +409,42 @@ struct MarsArgs {
     double        *ap;                              // [num_q]
     int32_t       *first_pos;                       // [num_q] junk-compacted position of the first good hit
     uint32_t      *status;
+    // gallery-sharded form (rank_mars_partial_kernel): this shard's candidates instead of the AP
+    uint64_t      *part_keys;                       // [num_q][max_rank] keys with GLOBAL gallery index
+    uint8_t       *part_cls;                        // [num_q][max_rank] bit0 good, bit1 junk
+    int32_t       *part_ngood;                      // [num_q] good images in this shard
+    uint32_t       index_offset;                    // global index of this shard's first gallery row
 };
 
 constexpr int kMarsTile = 1024;                     // elements examined between buffer checks
 
-__global__ void __launch_bounds__(kRankThreads)
-rank_mars_kernel(MarsArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);                 // buf_len keys
-    uint8_t  *cls = reinterpret_cast<uint8_t *>(smem_raw + a.buf_len * 8);  // max_rank class bytes
-    __shared__ int s_cnt, s_ngood;
-    __shared__ unsigned long long s_thr;
-
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const int ng = a.num_g, K = a.max_rank, L = a.buf_len;
-    const int pid = a.q_pid[q], cam = a.q_cam[q];
-    const float *row = a.dist + static_cast<size_t>(q) * a.ld;
-
-    if (tid == 0) { s_cnt = 0; s_ngood = 0; s_thr = kKeyMax; }
-    __syncthreads();
-
-    // number of good images: same pid, other camera (rank.py:166)
-    {
-        int good = 0;
-        const int nvec = ng >> 2;
-        const int4 *p4 = reinterpret_cast<const int4 *>(a.g_pid);
-        for (int v = tid; v < nvec; v += kRankThreads) {
-            const int4 p = __ldg(p4 + v);
-            if (p.x == pid) good += (a.g_cam[4 * v] != cam);
-            if (p.y == pid) good += (a.g_cam[4 * v + 1] != cam);
-            if (p.z == pid) good += (a.g_cam[4 * v + 2] != cam);
-            if (p.w == pid) good += (a.g_cam[4 * v + 3] != cam);
-        }
-        const int j = (nvec << 2) + tid;
-        if (j < ng && a.g_pid[j] == pid) good += (a.g_cam[j] != cam);
-        good = warp_sum(good);
-        if ((tid & 31) == 0 && good) atomicAdd(&s_ngood, good);
+// number of good images for the query: same pid, other camera (rank.py:166); result in *s_ngood
+__device__ __forceinline__ void mars_count_good(const MarsArgs &a, int pid, int cam, int tid, int *s_ngood) {
+    const int ng = a.num_g;
+    int good = 0;
+    const int nvec = ng >> 2;
+    const int4 *p4 = reinterpret_cast<const int4 *>(a.g_pid);
+    for (int v = tid; v < nvec; v += kRankThreads) {
+        const int4 p = __ldg(p4 + v);
+        if (p.x == pid) good += (a.g_cam[4 * v] != cam);
+        if (p.y == pid) good += (a.g_cam[4 * v + 1] != cam);
+        if (p.z == pid) good += (a.g_cam[4 * v + 2] != cam);
+        if (p.w == pid) good += (a.g_cam[4 * v + 3] != cam);
     }
+    const int j = (nvec << 2) + tid;
+    if (j < ng && a.g_pid[j] == pid) good += (a.g_cam[j] != cam);
+    good = warp_sum(good);
+    if ((tid & 31) == 0 && good) atomicAdd(s_ngood, good);
+}
 
-    // running top-K: keep candidates below the threshold, compact when the buffer may overflow
+// Running top-K of one row: candidates below the threshold (K-th smallest key so far) go to a
+// shared buffer, which is sorted and cut back to K whenever the next tile could overflow it.
+// On return buf[0..valid) holds the min(K, n) smallest keys in order; returns valid.
+__device__ __forceinline__ int mars_select_topk(const float *__restrict__ row, int ng, int K, int L,
+                                                uint64_t *buf, int *s_cnt, unsigned long long *s_thr, int tid) {
     for (int base = 0; base < ng; base += kMarsTile) {
-        const uint64_t thr = s_thr;
-        const int j = base + tid * 4;
-        // the tile is [base, base+1024): thread t owns 4 consecutive elements
+        const uint64_t thr = *s_thr;
+        const int j = base + tid * 4;               // thread t owns 4 consecutive elements of the tile
         float d[4];
         int n_here = 0;
         if (j + 3 < ng && ((reinterpret_cast<uintptr_t>(row + j) & 15u) == 0)) {
@@ -461,10 +455,10 @@ rank_mars_kernel(MarsArgs a) {
         }
         for (int k = 0; k < n_here; ++k) {
             const uint64_t key = rank_key(d[k], static_cast<uint32_t>(j + k));
-            if (key < thr) buf[atomicAdd(&s_cnt, 1)] = key;       // s_cnt <= L - tile before the tile
+            if (key < thr) buf[atomicAdd(s_cnt, 1)] = key;        // *s_cnt <= L - tile before the tile
         }
         __syncthreads();
-        const int cnt = s_cnt;
+        const int cnt = *s_cnt;
         __syncthreads();                   // everyone holds the same cnt before anyone appends again
         const bool last = (base + kMarsTile >= ng);
         if (cnt > L - kMarsTile || last) {
@@ -473,31 +467,23 @@ rank_mars_kernel(MarsArgs a) {
             bitonic_sort_u64<false>(buf, L, tid, kRankThreads);
             if (tid == 0) {
                 const int keep = cnt < K ? cnt : K;
-                s_cnt = keep;
-                if (keep == K) s_thr = buf[K - 1];     // later keys must beat the current K-th
+                *s_cnt = keep;
+                if (keep == K) *s_thr = buf[K - 1];    // later keys must beat the current K-th
             }
             __syncthreads();
         }
     }
-    // buf[0..K) = the K smallest keys in order (num_g >= K is checked by the host)
+    return *s_cnt;
+}
 
-    // classify the K ranked items: bit0 good, bit1 junk (rank.py:166-169)
-    for (int n = tid; n < K; n += kRankThreads) {
-        const uint32_t g = static_cast<uint32_t>(buf[n]);
-        const int gp = a.g_pid[g], gc = a.g_cam[g];
-        const bool good = (gp == pid) && (gc != cam);
-        const bool junk = (gp == -1) || ((gp == pid) && (gc == cam));
-        cls[n] = static_cast<uint8_t>((good ? 1 : 0) | (junk ? 2 : 0));
-    }
-    __syncthreads();
-    if (tid != 0) return;
-
-    // Compute_AP (rank.py:180-212) in Python-float (double) arithmetic, one rounding per operation
-    const int ngood = s_ngood;
+// Compute_AP (rank.py:180-212) in Python-float (double) arithmetic, one rounding per operation.
+// cls[n]: bit0 good, bit1 junk for the n-th ranked gallery item; n_ranked of them.
+__device__ __forceinline__ void mars_compute_ap(const uint8_t *cls, int n_ranked, int ngood,
+                                                double *ap_out, int *first_pos_out, uint32_t *status) {
     double old_recall = 0.0, old_precision = 1.0, ap = 0.0;
     int inter = 0, j_eff = 0, good_now = 0, njunk = 0, first_pos = INT_MAX;
     bool zero_div = false;
-    for (int n = 0; n < K; ++n) {
+    for (int n = 0; n < n_ranked; ++n) {
         const int c = cls[n];
         if (c & 1) {
             if (first_pos == INT_MAX) first_pos = n - njunk;         // cmc[n - njunk:] = 1
@@ -519,35 +505,161 @@ rank_mars_kernel(MarsArgs a) {
         ++j_eff;
         if (good_now == ngood) break;
     }
-    if (zero_div) atomicOr(a.status, AGRL_ST_ZERO_DIVISION);
-    a.ap[q] = ap;
-    a.first_pos[q] = first_pos;
+    if (zero_div) atomicOr(status, AGRL_ST_ZERO_DIVISION);
+    *ap_out = ap;
+    *first_pos_out = first_pos;
 }
 
-// numpy's pairwise float64 summation (what np.mean runs on the ap vector, rank.py:176)
-__device__ double pairwise_sum_f64(const double *x, int n) {
+// kPartial = false: whole gallery on this GPU -> AP and first hit per query.
+// kPartial = true : gallery shard -> this shard's top-K candidates (global indices), their classes,
+//                   and the shard's good count, for rank_mars_merge_kernel.
+template <bool kPartial>
+__global__ void __launch_bounds__(kRankThreads)
+rank_mars_kernel(MarsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);                 // buf_len keys
+    uint8_t  *cls = reinterpret_cast<uint8_t *>(smem_raw + a.buf_len * 8);  // max_rank class bytes
+    __shared__ int s_cnt, s_ngood;
+    __shared__ unsigned long long s_thr;
+
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int K = a.max_rank;
+    const int pid = a.q_pid[q], cam = a.q_cam[q];
+    const float *row = a.dist + static_cast<size_t>(q) * a.ld;
+
+    if (tid == 0) { s_cnt = 0; s_ngood = 0; s_thr = kKeyMax; }
+    __syncthreads();
+    mars_count_good(a, pid, cam, tid, &s_ngood);
+    const int valid = mars_select_topk(row, a.num_g, K, a.buf_len, buf, &s_cnt, &s_thr, tid);
+
+    // classify the ranked items: bit0 good, bit1 junk (rank.py:166-169)
+    for (int n = tid; n < K; n += kRankThreads) {
+        uint8_t c = 0;
+        if (n < valid) {
+            const uint32_t g = static_cast<uint32_t>(buf[n]);
+            const int gp = a.g_pid[g], gc = a.g_cam[g];
+            const bool good = (gp == pid) && (gc != cam);
+            const bool junk = (gp == -1) || ((gp == pid) && (gc == cam));
+            c = static_cast<uint8_t>((good ? 1 : 0) | (junk ? 2 : 0));
+        }
+        if (kPartial) {
+            a.part_keys[static_cast<size_t>(q) * K + n] = (n < valid) ? buf[n] + a.index_offset : kKeyMax;
+            a.part_cls[static_cast<size_t>(q) * K + n] = c;
+        } else {
+            cls[n] = c;
+        }
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    if (kPartial) { a.part_ngood[q] = s_ngood; return; }
+    mars_compute_ap(cls, valid, s_ngood, &a.ap[q], &a.first_pos[q], a.status);
+}
+
+// Merge of the shards' candidates: one CTA per query sorts parts*K (key, class) pairs and runs
+// Compute_AP on the first K.  keys/cls are laid out [part][query][K].
+struct MarsMergeArgs {
+    const uint64_t *keys;
+    const uint8_t  *cls;
+    const int32_t  *ngood;              // [num_q], already summed over the shards
+    int             parts, num_q, max_rank, n2;      // n2 = power of two >= parts * max_rank
+    double         *ap;
+    int32_t        *first_pos;
+    uint32_t       *status;
+};
+
+__global__ void __launch_bounds__(kRankThreads)
+rank_mars_merge_kernel(MarsMergeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
+    uint8_t  *cls = reinterpret_cast<uint8_t *>(smem_raw + static_cast<size_t>(a.n2) * 8);
+    const int q = blockIdx.x, tid = threadIdx.x, K = a.max_rank;
+    const int total = a.parts * K;
+    for (int i = tid; i < a.n2; i += kRankThreads) {
+        if (i < total) {
+            const size_t src = (static_cast<size_t>(i / K) * a.num_q + q) * K + (i % K);
+            keys[i] = a.keys[src];
+            cls[i] = a.cls[src];
+        } else { keys[i] = kKeyMax; cls[i] = 0; }
+    }
+    __syncthreads();
+    // bitonic sort of the keys carrying the class byte
+    for (int k = 2; k <= a.n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (a.n2 >> 1); t += kRankThreads) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const uint64_t x = keys[lo], y = keys[hi];
+                if ((x > y) == ((lo & k) == 0)) {
+                    keys[lo] = y; keys[hi] = x;
+                    const uint8_t c = cls[lo]; cls[lo] = cls[hi]; cls[hi] = c;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid != 0) return;
+    int valid = 0;
+    while (valid < K && keys[valid] != kKeyMax) ++valid;
+    mars_compute_ap(cls, valid, a.ngood[q], &a.ap[q], &a.first_pos[q], a.status);
+}
+
+// numpy's pairwise float64 summation (what np.mean runs on the ap vector, rank.py:176):
+// blocks of <= 128 elements are summed with eight interleaved partial sums and a fixed tree, larger
+// ranges split at n/2 rounded down to a multiple of 8.  Evaluated post-order with an explicit stack
+// (device recursion would overflow the default 1 KiB thread stack).
+__device__ double pairwise_leaf_f64(const double *x, int n) {
     if (n < 8) {
         double r = 0.0;
         for (int i = 0; i < n; ++i) r = __dadd_rn(r, x[i]);
         return r;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = x[k];
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int k = 0; k < 8; ++k) r[k] = x[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], x[i + k]);
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, x[i]);
-        return res;
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], x[i + k]);
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(pairwise_sum_f64(x, n2), pairwise_sum_f64(x + n2, n - n2));
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, x[i]);
+    return res;
+}
+
+__device__ double pairwise_sum_f64(const double *x, int n) {
+    constexpr int kDepth = 40;
+    int off[kDepth], len[kDepth], state[kDepth];     // state: 0 fresh, 1 waiting for left, 2 waiting for right
+    double left[kDepth];
+    int sp = 0;
+    off[0] = 0; len[0] = n; state[0] = 0; sp = 1;
+    double ret = 0.0;
+    bool have_ret = false;
+    while (sp > 0) {
+        const int t = sp - 1;
+        if (have_ret) {                               // a child of frame t just returned
+            have_ret = false;
+            if (state[t] == 1) {                      // left done -> descend right
+                left[t] = ret;
+                state[t] = 2;
+                int n2 = len[t] / 2; n2 -= n2 % 8;
+                off[sp] = off[t] + n2; len[sp] = len[t] - n2; state[sp] = 0; ++sp;
+            } else {                                  // right done -> combine and return
+                ret = __dadd_rn(left[t], ret);
+                have_ret = true;
+                --sp;
+            }
+        } else if (len[t] <= 128) {
+            ret = pairwise_leaf_f64(x + off[t], len[t]);
+            have_ret = true;
+            --sp;
+        } else {                                      // descend left
+            state[t] = 1;
+            int n2 = len[t] / 2; n2 -= n2 % 8;
+            off[sp] = off[t]; len[sp] = n2; state[sp] = 0; ++sp;
+        }
+    }
+    return ret;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -621,7 +733,7 @@ static int narrow_labels(const RankWorkspace &w, const int64_t *qp, const int64_
     if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
     if (blocks < 1) blocks = 1;
     narrow_labels_kernel<<<dim3(blocks, 4), 256, 0, st>>>(la, status);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "narrow_labels");
     return AGRL_OK;
 }
 
@@ -681,11 +793,11 @@ extern "C" int agrl_rank_market1501_dev(const float *distmat, int64_t ld,
     AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_market_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     rank_market_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "rank_market");
     rank_market_overflow_kernel<<<kOverflowCtas, kRankThreads, 0, st>>>(a, w.slab_keys, w.slab_terms);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "rank_market_overflow");
     rank_market_finish_kernel<<<1, 1024, 0, st>>>(a, w.hist, cmc, map, num_valid, status);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "rank_market_finish");
     return AGRL_OK;
 }
 
@@ -718,13 +830,83 @@ extern "C" int agrl_rank_mars_dev(const float *distmat, int64_t ld,
     a.ap = all_ap ? all_ap : w.ap_f64;
     a.first_pos = w.first;
     a.status = status;
+    a.part_keys = nullptr; a.part_cls = nullptr; a.part_ngood = nullptr; a.index_offset = 0;
 
     const size_t smem = static_cast<size_t>(L) * 8 + align_up(static_cast<size_t>(max_rank), 16);
-    AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    rank_mars_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
-    AGRL_LAUNCH_CHECK();
+    rank_mars_kernel<false><<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
+    AGRL_LAUNCH_CHECK(st, "rank_mars");
     rank_mars_finish_kernel<<<1, 1024, 0, st>>>(a, w.hist, cmc, map);
-    AGRL_LAUNCH_CHECK();
+    AGRL_LAUNCH_CHECK(st, "rank_mars_finish");
+    return AGRL_OK;
+}
+
+// ---- gallery-sharded MARS metric --------------------------------------------
+extern "C" int agrl_rank_mars_partial_dev(const float *distmat, int64_t ld,
+                                          const int64_t *q_pids, const int64_t *g_pids,
+                                          const int64_t *q_camids, const int64_t *g_camids,
+                                          int64_t num_q, int64_t num_g, int64_t max_rank, int64_t index_offset,
+                                          uint64_t *keys, uint8_t *cls, int32_t *ngood, uint32_t *status,
+                                          void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_rank_args(distmat, q_pids, g_pids, q_camids, g_camids, num_q, num_g, max_rank, ld);
+    if (rc) return rc;
+    if (!keys || !cls || !ngood || !status || num_q < 1 || index_offset < 0) return AGRL_E_INVALID;
+    if (max_rank > 8192 || index_offset + num_g > 0xFFFFFFFFll) return AGRL_E_UNSUPPORTED;
+    if ((rc = agrl_device_ok())) return rc;
+    RankWorkspace w = carve_rank(ws, num_q, num_g, max_rank);
+    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AGRL_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(uint32_t), st));
+    if ((rc = narrow_labels(w, q_pids, g_pids, q_camids, g_camids, num_q, num_g, status, st))) return rc;
+    MarsArgs a;
+    a.dist = distmat; a.ld = ld;
+    a.q_pid = w.q_pid; a.q_cam = w.q_cam; a.g_pid = w.g_pid; a.g_cam = w.g_cam;
+    a.num_q = static_cast<int>(num_q); a.num_g = static_cast<int>(num_g); a.max_rank = static_cast<int>(max_rank);
+    int L = 2 * kMarsTile;
+    while (L < 2 * max_rank) L <<= 1;
+    a.buf_len = L;
+    a.ap = nullptr; a.first_pos = nullptr; a.status = status;
+    a.part_keys = keys; a.part_cls = cls; a.part_ngood = ngood;
+    a.index_offset = static_cast<uint32_t>(index_offset);
+    const size_t smem = static_cast<size_t>(L) * 8 + align_up(static_cast<size_t>(max_rank), 16);
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    rank_mars_kernel<true><<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
+    AGRL_LAUNCH_CHECK(st, "rank_mars_partial");
+    return AGRL_OK;
+}
+
+extern "C" int agrl_rank_mars_merge_dev(const uint64_t *keys, const uint8_t *cls, const int32_t *ngood,
+                                        int64_t parts, int64_t num_q, int64_t max_rank,
+                                        double *cmc, double *map, double *all_ap, uint32_t *status,
+                                        void *ws, size_t ws_bytes, void *stream) {
+    if (!keys || !cls || !ngood || !cmc || !map || !status) return AGRL_E_INVALID;
+    if (parts < 1 || num_q < 1 || max_rank < 1) return AGRL_E_INVALID;
+    if (parts * max_rank > 16384 || num_q > INT32_MAX / 2) return AGRL_E_UNSUPPORTED;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    RankWorkspace w = carve_rank(ws, num_q, 0, max_rank);
+    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MarsMergeArgs m;
+    m.keys = keys; m.cls = cls; m.ngood = ngood;
+    m.parts = static_cast<int>(parts); m.num_q = static_cast<int>(num_q); m.max_rank = static_cast<int>(max_rank);
+    int n2 = 2;
+    while (n2 < parts * max_rank) n2 <<= 1;
+    m.n2 = n2;
+    m.ap = all_ap ? all_ap : w.ap_f64;
+    m.first_pos = w.first;
+    m.status = status;
+    const size_t smem = static_cast<size_t>(n2) * 9;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    rank_mars_merge_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(m);
+    AGRL_LAUNCH_CHECK(st, "rank_mars_merge");
+    MarsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.num_q = m.num_q; a.max_rank = m.max_rank; a.ap = m.ap; a.first_pos = m.first_pos; a.status = status;
+    rank_mars_finish_kernel<<<1, 1024, 0, st>>>(a, w.hist, cmc, map);
+    AGRL_LAUNCH_CHECK(st, "rank_mars_finish");
     return AGRL_OK;
 }

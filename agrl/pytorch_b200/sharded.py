@@ -1,0 +1,137 @@
+"""Gallery-sharded evaluation over the GPUs of one box.
+
+The only part of AGRL's test-time path that needs communication: each rank owns a slice of the
+gallery (its rows of the feature matrix are already there when the head ran sharded), computes its
+block of the distance matrix and, per query, its best ``max_rank`` candidates + good-image count with
+the kernels of libagrl_b200; one NCCL all-gather of the (key, class) lists and one all-reduce of the
+counts later, every rank merges them into exactly the CMC/mAP the unsharded evaluator would return.
+Messages are tiny (num_q x max_rank x 9 B per rank), so the merge is latency-bound and the flat
+one-shot collectives of NVSwitch are the right shape.  The graph head needs no collective at all.
+
+    cmc, mAP = evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids_local)
+
+``ops`` lets the tests drive the same plumbing with CPU stand-ins under gloo; the product default is
+the CUDA implementation and there is no fallback.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_bounds(n, world):
+    """Contiguous, near-equal row ranges [(lo, hi)] of a length-n gallery for `world` ranks."""
+    base, extra = divmod(n, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class CudaOps(object):
+    """Per-rank compute on the rank's current CUDA device (libagrl_b200)."""
+
+    def __init__(self, split=_lib.SPLIT_BF16X3):
+        self.lib = _lib.require_device()
+        self.split = split
+        self._ws = None
+
+    def _workspace(self, dev, nbytes):
+        if self._ws is None or self._ws.device != dev or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def distance(self, qf, gf, metric):
+        from .metrics import compute_distance_matrix
+        return compute_distance_matrix(qf, gf, metric, split=self.split)
+
+    def partial(self, d, q_pids, g_pids, q_camids, g_camids, max_rank, offset):
+        dev = d.device
+        nq, ng = d.shape
+        keys = torch.empty(nq, max_rank, dtype=torch.int64, device=dev)
+        cls = torch.empty(nq, max_rank, dtype=torch.uint8, device=dev)
+        ngood = torch.empty(nq, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        wsb = self.lib.agrl_rank_workspace_bytes(nq, ng, max_rank)
+        ws = self._workspace(dev, wsb)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.agrl_rank_mars_partial_dev(
+                d.data_ptr(), d.stride(0), q_pids.data_ptr(), g_pids.data_ptr(), q_camids.data_ptr(),
+                g_camids.data_ptr(), nq, ng, max_rank, offset, keys.data_ptr(), cls.data_ptr(), ngood.data_ptr(),
+                status.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream))
+        return keys, cls, ngood, status
+
+    def merge(self, keys_all, cls_all, ngood, max_rank, status_parts):
+        dev = keys_all.device
+        parts, nq = keys_all.shape[0], keys_all.shape[1]
+        out = torch.zeros(max_rank + 2, dtype=torch.float64, device=dev)      # [cmc.., mAP, status]
+        wsb = self.lib.agrl_rank_workspace_bytes(nq, 0, max_rank)
+        ws = self._workspace(dev, wsb)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.agrl_rank_mars_merge_dev(
+                keys_all.data_ptr(), cls_all.data_ptr(), ngood.data_ptr(), parts, nq, max_rank,
+                out.data_ptr(), out.data_ptr() + 8 * max_rank, None, out.data_ptr() + 8 * (max_rank + 1),
+                ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream))
+            host = out.cpu()
+            st_parts = int(status_parts.cpu())
+        status = int(host.view(torch.int32)[2 * (max_rank + 1)]) | st_parts
+        from .metrics.rank import _raise_status
+        _raise_status(status)
+        return host[:max_rank].numpy().copy(), np.float64(host[max_rank])
+
+
+def _as_dev_i64(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.int64)).to(dev)
+
+
+def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids_local, metric='euclidean',
+                          max_rank=50, group=None, broadcast_queries=True, ops=None):
+    """MARS-metric CMC/mAP (rank.py:160-212) of ``qf`` against the union of every rank's gallery shard.
+
+    qf (num_q, d) and the query labels must be the same on every rank (``broadcast_queries`` copies
+    rank 0's); gf_local (num_g_r, d) and its labels are this rank's rows.  Gallery indices are global:
+    shard r starts at sum(num_g_0..r-1), which is also how ties are broken (by global index).
+    Returns (numpy.float64[max_rank], numpy.float64) on every rank.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = qf.device
+    ops = ops or CudaOps()
+    qp, qc = _as_dev_i64(q_pids, dev), _as_dev_i64(q_camids, dev)
+    gp, gc = _as_dev_i64(g_pids_local, dev), _as_dev_i64(g_camids_local, dev)
+    qf = qf.contiguous()
+    if world > 1 and broadcast_queries:
+        for t in (qf, qp, qc):
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    # global index of this shard's first row
+    n_local = torch.tensor([gf_local.shape[0]], dtype=torch.int64, device=dev)
+    if world > 1:
+        counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, n_local, group=group)
+        counts = counts.cpu().tolist()
+        rank = dist.get_rank(group)
+    else:
+        counts, rank = [int(n_local)], 0
+    total = sum(counts)
+    if total < max_rank:
+        raise ValueError('could not broadcast input array from shape ({},) into shape ({},)'.format(total, max_rank))
+    offset = sum(counts[:rank])
+
+    d = ops.distance(qf, gf_local, metric)
+    keys, cls, ngood, status = ops.partial(d, qp, gp, qc, gc, max_rank, offset)
+    if world > 1:
+        nq = keys.shape[0]
+        keys_all = torch.empty((world * nq, max_rank), dtype=keys.dtype, device=dev)   # rank-major concatenation
+        cls_all = torch.empty((world * nq, max_rank), dtype=cls.dtype, device=dev)
+        dist.all_gather_into_tensor(keys_all, keys, group=group)
+        dist.all_gather_into_tensor(cls_all, cls, group=group)
+        keys_all, cls_all = keys_all.view(world, nq, max_rank), cls_all.view(world, nq, max_rank)
+        dist.all_reduce(ngood, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
+    else:
+        keys_all, cls_all = keys.unsqueeze(0), cls.unsqueeze(0)
+    return ops.merge(keys_all, cls_all, ngood, max_rank, status)

@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on synthetic MARS-shaped data, one JSON line ("Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Job (BASELINE.json metric "MARS-shape tracklets/s (graph head) + query x gallery eval ms"):
+one STEP is a whole MARS-shaped test pass minus the stock backbone -- the graph head over
+J = 1980 + 9330 = 11310 tracklets (8 frames, 2048 x 16 x 8 layer4 maps each, fed from a resident
+pool that is larger than L2 and cycled), then the 1980 x 9330 distance matrix on the 4096-d
+features the head just produced, then CMC/mAP (MARS metric, what the reference's test() calls).
+`value` = J / step time with the maps resident in HBM; `eval_ms` carries the distance + ranking
+part; `e2e` is the same job through the host-buffer API (maps, features, distance matrix and labels
+all start in pinned host memory, results end on the host).  At N > 1 every rank runs the head on
+its own J tracklets (no collective) and owns a 9330-row gallery shard of a N x 9330 gallery; the
+per-query top-k / good counts are merged with NCCL (weak scaling).
+
+`--impl reference` times the reference's CPU implementation of the same path on the host cores
+(oracle/: torch-CPU restatement of head and distance, the reference's own compiled rank_cy and the
+C restatement of evaluate_mars), on a bounded sample of the job, and prints the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+NQ, NG, NIDS, NCAMS = 1980, 9330, 626, 6
+S, C, H, W = 8, 2048, 16, 8
+BYTES_PER_TRACKLET = 2 * S * C * H * W * 4 + 56 * 56 * 4 + 2 * C * 4        # 16 806 144
+FLOPS_PER_TRACKLET = 2 * (2 * 56 * C * C + 2 * 2 * 56 * 56 * C)            # ~0.99 GFLOP
+METRIC = 'MARS-shape tracklets/s (graph head) + query×gallery eval ms at 1/2/4/8 B200'
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return dict(hbm_gbs=p['hbm_gbs'], bf16_tflops=p['bf16_tflops'], bf16_sustained=p['bf16_tflops_sustained'],
+                    source='measured')
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic job
+# ------------------------------------------------------------------------------------------------
+def make_labels(rank, world):
+    from agrl.pytorch_b200 import synthetic as synth
+    qp, qc, gp, gc = synth.eval_labels((NQ, NG, NIDS, NCAMS), seed=100 + rank)
+    return qp, qc, gp, gc
+
+
+def make_head_weights(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+    for name in ('global_bottleneck', 'att_bottleneck', 'graph_layers.0.bn', 'graph_layers.1.bn'):
+        w[name + '.weight'] = 1.0 + 0.1 * torch.randn(C, generator=g)
+        w[name + '.bias'] = 0.1 * torch.randn(C, generator=g)
+        w[name + '.running_mean'] = 0.1 * torch.randn(C, generator=g)
+        w[name + '.running_var'] = 0.5 + torch.rand(C, generator=g)
+    for i in range(2):
+        w['graph_layers.%d.linear.weight' % i] = 0.01 * torch.randn(C, C, generator=g)
+    return w
+
+
+def make_model(dev, weights):
+    from agrl.pytorch_b200 import models
+    m = models.init_model('vmgn', num_classes=625, loss={'xent', 'htri'}, last_stride=1, num_split=4, num_gb=2,
+                          num_scale=1, pyramid_part=True, use_pose=True, learn_graph=True, pretrained=False)
+    sd = m.state_dict()
+    for k, v in weights.items():
+        sd[k].copy_(v)
+    # only the head's parameters are needed on the device (the backbone is not part of this path)
+    for name in ('graph_layers', 'global_bottleneck', 'att_bottleneck'):
+        getattr(m, name).to(dev)
+    return m.eval()
+
+
+def make_pool(n, dev, seed, pinned=False):
+    """n tracklets of post-ReLU-like layer4 maps + a pose adjacency each; generated on the target."""
+    shape = (n * S, C, H, W)
+    if pinned:
+        g = torch.Generator().manual_seed(seed)
+        x1 = torch.empty(shape, pin_memory=True)
+        x2 = torch.empty(shape, pin_memory=True)
+        blk = 64 * S
+        for i in range(0, n * S, blk):             # fill in blocks: keeps the transient small
+            x1[i:i + blk] = torch.randn((min(blk, n * S - i), C, H, W), generator=g).clamp_(min=0)
+            x2[i:i + blk] = torch.randn((min(blk, n * S - i), C, H, W), generator=g).clamp_(min=0)
+    else:
+        g = torch.Generator(device=dev).manual_seed(seed)
+        x1 = torch.randn(shape, generator=g, device=dev).clamp_(min=0)
+        x2 = torch.randn(shape, generator=g, device=dev).clamp_(min=0)
+    from agrl.pytorch_b200 import synthetic as synth
+    adj = synth.pose_adjacency(n, S, 7, seed=seed)
+    adj = adj.pin_memory() if pinned else adj.to(dev)
+    return x1, x2, adj
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from agrl.pytorch_b200 import _lib, metrics, sharded
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    lib = _lib.require_device()
+    pk = peaks()
+
+    J, pool_n = NQ + NG, args.pool
+    weights = make_head_weights()
+    model = make_model(dev, weights)
+    x1, x2, adj = make_pool(pool_n, dev, seed=1 + rank)
+    qp, qc, gp, gc = make_labels(rank, world)
+    lab = [torch.as_tensor(a).to(dev) for a in (qp, gp, qc, gc)]
+    feats = torch.empty(J, 2 * C, device=dev)
+    chunks = [(o, min(pool_n, J - o)) for o in range(0, J, pool_n)]
+    stream = torch.cuda.current_stream(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def head_pass():
+        for off, n in chunks:
+            feats[off:off + n] = model.head(x1[:n * S], x2[:n * S], adj[:n], S)
+
+    def eval_pass():
+        if world == 1:
+            d = metrics.compute_distance_matrix(feats[:NQ], feats[NQ:], args.dist_metric)
+            return metrics.evaluate_rank(d, lab[0], lab[1], lab[2], lab[3], use_metric_mars=True)
+        return sharded.evaluate_mars_sharded(feats[:NQ], feats[NQ:], lab[0], lab[1], lab[2], lab[3],
+                                             metric=args.dist_metric, max_rank=50)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            head_pass(); result = eval_pass()
+        # ---- timed region: exactly K steps, device timed, max over ranks -------------------------
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        launches0 = _lib.launch_count()
+        t_head, t_eval = [], []
+        e0, e3 = ev(), ev()
+        e0.record(stream)
+        marks = []
+        for _ in range(args.steps):
+            a, b, c = ev(), ev(), ev()
+            a.record(stream); head_pass(); b.record(stream); result = eval_pass(); c.record(stream)
+            marks.append((a, b, c))
+        e3.record(stream)
+        barrier()
+        total_ms = e0.elapsed_time(e3)
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        head_ms = float(np.mean([a.elapsed_time(b) for a, b, c in marks]))
+        eval_ms = float(np.mean([b.elapsed_time(c) for a, b, c in marks]))
+        if world > 1:
+            t = torch.tensor([total_ms, head_ms, eval_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms, head_ms, eval_ms = [float(v) for v in t.cpu()]
+        ms_per_step = total_ms / args.steps
+        value = world * J / (ms_per_step * 1e-3)
+
+        # ---- kernel timeline of one more step (CUDA events after every kernel, same stream) ------
+        timeline = None
+        if rank == 0:
+            torch.cuda.synchronize(dev)
+            with _lib.profile(stream.cuda_stream) as prof:
+                head_pass(); eval_pass()
+            timeline = prof.totals()
+
+        # ---- end to end through host buffers -------------------------------------------------
+        e2e = None
+        if not args.no_e2e:
+            e2e = run_e2e(args, model, dev, rank, world, (qp, qc, gp, gc))
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    step_ms = sum(t for _, t in timeline.values())
+    kern = {k: dict(launches=n, ms=round(t, 4), share=round(t / step_ms, 4)) for k, (n, t) in sorted(
+        timeline.items(), key=lambda kv: -kv[1][1])}
+    top = max(timeline.items(), key=lambda kv: kv[1][1])[0]
+    n_top, ms_top = timeline[top]
+    # roofline of the dominant kernel (algorithmic work per launch / measured launch duration)
+    if top == 'pool':
+        per_launch = pool_n * BYTES_PER_TRACKLET
+        roof = dict(kernel=top, bound='hbm', unit='GB/s', peak=pk['hbm_gbs'],
+                    achieved=J * BYTES_PER_TRACKLET / (ms_top * 1e-3) / 1e9)
+    elif top.startswith('gemm'):
+        passes = 3 if top == 'gemm_graph_layer' else 6
+        flops = passes * (2 * 56 * C * C * J * 2 if top == 'gemm_graph_layer' else 2 * NQ * NG * 2 * C)
+        roof = dict(kernel=top, bound='tensor', unit='TFLOP/s', peak=pk['bf16_sustained'],
+                    achieved=flops / (ms_top * 1e-3) / 1e12, passes=passes)
+    else:
+        roof = dict(kernel=top, bound='hbm', unit='GB/s', peak=pk['hbm_gbs'],
+                    achieved=(J * 56 * C * 4 * 2) / (ms_top * 1e-3) / 1e9)
+    roof['frac'] = roof['achieved'] / roof['peak']
+    roof['traffic'] = None
+    roof['peak_source'] = pk['source']
+    roof['launches'] = n_top
+    roof['avg_launch_ms'] = ms_top / n_top
+    # whole-head roofline as SURVEY 8(d) defines it: algorithmic bytes per tracklet / head time
+    head_gbs = J * BYTES_PER_TRACKLET / (head_ms * 1e-3) / 1e9
+    gemm_d = timeline.get('gemm_distance', (1, float('nan')))[1]
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'tracklets/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'fp32 (bf16x2/bf16x3 split operands on tcgen05, fp32 accumulate)',
+        'data': 'synthetic',
+        'config': {'workload': 'MARS-shaped test pass: graph head over 11310 tracklets (8 frames, 2048x16x8 maps), '
+                               '1980x9330 %s distance on the 4096-d features, MARS-metric CMC/mAP' % args.dist_metric,
+                   'tracklets_per_step_per_gpu': J, 'pool_tracklets': pool_n,
+                   'cache': 'input pool %.1f GB per GPU, larger than L2; cycled' % (pool_n * BYTES_PER_TRACKLET / 1e9),
+                   'parallelism': 'independent head shards + gallery-sharded eval (NCCL merge)' if world > 1 else 'single GPU'},
+        'head_ms': head_ms, 'eval_ms': eval_ms,
+        'head_tracklets_per_s_per_gpu': J / (head_ms * 1e-3),
+        'head_hbm': {'achieved': head_gbs, 'peak': pk['hbm_gbs'], 'frac': head_gbs / pk['hbm_gbs'], 'unit': 'GB/s',
+                     'note': 'algorithmic 16806144 B per tracklet / whole-head time (SURVEY 8d)'},
+        'distance': {'ms': gemm_d, 'algorithmic_tflops': 2 * NQ * NG * 2 * C / (gemm_d * 1e-3) / 1e12,
+                     'tensor_pipe_frac': 6 * 2 * NQ * NG * 2 * C / (gemm_d * 1e-3) / 1e12 / pk['bf16_sustained']},
+        'roofline': roof, 'kernels': kern, 'gpu_launches': int(launches),
+        'clocks': clocks, 'result': {'mAP': float(result[1]), 'rank1': float(result[0][0])},
+    }
+    if e2e is not None:
+        line['e2e'] = e2e
+    if not args.no_cpu_baseline and world >= 1:
+        line['cpu_baseline'] = cpu_reference(args, steps=1, warmup=0)['cpu_baseline']
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, model, dev, rank, world, labels):
+    """Same job through the host-facing API: maps in pinned host memory, H2D chunk by chunk on a copy
+    stream (double buffered against the head), features back to the host, then the reference's own
+    call sequence compute_distance_matrix(CPU tensors) -> .numpy() -> evaluate_rank(numpy)
+    (train_vidreid_xent_htri.py:477-531)."""
+    import torch.distributed as dist
+    from agrl.pytorch_b200 import metrics
+    J, n_host, chunk = NQ + NG, args.e2e_pool, args.e2e_chunk
+    hx1, hx2, hadj = make_pool(n_host, dev, seed=7 + rank, pinned=True)
+    qp, qc, gp, gc = labels
+    bufs = [(torch.empty(chunk * S, C, H, W, device=dev), torch.empty(chunk * S, C, H, W, device=dev),
+             torch.empty(chunk, 56, 56, device=dev)) for _ in range(2)]
+    feats_host = torch.empty(J, 2 * C, pin_memory=True)
+    copy_stream = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    chunks = [(o, min(chunk, J - o)) for o in range(0, J, chunk)]
+    h2d = J * BYTES_PER_TRACKLET - J * 2 * C * 4 + J * 2 * C * 4 + NQ * NG * 4 + (NQ + NG) * 16    # maps+adj, features, distmat, labels
+    d2h = J * 2 * C * 4 + NQ * NG * 4 + 51 * 8
+
+    def one_step():
+        ready = [torch.cuda.Event() for _ in chunks]
+        freed = [torch.cuda.Event() for _ in chunks]
+        for i, (off, n) in enumerate(chunks):
+            b1, b2, ba = bufs[i % 2]
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(freed[i - 2])
+                src = (off % n_host)
+                if src + n > n_host:
+                    src = 0
+                b1[:n * S].copy_(hx1[src * S:(src + n) * S], non_blocking=True)
+                b2[:n * S].copy_(hx2[src * S:(src + n) * S], non_blocking=True)
+                ba[:n].copy_(hadj[src:src + n], non_blocking=True)
+                ready[i].record(copy_stream)
+            main.wait_event(ready[i])
+            f = model.head(b1[:n * S], b2[:n * S], ba[:n], S)
+            feats_host[off:off + n].copy_(f, non_blocking=True)
+            freed[i].record(main)
+        main.synchronize()
+        d = metrics.compute_distance_matrix(feats_host[:NQ], feats_host[NQ:], args.dist_metric)   # CPU tensors
+        return metrics.evaluate_rank(d.numpy(), qp, gp, qc, gc, use_metric_mars=True)
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    one_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = one_step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.cpu())
+    del hx1, hx2, bufs
+    return {'value': world * J / dt, 'unit': 'tracklets/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+            'ms_per_step': dt * 1e3, 'steps': steps,
+            'note': 'layer4 maps start in pinned host memory (16.8 MB/tracklet over PCIe); eval via CPU-tensor / numpy API'}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the same path, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(args, steps, warmup):
+    from oracle import head as ohead, distance as odist, rank as orank
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    J, n_head = NQ + NG, args.cpu_head_sample
+    weights = make_head_weights()
+    g = torch.Generator().manual_seed(3)
+    x1 = torch.randn(n_head * S, C, H, W, generator=g).clamp_(min=0)
+    x2 = torch.randn(n_head * S, C, H, W, generator=g).clamp_(min=0)
+    from agrl.pytorch_b200 import synthetic as synth
+    adj = synth.pose_adjacency(n_head, S, 7, seed=3)
+    qp, qc, gp, gc = make_labels(0, 1)
+    feats = torch.randn(J, 2 * C, generator=g)
+    have_ref_cy = orank.reference_rank_cy() is not None
+
+    def one():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ohead.head_forward(x1, x2, adj, weights)
+        t1 = time.perf_counter()
+        d = odist.distance_matrix(feats[:NQ], feats[NQ:], args.dist_metric)
+        t2 = time.perf_counter()
+        orank.mars_port(d.numpy(), qp, gp, qc, gc, 50)
+        t3 = time.perf_counter()
+        cy = None
+        if have_ref_cy:
+            orank.reference_evaluate_cy(d.numpy(), qp, gp, qc, gc, 50, stable=False)
+            cy = time.perf_counter() - t3
+        return (t1 - t0) / n_head, t2 - t1, t3 - t2, cy
+
+    for _ in range(warmup):
+        one()
+    runs = [one() for _ in range(max(1, steps))]
+    per_tracklet = min(r[0] for r in runs)
+    t_dist = min(r[1] for r in runs)
+    t_rank = min(r[2] for r in runs)
+    t_cy = min(r[3] for r in runs) if have_ref_cy else None
+    job_s = J * per_tracklet + t_dist + t_rank
+    value = J / job_s
+    base = {'value': value, 'unit': 'tracklets/s', 'cores': cores, 'kind': 'port',
+            'sample': 'head: %d of %d tracklets timed with the torch-CPU restatement (%.2f ms/tracklet, extrapolated); '
+                      'distance 1980x9330x4096 (%.0f ms) and MARS-metric ranking (C restatement, %.0f ms) in full'
+                      % (n_head, J, per_tracklet * 1e3, t_dist * 1e3, t_rank * 1e3),
+            'head_ms_per_tracklet': per_tracklet * 1e3, 'distance_ms': t_dist * 1e3, 'rank_mars_ms': t_rank * 1e3,
+            'rank_cy_reference_ms': None if t_cy is None else t_cy * 1e3}
+    return {'cpu_baseline': base, 'job_s': job_s, 'eval_ms': (t_dist + t_rank) * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = cpu_reference(args, steps=args.steps, warmup=args.warmup)
+    base = r['cpu_baseline']
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'tracklets/s',
+            'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': r['job_s'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': 'MARS-shaped test pass on the host CPU: graph head (sampled, extrapolated to 11310 '
+                                   'tracklets) + 1980x9330 %s distance + MARS-metric CMC/mAP' % args.dist_metric},
+            'eval_ms': r['eval_ms'], 'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': 'tracklets/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--pool', type=int, default=256, help='tracklets in the resident input pool (4.3 GB at 256)')
+    ap.add_argument('--dist-metric', default='euclidean', choices=['euclidean', 'cosine'])
+    ap.add_argument('--e2e-pool', type=int, default=128)
+    ap.add_argument('--e2e-chunk', type=int, default=64)
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--cpu-head-sample', type=int, default=32)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

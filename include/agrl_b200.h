@@ -76,6 +76,11 @@ AGRL_API const char *agrl_last_cuda_error(void);           /* thread-local text 
 AGRL_API int         agrl_device_ok(void);
 /* number of kernels this library has launched from the calling thread (bench.py `gpu_launches`)   */
 AGRL_API uint64_t    agrl_launch_count(void);
+/* Kernel timeline of the calling thread: between begin and end every kernel this library launches is
+ * followed by a CUDA event on its stream; end synchronises and writes "name:ms;name:ms;..." (the
+ * time from the previous event to this one, i.e. the kernel's duration on a busy stream). */
+AGRL_API int         agrl_profile_begin(void *stream);
+AGRL_API int         agrl_profile_end(char *text, size_t capacity);
 
 /* =============================================================================================
  * (3) Ranking -- replaces rank_cy.evaluate_cy (torchreid/metrics/rank_cylib/rank_cy.pyx:24-32,
@@ -119,6 +124,29 @@ AGRL_API int agrl_rank_mars_dev(const float *distmat_dev, int64_t ld_dist,
                        double *cmc_dev, double *map_dev, double *all_ap_dev,
                        uint32_t *status_dev,
                        void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/*
+ * Gallery-sharded MARS metric (one gallery shard per GPU).  Each shard calls
+ * _partial on its (num_q, num_g_shard) distance block: it emits, per query, the shard's best max_rank
+ * candidates as 64-bit keys (order-preserving distance bits << 32 | GLOBAL gallery index; all-ones =
+ * empty slot), their class bytes (bit0 good, bit1 junk) and the shard's good-image count.  After an
+ * all-gather of keys/classes ([part][query][max_rank]) and an all-reduce(sum) of the good counts,
+ * _merge produces exactly what agrl_rank_mars_dev would on the concatenated gallery.
+ * The status word of _partial only ever carries AGRL_ST_LABEL_RANGE; _merge ORs AGRL_ST_ZERO_DIVISION
+ * into its own (which the caller zeroes).  parts * max_rank <= 16384.
+ */
+AGRL_API int agrl_rank_mars_partial_dev(const float *distmat_dev, int64_t ld_dist,
+                               const int64_t *q_pids_dev, const int64_t *g_pids_dev,
+                               const int64_t *q_camids_dev, const int64_t *g_camids_dev,
+                               int64_t num_q, int64_t num_g, int64_t max_rank, int64_t index_offset,
+                               uint64_t *keys_dev, uint8_t *cls_dev, int32_t *ngood_dev,
+                               uint32_t *status_dev,
+                               void *workspace_dev, size_t workspace_bytes, void *stream);
+AGRL_API int agrl_rank_mars_merge_dev(const uint64_t *keys_dev, const uint8_t *cls_dev,
+                             const int32_t *ngood_dev, int64_t parts, int64_t num_q, int64_t max_rank,
+                             double *cmc_dev, double *map_dev, double *all_ap_dev,
+                             uint32_t *status_dev,
+                             void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* Host-buffer forms (numpy in / numpy out like the reference).  cmc_host must hold max_rank
  * entries; *rank_len_out receives min(max_rank, num_g) for the market1501 metric. */

@@ -93,10 +93,10 @@ def test_full_model_through_cudnn_backbone():
     model = models.init_model('vmgn', num_classes=625, loss={'xent', 'htri'}, last_stride=1, num_split=4,
                               num_gb=2, num_scale=1, pyramid_part=True, use_pose=True, learn_graph=True,
                               pretrained=False)
-    assert float(model.state_dict()['conv1.weight'].double().sum()) == float(g['conv1_checksum'])
+    assert abs(float(model.state_dict()['conv1.weight'].double().sum()) - float(g['conv1_checksum'])) < 1e-9
     gen = torch.Generator().manual_seed(int(g['input_seed']))
     x = torch.randn(2, 8, 3, 256, 128, generator=gen)
-    assert float(x.double().sum()) == float(g['x_checksum'])
+    assert abs(float(x.double().sum()) - float(g['x_checksum'])) < 1e-6
     adj = synth.pose_adjacency(2, 8, 7, seed=int(g['input_seed']))
     model = model.cuda().eval()
     with torch.no_grad():

@@ -131,3 +131,27 @@ def test_evaluate_rank_dispatch(metrics):
     assert metrics.evaluate_rank(d, *ids) is None                       # no metric flag (rank.py:232-238)
     with pytest.raises(NotImplementedError):
         metrics.evaluate_rank(d, *ids, use_metric_cuhk03=True)
+
+
+@pytest.mark.parametrize('shape,seed,kind,parts', [('dukev', 21, 'randn', 3), ((100, 2049, 40, 4), 22, 'ties', 2),
+                                                   ('mars', 23, 'randn', 8), ((33, 70, 5, 2), 24, 'ties', 4)])
+def test_sharded_partial_and_merge_kernels(shape, seed, kind, parts):
+    """the gallery-sharded MARS kernels (partial per shard + merge), single process: shards are
+    column slices of one distance matrix; result must be bit-identical to the unsharded oracle"""
+    from agrl.pytorch_b200 import sharded
+    qp, qc, gp, gc = synth.eval_labels(shape, seed=seed)
+    d = _distmat(kind, len(qp), len(gp), seed)
+    K = 50
+    ref_cmc, ref_map = orank.mars_port(d, qp, gp, qc, gc, K)
+    ops = sharded.CudaOps()
+    dev = torch.device('cuda')
+    dd = torch.from_numpy(d).to(dev)
+    tq, tqc = torch.as_tensor(qp).to(dev), torch.as_tensor(qc).to(dev)
+    keys, cls, ngood = [], [], 0
+    for lo, hi in sharded.shard_bounds(len(gp), parts):
+        k, c, n, st = ops.partial(dd[:, lo:hi], tq, torch.as_tensor(gp[lo:hi]).to(dev), tqc,
+                                  torch.as_tensor(gc[lo:hi]).to(dev), K, lo)
+        keys.append(k); cls.append(c); ngood = ngood + n
+    cmc, mAP = ops.merge(torch.stack(keys), torch.stack(cls), ngood, K, st)
+    assert np.array_equal(_bits64(cmc), _bits64(ref_cmc))
+    assert _bits64(mAP) == _bits64(ref_map)

@@ -18,7 +18,8 @@ def regenerate(g):
     wts = synth.head_weights(2048, 2, seed=int(g['weights_seed']), randomise_bn=bool(g['randomise_bn']))
     chk = float(x1.double().sum() + 3 * x2.double().sum() + 7 * adj.double().sum()
                 + sum(v.double().sum() for v in wts.values()))
-    assert chk == float(g['checksum']), 'torch RNG stream drifted: regenerate tests/golden'
+    # summation order of .sum() may differ between CPUs: compare to 1e-12, not bit for bit
+    assert abs(chk - float(g['checksum'])) <= 1e-12 * abs(chk), 'torch RNG stream drifted: regenerate tests/golden'
     return x1, x2, adj, wts
 
 
