@@ -59,11 +59,11 @@ extern "C" int agrl_distance_dev(const float *q, int64_t ld_q, const float *g, i
     if ((rc = gemm::launch_split_planes(sg, st))) return rc;
 
     CUtensorMap map_q, map_g;
-    if ((rc = gemm::make_plane_tensor_map(&map_q, w.q_planes, num_q, kp, split))) return rc;
-    if ((rc = gemm::make_plane_tensor_map(&map_g, w.g_planes, num_g, kp, split))) return rc;
+    if ((rc = gemm::make_plane_tensor_map(&map_q, w.q_planes, num_q, kp, split, gemm::BM))) return rc;
+    if ((rc = gemm::make_plane_tensor_map(&map_g, w.g_planes, num_g, kp, split, 128))) return rc;
 
     gemm::EpiDistance epi{w.qn, w.gn, out, ld_out, metric};
     if (split == AGRL_SPLIT_BF16X3)
-        return gemm::launch_split_gemm<3>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
-    return gemm::launch_split_gemm<2>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
+        return gemm::launch_split_gemm<3, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
+    return gemm::launch_split_gemm<2, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
 }

@@ -12,11 +12,13 @@
 // Kernel anatomy (one persistent CTA per SM, 256 threads, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of the A and B plane tiles into a
 //               ring of shared-memory stages, completion on mbarriers
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (cta_group::1, 128 x 128 x 16, kind::f16),
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (cta_group::1, 128 x BN x 16, kind::f16),
 //               tcgen05.commit frees the smem stage / publishes the accumulator
 //   warp 2      TMEM allocator (2 stages x [main | correction] x 128 columns = all 512 columns)
-//   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns), transpose through padded smem so that
-//               global stores are full 128 B lines, fused element-wise epilogue functor
+//   warps 4..   epilogue: tcgen05.ld (32 lanes x 32 columns) + fused element-wise functor; either
+//               4 warps transposing through padded smem so stores are full 128 B lines at any row
+//               alignment (distance), or 8 warps doing 16-byte accesses straight from registers with
+//               the residual tile prefetched into L2 during the mainloop (graph layer)
 // The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -27,22 +29,33 @@
 namespace agrl {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 64;           // CTA tile; BK bf16 = one 128-byte swizzle row
+constexpr int BM = 128, BK = 64;                     // CTA tile rows; BK bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kPlaneTileBytes = BM * BK * 2;         // 16 KiB: one plane of an A (or B) tile
-constexpr int kThreads = 256;
-constexpr int kEpiWarps = 4;
+constexpr int kTileBytesA = BM * BK * 2;             // 16 KiB: one plane of an A tile
+constexpr int kCtrlWarps = 4;                        // TMA producer, MMA issuer, TMEM allocator, spare
 constexpr int kAccStages = 2;
-constexpr int kAccCols = 2 * BN;                     // per stage: [main a0.b0 | correction products]
-constexpr int kTmemCols = kAccStages * kAccCols;     // 512 columns: all of TMEM
+constexpr int kTmemCols = 512;                       // all of TMEM: 2 stages x 256 columns
 constexpr int kEpiPad = 33;
-constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPad * 4;
-static_assert(BM == BN, "A and B tiles share one TMA box shape");
+constexpr int kEpiBytes = 4 * 32 * kEpiPad * 4;       // transpose staging of the 4-warp (scalar-store) epilogue
 
-template <int P> struct Config {
-    static constexpr int kStages = (P == 3) ? 2 : 3;
-    static constexpr int kStageBytes = 2 * P * kPlaneTileBytes;
+// P      operand planes (2: three products, 3: six products)
+// BN     tile width: 128 or 256 (UMMA 128 x BN x 16)
+// kSplit keep the dominant a0.b0 sum and the correction products in separate TMEM accumulators
+//        (needs 2*BN columns per stage, hence BN = 128)
+template <int P, int BN, bool kSplit, bool kDirect = false> struct Config {
+    // epilogue flavour: kDirect = registers -> 16-byte global accesses, 8 warps (two per TMEM lane
+    // quarter, half the columns each), no smem; otherwise 4 warps and a padded smem transpose so
+    // that stores are coalesced along rows of arbitrary alignment.
+    static constexpr int kEpiWarps = kDirect ? 8 : 4;
+    static constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
+    static_assert(BN == 128 || BN == 256, "tile width");
+    static_assert(!kSplit || BN == 128, "two accumulators of 256 columns do not fit twice in TMEM");
+    static constexpr int kTileBytesB = BN * BK * 2;
+    static constexpr int kStageBytes = P * (kTileBytesA + kTileBytesB);
+    static constexpr int kStages = (200 * 1024) / kStageBytes;          // 96 KiB stages -> 2, 64 KiB -> 3
+    static constexpr int kAccCols = kSplit ? 2 * BN : BN;               // columns per accumulator stage
     static constexpr int kNumPairs = (P == 3) ? 6 : (P == 2 ? 3 : 1);
+    static_assert(kStages >= 2 && kAccStages * kAccCols <= kTmemCols, "resources");
     // dynamic smem: stages | epilogue staging | barriers ; +1024 for manual alignment
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 1024;
 };
@@ -147,6 +160,7 @@ constexpr uint32_t make_idesc(int m, int n) {
 // ---- epilogue functors: value for output element (row, col) given the accumulator -------------
 struct EpiDistance {            // distance.py:59-73 / :76-89
     static constexpr const char *kName = "gemm_distance";
+    static constexpr bool kDirect = false;      // rows of arbitrary alignment: coalesce through smem
     const float *qn, *gn;       // squared norms (euclidean); unused for cosine
     float *out;
     int64_t ld;
@@ -165,6 +179,36 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
 
 struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) + (1-gamma) * x
     static constexpr const char *kName = "gemm_graph_layer";
+    static constexpr bool kDirect = true;       // C % 4 == 0 and 16-byte aligned rows: vector accesses
+    // pull this thread's slice of the residual row into L2 before the accumulator is ready
+    __device__ __forceinline__ void prefetch(int row, int col0, int ncols, bool valid) const {
+        if (!valid) return;
+        const float *p = x + static_cast<size_t>(row) * ldx + col0;
+        for (int c = 0; c < ncols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c));
+    }
+    // 32 consecutive columns of one row: all residual loads first, then the math, then the stores
+    __device__ __forceinline__ void store_row32(int row, int col0, int n_cols, const uint32_t (&acc)[32]) const {
+        const float4 *xr = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * ldx + col0);
+        float4 *orow = reinterpret_cast<float4 *>(out + static_cast<size_t>(row) * ldo + col0);
+        const float4 *sc = reinterpret_cast<const float4 *>(scale + col0);
+        const float4 *sh = reinterpret_cast<const float4 *>(shift + col0);
+        if (col0 + 32 > n_cols) return;                       // N is a multiple of 32 for this epilogue
+        float4 xin[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xin[q] = __ldg(xr + q);
+        const float keep = 1.0f - gamma;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 s4 = __ldg(sc + q), t4 = __ldg(sh + q);
+            float4 o;
+            float h;
+            h = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, t4.x); h = h >= 0.f ? h : h * slope; o.x = fmaf(gamma, h, keep * xin[q].x);
+            h = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, t4.y); h = h >= 0.f ? h : h * slope; o.y = fmaf(gamma, h, keep * xin[q].y);
+            h = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, t4.z); h = h >= 0.f ? h : h * slope; o.z = fmaf(gamma, h, keep * xin[q].z);
+            h = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, t4.w); h = h >= 0.f ? h : h * slope; o.w = fmaf(gamma, h, keep * xin[q].w);
+            orow[q] = o;
+        }
+    }
     const float *x;             // layer input (M, ldx)
     const float *scale, *shift; // folded eval-mode BatchNorm1d per output channel
     float *out;
@@ -183,11 +227,12 @@ struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
 };
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int P, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int P, int BN, bool kSplit, class Epi>
+__global__ void __launch_bounds__((Config<P, BN, kSplit, Epi::kDirect>::kThreads), 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   int M, int N, int k_pad, Epi epi) {
-    using Cfg = Config<P>;
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect>;
+    constexpr int kAccCols = Cfg::kAccCols;
     extern __shared__ unsigned char smem_dyn[];
     // 128B-swizzled tiles need 1024-byte alignment
     unsigned char *smem = reinterpret_cast<unsigned char *>(
@@ -205,6 +250,13 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = k_pad / BK;
+    // Raster: the operand with FEWER tiles varies fastest, so the CTAs running at any moment share it
+    // (L2-resident) while the larger operand streams through exactly once.
+    const bool m_fast = tiles_m <= tiles_n;
+    auto tile_origin = [&](int tile, int &m0, int &n0) {
+        if (m_fast) { m0 = (tile % tiles_m) * BM; n0 = (tile / tiles_m) * BN; }
+        else        { n0 = (tile % tiles_n) * BN; m0 = (tile / tiles_n) * BM; }
+    };
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a);
@@ -212,7 +264,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, kEpiWarps); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -228,18 +280,19 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================= TMA producer =================
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            int m0, n0;
+            tile_origin(tile, m0, n0);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (lane == 0) {
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t sb = sa + P * kPlaneTileBytes;
+                    const uint32_t sb = sa + P * kTileBytesA;
                     mbar_arrive_expect_tx(full, Cfg::kStageBytes);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kPlaneTileBytes, &map_a, full, kb * BK, m0, p);
+                    for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kTileBytesA, &map_a, full, kb * BK, m0, p);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) tma_load_3d(sb + p * kPlaneTileBytes, &map_b, full, kb * BK, n0, p);
+                    for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::kTileBytesB, &map_b, full, kb * BK, n0, p);
                 }
                 __syncwarp();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -260,23 +313,23 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // the big a0.b0 sum spares it 5/6 (P=3) of those truncations, and the correction sum itself
             // is ~2^-8 smaller, so its own truncation is negligible.
             const uint32_t d_main = tmem_base + acc * kAccCols;
-            const uint32_t d_corr = d_main + BN;
+            const uint32_t d_corr = kSplit ? d_main + BN : d_main;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(bar_full + 8 * stage, phase);            // TMA bytes have landed
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t sb = sa + P * kPlaneTileBytes;
+                    const uint32_t sb = sa + P * kTileBytesA;
 #pragma unroll
                     for (int i = 0; i < Cfg::kNumPairs; ++i) {
                         int pa, pb;
                         pair_of(P, i, pa, pb);
-                        const uint64_t da = make_smem_desc(sa + pa * kPlaneTileBytes);
-                        const uint64_t db = make_smem_desc(sb + pb * kPlaneTileBytes);
+                        const uint64_t da = make_smem_desc(sa + pa * kTileBytesA);
+                        const uint64_t db = make_smem_desc(sb + pb * Cfg::kTileBytesB);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
-                            if (i == Cfg::kNumPairs - 1)
+                            if (kSplit && i == Cfg::kNumPairs - 1)
                                 tc_mma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                             else
                                 tc_mma_bf16(d_corr, da + 2 * k, db + 2 * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
@@ -289,39 +342,65 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= kCtrlWarps) {
         // ================= epilogue =================
-        const int ew = warp - 4;                                   // == warp % 4: the TMEM lane quarter
-        float *buf = epi_buf + ew * 32 * kEpiPad;
+        const int ew = warp - kCtrlWarps;
+        const int quarter = ew & 3;                                // == warp % 4: the TMEM lane quarter
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            int m0, n0;
+            tile_origin(tile, m0, n0);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            tc_fence_after();
-            const int row_base = m0 + ew * 32;
+            const int row_base = m0 + quarter * 32;
+            const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
+            if constexpr (Epi::kDirect) {
+                // thread = one output row, 16-byte accesses straight from registers; warps 4-7 of the
+                // group take the upper half of the tile's columns
+                const int col_half = (ew >> 2) * (BN / 2);
+                const int row = row_base + lane;
+                epi.prefetch(row, n0 + col_half, BN / 2, row < M);     // residual tile -> L2 while the MMAs run
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32], rc[32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kAccCols + c * 32;
-                tmem_ld_32x32(taddr, r);
-                tmem_ld_32x32(taddr + BN, rc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    buf[lane * kEpiPad + j] = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]));
-                __syncwarp();
-                const int col = n0 + c * 32 + lane;
-                if (col < N) {
-                    const typename Epi::Col cs = epi.col_state(col);
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = row_base + rr;
-                        if (row < M) epi.store(row, col, buf[rr * kEpiPad + lane], cs);
-                    }
+                for (int c = 0; c < BN / 2; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tq + col_half + c, r);
+                    tmem_ld_wait();
+                    if (row < M) epi.store_row32(row, n0 + col_half + c, N, r);
                 }
-                __syncwarp();
+            } else {
+                float *buf = epi_buf + quarter * 32 * kEpiPad;
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tq + c * 32, r);
+                    if (kSplit) {
+                        uint32_t rc[32];
+                        tmem_ld_32x32(tq + BN + c * 32, rc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            buf[lane * kEpiPad + j] = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]));
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) buf[lane * kEpiPad + j] = __uint_as_float(r[j]);
+                    }
+                    __syncwarp();
+                    const int col = n0 + c * 32 + lane;
+                    if (col < N) {
+                        const typename Epi::Col cs = epi.col_state(col);
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const int row = row_base + rr;
+                            if (row < M) epi.store(row, col, buf[rr * kEpiPad + lane], cs);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -334,18 +413,20 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-// 3-D tensor map over planes [P][rows][k_pad] of bf16: box = (BK, BM, 1), 128-byte swizzle
-int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P);
+// 3-D tensor map over planes [P][rows][k_pad] of bf16: box = (BK, box_rows, 1), 128-byte swizzle.
+// box_rows = BM for the A operand, the kernel's BN for the B operand.
+int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows);
 
-template <int P, class Epi>
+template <int P, int BN, bool kSplit, class Epi>
 int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,
                       const Epi &epi, cudaStream_t st) {
-    using Cfg = Config<P>;
-    auto kern = split_gemm_kernel<P, Epi>;
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect>;
+    static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
+    auto kern = split_gemm_kernel<P, BN, kSplit, Epi>;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
     AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;
 }

@@ -148,9 +148,9 @@ pool_kernel(PoolArgs a) {
 // ------------------------------------------------------------------------------------------------
 // graph kernel: one CTA per tracklet
 // ------------------------------------------------------------------------------------------------
-constexpr int kChunk = 256;                 // channels staged per step
+constexpr int kChunk = 128;                 // channels staged per step (double buffered)
 constexpr int kXsLd = kChunk + 4;           // padded row stride (floats), keeps float4 alignment
-constexpr int kGLd = kMaxNodes + 1;
+constexpr int kGLd = kMaxNodes + 4;         // graph row stride: float4-aligned rows
 
 struct GraphArgs {
     const float *x;                    // (B, V, C) layer input
@@ -164,74 +164,110 @@ struct GraphArgs {
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// stage X[:, c0:c0+kChunk] (V rows; rows V..NT*4-1 stay zero) into shared memory
-__device__ __forceinline__ void stage_chunk(float *xs, const float *x, int V, int C, int c0, int tid) {
-    const int per_row = kChunk / 4;
+// start staging X[:, c0:c0+kChunk] (V rows; rows V.. stay zero) into one of the two smem buffers
+__device__ __forceinline__ void stage_chunk_async(float *xs, const float *x, int V, int C, int c0, int tid) {
+    constexpr int per_row = kChunk / 4;
     for (int i = tid; i < V * per_row; i += kHeadThreads) {
         const int r = i / per_row, q = i % per_row;
         cp_async16(xs + r * kXsLd + q * 4, x + static_cast<size_t>(r) * C + c0 + q * 4);
     }
-    cp_async_wait_all();
+    cp_async_commit();
+}
+
+// Run `body(buffer)` over all channel chunks of x with the next chunk in flight (cp.async).
+template <class F>
+__device__ __forceinline__ void for_each_chunk(float *xs0, float *xs1, const float *x, int V, int C, int tid, F &&body) {
+    const int n = C / kChunk;
+    stage_chunk_async(xs0, x, V, C, 0, tid);
+    for (int i = 0; i < n; ++i) {
+        float *cur = (i & 1) ? xs1 : xs0;
+        if (i + 1 < n) {
+            stage_chunk_async((i & 1) ? xs0 : xs1, x, V, C, (i + 1) * kChunk, tid);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                       // chunk i is visible to every thread
+        body(cur, i * kChunk);
+        __syncthreads();                       // everyone is done with `cur` before it is refilled
+    }
 }
 
 template <int NT>                            // NT = ceil(V/4): 14 for the canonical V = 56
-__global__ void __launch_bounds__(kHeadThreads)
+__global__ void __launch_bounds__(kHeadThreads, 2)
 graph_kernel(GraphArgs a) {
+    constexpr int kRows = 4 * NT;                      // staged rows (>= V; the rest stay zero)
+    constexpr int kTiles = NT * (NT + 1) / 2;          // 4x4 Gram tiles of the upper triangle
+    constexpr int kGroups = (2 * kTiles <= kHeadThreads) ? 2 : 1;      // split the chunk's k range
+    constexpr int kRpg = NT / 2;                       // rows per thread in Y = G.X (8 row groups)
+    static_assert(NT % 2 == 0 && kTiles <= kHeadThreads, "tiling");
     extern __shared__ __align__(16) float smem_f[];
-    float *xs = smem_f;                                // [4*NT][kXsLd]
-    float *g = xs + 4 * NT * kXsLd;                    // [64][65]: Gram, then the mixed graph
+    float *xs0 = smem_f;                               // [kRows][kXsLd] x 2
+    float *xs1 = xs0 + kRows * kXsLd;
+    float *g = xs1 + kRows * kXsLd;                    // [64][68]: Gram, then the mixed graph
     float *sq = g + kMaxNodes * kGLd;                  // [64]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = a.V, C = a.C;
     const int b = blockIdx.x;
     const float *x = a.x + static_cast<size_t>(b) * V * C;
 
-    for (int i = tid; i < 4 * NT * kXsLd; i += kHeadThreads) xs[i] = 0.f;     // pad rows stay zero
+    for (int i = tid; i < 2 * kRows * kXsLd; i += kHeadThreads) xs0[i] = 0.f;   // pad rows stay zero
+    for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
     __syncthreads();
 
     if (a.learn_graph) {
-        // ---- Gram matrix: thread (ti, tj) owns rows {ti + NT*e} x {tj + NT*f}, e,f < 4 ----
-        const bool active = tid < NT * NT;
-        const int ti = tid / NT, tj = tid % NT;
+        // ---- Gram matrix, upper triangle only: thread (ti <= tj) owns rows {ti+NT*e} x {tj+NT*f} ----
+        const int u = tid % kTiles, kg = tid / kTiles;
+        const bool active = kg < kGroups;
+        int ti = 0, tj = u;
+        while (tj >= NT - ti) { tj -= NT - ti; ++ti; }          // u -> (ti, tj), tj counted from ti
+        tj += ti;
         float acc[4][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
             for (int f = 0; f < 4; ++f) acc[e][f] = 0.f;
-        for (int c0 = 0; c0 < C; c0 += kChunk) {
-            stage_chunk(xs, x, V, C, c0, tid);
-            __syncthreads();
-            if (active) {
-#pragma unroll 4
-                for (int k = 0; k < kChunk; k += 4) {
-                    float4 av[4], bv[4];
+        for_each_chunk(xs0, xs1, x, V, C, tid, [&](const float *xs, int) {
+            if (!active) return;
+            const int k0 = kg * (kChunk / kGroups);
+#pragma unroll 2
+            for (int k = k0; k < k0 + kChunk / kGroups; k += 4) {
+                float4 av[4], bv[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        av[e] = *reinterpret_cast<const float4 *>(xs + (ti + NT * e) * kXsLd + k);
-                        bv[e] = *reinterpret_cast<const float4 *>(xs + (tj + NT * e) * kXsLd + k);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-#pragma unroll
-                        for (int f = 0; f < 4; ++f) {
-                            acc[e][f] = fmaf(av[e].x, bv[f].x, acc[e][f]);
-                            acc[e][f] = fmaf(av[e].y, bv[f].y, acc[e][f]);
-                            acc[e][f] = fmaf(av[e].z, bv[f].z, acc[e][f]);
-                            acc[e][f] = fmaf(av[e].w, bv[f].w, acc[e][f]);
-                        }
+                for (int e = 0; e < 4; ++e) {
+                    av[e] = *reinterpret_cast<const float4 *>(xs + (ti + NT * e) * kXsLd + k);
+                    bv[e] = *reinterpret_cast<const float4 *>(xs + (tj + NT * e) * kXsLd + k);
                 }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        acc[e][f] = fmaf(av[e].x, bv[f].x, acc[e][f]);
+                        acc[e][f] = fmaf(av[e].y, bv[f].y, acc[e][f]);
+                        acc[e][f] = fmaf(av[e].z, bv[f].z, acc[e][f]);
+                        acc[e][f] = fmaf(av[e].w, bv[f].w, acc[e][f]);
+                    }
+            }
+        });
+        // combine the k groups and mirror into the lower triangle
+#pragma unroll
+        for (int grp = 0; grp < kGroups; ++grp) {
+            if (active && kg == grp) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const int r = ti + NT * e, c = tj + NT * f;
+                        const float v = (grp == 0) ? acc[e][f] : g[r * kGLd + c] + acc[e][f];
+                        g[r * kGLd + c] = v;
+                        if (ti != tj) g[c * kGLd + r] = v;     // a diagonal tile holds both (r,c) and (c,r) itself
+                    }
             }
             __syncthreads();
         }
-        if (active) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-#pragma unroll
-                for (int f = 0; f < 4; ++f) g[(ti + NT * e) * kGLd + (tj + NT * f)] = acc[e][f];
-        }
-        __syncthreads();
         if (tid < V) sq[tid] = g[tid * kGLd + tid];
         __syncthreads();
         // ---- affinity 2 / (exp(sqrt(max(d2, 1e-12))) + 1)  (vmgn.py:116-120) ----
@@ -259,33 +295,40 @@ graph_kernel(GraphArgs a) {
         } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
         else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
         __syncwarp();
-        if (lane < V) g[r * kGLd + lane] = m0;
-        if (c1 < kMaxNodes) g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
+        g[r * kGLd + lane] = (lane < V) ? m0 : 0.f;
+        g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
     }
-    // rows V..63 of the graph are never read; columns V..63 are zero
+    // graph rows >= V are never stored; graph columns >= V are zero
     __syncthreads();
 
-    // ---- Y = G . X : thread (rg, cq) owns rows {rg*NT .. rg*NT+NT-1} x 4 channels ----
-    const int rg = tid >> 6, cq = tid & 63;
+    // ---- Y = G . X : thread (rg, cq) owns rows {rg*kRpg ..+kRpg-1} x 4 channels of the chunk ----
+    const int rg = tid >> 5, cq = tid & 31;              // a warp shares rg -> graph weights broadcast
     const size_t row0 = static_cast<size_t>(b) * V;
-    for (int c0 = 0; c0 < C; c0 += kChunk) {
-        stage_chunk(xs, x, V, C, c0, tid);
-        __syncthreads();
-        float acc[NT][4];
+    const int jmax = (V + 3) & ~3;
+    for_each_chunk(xs0, xs1, x, V, C, tid, [&](const float *xs, int c0) {
+        float acc[kRpg][4];
 #pragma unroll
-        for (int r = 0; r < NT; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-        for (int j = 0; j < V; ++j) {
-            const float4 xv = *reinterpret_cast<const float4 *>(xs + j * kXsLd + cq * 4);
+        for (int r = 0; r < kRpg; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+        for (int j = 0; j < jmax; j += 4) {
+            float4 xv[4];
 #pragma unroll
-            for (int r = 0; r < NT; ++r) {
-                const float w = g[(rg * NT + r) * kGLd + j];            // warp-uniform address: broadcast
-                acc[r][0] = fmaf(w, xv.x, acc[r][0]); acc[r][1] = fmaf(w, xv.y, acc[r][1]);
-                acc[r][2] = fmaf(w, xv.z, acc[r][2]); acc[r][3] = fmaf(w, xv.w, acc[r][3]);
+            for (int jj = 0; jj < 4; ++jj) xv[jj] = *reinterpret_cast<const float4 *>(xs + (j + jj) * kXsLd + cq * 4);
+#pragma unroll
+            for (int r = 0; r < kRpg; ++r) {
+                const float4 w = *reinterpret_cast<const float4 *>(g + (rg * kRpg + r) * kGLd + j);
+                acc[r][0] = fmaf(w.x, xv[0].x, acc[r][0]); acc[r][1] = fmaf(w.x, xv[0].y, acc[r][1]);
+                acc[r][2] = fmaf(w.x, xv[0].z, acc[r][2]); acc[r][3] = fmaf(w.x, xv[0].w, acc[r][3]);
+                acc[r][0] = fmaf(w.y, xv[1].x, acc[r][0]); acc[r][1] = fmaf(w.y, xv[1].y, acc[r][1]);
+                acc[r][2] = fmaf(w.y, xv[1].z, acc[r][2]); acc[r][3] = fmaf(w.y, xv[1].w, acc[r][3]);
+                acc[r][0] = fmaf(w.z, xv[2].x, acc[r][0]); acc[r][1] = fmaf(w.z, xv[2].y, acc[r][1]);
+                acc[r][2] = fmaf(w.z, xv[2].z, acc[r][2]); acc[r][3] = fmaf(w.z, xv[2].w, acc[r][3]);
+                acc[r][0] = fmaf(w.w, xv[3].x, acc[r][0]); acc[r][1] = fmaf(w.w, xv[3].y, acc[r][1]);
+                acc[r][2] = fmaf(w.w, xv[3].z, acc[r][2]); acc[r][3] = fmaf(w.w, xv[3].w, acc[r][3]);
             }
         }
 #pragma unroll
-        for (int r = 0; r < NT; ++r) {
-            const int row = rg * NT + r;
+        for (int r = 0; r < kRpg; ++r) {
+            const int row = rg * kRpg + r;
             if (row < V) {
                 float v0 = acc[r][0], v1 = acc[r][1], v2 = acc[r][2], v3 = acc[r][3];
                 __nv_bfloat16 *dst = a.y_planes + (row0 + row) * C + c0 + cq * 4;
@@ -305,8 +348,7 @@ graph_kernel(GraphArgs a) {
                 }
             }
         }
-        __syncthreads();
-    }
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -401,7 +443,7 @@ static int check_params(const agrl_head_params *p) {
 
 template <int NT>
 static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
-    const size_t smem = (static_cast<size_t>(4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
+    const size_t smem = (static_cast<size_t>(2 * 4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
     AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     graph_kernel<NT><<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
     AGRL_LAUNCH_CHECK(st, "graph");
@@ -483,17 +525,17 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     // 2. graph layers
     const int64_t rows = batch * V;
     CUtensorMap map_y, map_w;
-    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, hwk.y_planes, rows, C, p->split))) return rc;
+    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, hwk.y_planes, rows, C, p->split, gemm::BM))) return rc;
     int cur = 0;
     for (int l = 0; l < L; ++l) {
         GraphArgs ga{hwk.x[cur], adj, hwk.y_planes, rows * C, V, C, p->split, p->use_pose, p->learn_graph};
         if (V == 56) rc = launch_graph<14>(ga, batch, st); else rc = launch_graph<16>(ga, batch, st);
         if (rc) return rc;
-        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split))) return rc;
+        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, p->split == AGRL_SPLIT_BF16X3 ? 128 : 256))) return rc;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : hwk.x[cur ^ 1];
         gemm::EpiGraphLayer epi{hwk.x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope};
-        if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
-        else rc = gemm::launch_split_gemm<2>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        else rc = gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
         if (rc) return rc;
         if (dst == nodes_out) { hwk.x[cur ^ 1] = nodes_out; }
         cur ^= 1;

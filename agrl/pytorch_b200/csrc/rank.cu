@@ -388,10 +388,22 @@ rank_market_finish_kernel(MarketArgs a, int32_t *hist /*[rank_len+1], zeroed her
             cmc_out[r] = __fdiv_rn(static_cast<float>(sum), fvalid);
         }
     }
-    if (tid == 0) {
-        float acc = 0.f;
+    // mAP: fp32 sum in query order (rank_cy.pyx:236-239).  The chain is sequential by definition;
+    // blocks of ap are staged in shared memory by the whole CTA so the one adding thread never
+    // waits on global memory.
+    __shared__ float s_ap[4096];
+    float acc = 0.f;
+    for (int base = 0; base < nq; base += 4096) {
+        __syncthreads();
+        for (int i = tid; i < 4096 && base + i < nq; i += nthr) s_ap[i] = a.ap[base + i];
+        __syncthreads();
+        if (tid == 0) {
+            const int n = nq - base < 4096 ? nq - base : 4096;
 #pragma unroll 8
-        for (int q = 0; q < nq; ++q) acc = __fadd_rn(acc, a.ap[q]);     // invalid queries hold +0
+            for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, s_ap[i]);   // invalid queries hold +0
+        }
+    }
+    if (tid == 0) {
         *map_out = __fdiv_rn(acc, fvalid);
         if (num_valid_out) *num_valid_out = nvalid;
     }
@@ -439,32 +451,48 @@ __device__ __forceinline__ void mars_count_good(const MarsArgs &a, int pid, int 
 
 // Running top-K of one row: candidates below the threshold (K-th smallest key so far) go to a
 // shared buffer, which is sorted and cut back to K whenever the next tile could overflow it.
-// On return buf[0..valid) holds the min(K, n) smallest keys in order; returns valid.
+// The first tile is short (one element per thread) so that a cheap sort establishes a threshold
+// early; with it only ~K*ln(n/256) later elements ever reach the buffer.  Sorts cover just the
+// occupied power-of-two prefix.  On return buf[0..valid) holds the min(K, n) smallest keys in order.
 __device__ __forceinline__ int mars_select_topk(const float *__restrict__ row, int ng, int K, int L,
                                                 uint64_t *buf, int *s_cnt, unsigned long long *s_thr, int tid) {
-    for (int base = 0; base < ng; base += kMarsTile) {
+    int base = 0;
+    bool first = true;
+    while (base < ng) {
         const uint64_t thr = *s_thr;
-        const int j = base + tid * 4;               // thread t owns 4 consecutive elements of the tile
-        float d[4];
-        int n_here = 0;
-        if (j + 3 < ng && ((reinterpret_cast<uintptr_t>(row + j) & 15u) == 0)) {
-            const float4 x = __ldg(reinterpret_cast<const float4 *>(row + j));
-            d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w; n_here = 4;
+        const int tile = (first && K <= kRankThreads / 2) ? kRankThreads : kMarsTile;
+        if (tile == kRankThreads) {
+            const int j = base + tid;
+            if (j < ng) {
+                const uint64_t key = rank_key(row[j], static_cast<uint32_t>(j));
+                if (key < thr) buf[atomicAdd(s_cnt, 1)] = key;
+            }
         } else {
-            for (int k = 0; k < 4; ++k) if (j + k < ng) { d[k] = row[j + k]; n_here = k + 1; }
+            const int j = base + tid * 4;               // thread t owns 4 consecutive elements of the tile
+            float d[4];
+            int n_here = 0;
+            if (j + 3 < ng && ((reinterpret_cast<uintptr_t>(row + j) & 15u) == 0)) {
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(row + j));
+                d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w; n_here = 4;
+            } else {
+                for (int k = 0; k < 4; ++k) if (j + k < ng) { d[k] = row[j + k]; n_here = k + 1; }
+            }
+            for (int k = 0; k < n_here; ++k) {
+                const uint64_t key = rank_key(d[k], static_cast<uint32_t>(j + k));
+                if (key < thr) buf[atomicAdd(s_cnt, 1)] = key;    // *s_cnt <= L - kMarsTile before a tile
+            }
         }
-        for (int k = 0; k < n_here; ++k) {
-            const uint64_t key = rank_key(d[k], static_cast<uint32_t>(j + k));
-            if (key < thr) buf[atomicAdd(s_cnt, 1)] = key;        // *s_cnt <= L - tile before the tile
-        }
+        base += tile;
         __syncthreads();
         const int cnt = *s_cnt;
         __syncthreads();                   // everyone holds the same cnt before anyone appends again
-        const bool last = (base + kMarsTile >= ng);
-        if (cnt > L - kMarsTile || last) {
-            for (int i = cnt + tid; i < L; i += kRankThreads) buf[i] = kKeyMax;
+        const bool last = (base >= ng);
+        if (cnt > L - kMarsTile || last || first) {
+            int n2 = 2;
+            while (n2 < cnt) n2 <<= 1;                 // cnt <= L and L is a power of two
+            for (int i = cnt + tid; i < n2; i += kRankThreads) buf[i] = kKeyMax;
             __syncthreads();
-            bitonic_sort_u64<false>(buf, L, tid, kRankThreads);
+            bitonic_sort_u64<false>(buf, n2, tid, kRankThreads);
             if (tid == 0) {
                 const int keep = cnt < K ? cnt : K;
                 *s_cnt = keep;
@@ -472,6 +500,7 @@ __device__ __forceinline__ int mars_select_topk(const float *__restrict__ row, i
             }
             __syncthreads();
         }
+        first = false;
     }
     return *s_cnt;
 }
@@ -604,9 +633,10 @@ rank_mars_merge_kernel(MarsMergeArgs a) {
 }
 
 // numpy's pairwise float64 summation (what np.mean runs on the ap vector, rank.py:176):
-// blocks of <= 128 elements are summed with eight interleaved partial sums and a fixed tree, larger
-// ranges split at n/2 rounded down to a multiple of 8.  Evaluated post-order with an explicit stack
-// (device recursion would overflow the default 1 KiB thread stack).
+// ranges of <= 128 elements ("leaves") are summed with eight interleaved partial sums and a fixed
+// tree, larger ranges split at n/2 rounded down to a multiple of 8, left + right.  The split tree
+// only depends on n, so the leaves are evaluated in parallel (one thread each) and a single thread
+// then replays the tree over the leaf sums -- same additions, same order, same bits.
 __device__ double pairwise_leaf_f64(const double *x, int n) {
     if (n < 8) {
         double r = 0.0;
@@ -627,12 +657,16 @@ __device__ double pairwise_leaf_f64(const double *x, int n) {
     return res;
 }
 
-__device__ double pairwise_sum_f64(const double *x, int n) {
+// Post-order walk of the split tree with an explicit stack (device recursion would overflow the
+// default 1 KiB thread stack).  kEnumerate: record the leaves (offset, length) in visiting order;
+// otherwise: combine the precomputed leaf sums.  Returns the number of leaves / leaves consumed.
+template <bool kEnumerate>
+__device__ int pairwise_walk(int n, int2 *leaves, const double *leaf_sum, int max_leaves, double *result) {
     constexpr int kDepth = 40;
-    int off[kDepth], len[kDepth], state[kDepth];     // state: 0 fresh, 1 waiting for left, 2 waiting for right
+    int off[kDepth], len[kDepth], state[kDepth];     // state: 1 waiting for left, 2 waiting for right
     double left[kDepth];
-    int sp = 0;
-    off[0] = 0; len[0] = n; state[0] = 0; sp = 1;
+    int sp = 1, nleaf = 0;
+    off[0] = 0; len[0] = n; state[0] = 0;
     double ret = 0.0;
     bool have_ret = false;
     while (sp > 0) {
@@ -650,7 +684,9 @@ __device__ double pairwise_sum_f64(const double *x, int n) {
                 --sp;
             }
         } else if (len[t] <= 128) {
-            ret = pairwise_leaf_f64(x + off[t], len[t]);
+            if (kEnumerate) { if (nleaf < max_leaves) leaves[nleaf] = make_int2(off[t], len[t]); }
+            else ret = leaf_sum[nleaf];
+            ++nleaf;
             have_ret = true;
             --sp;
         } else {                                      // descend left
@@ -659,19 +695,29 @@ __device__ double pairwise_sum_f64(const double *x, int n) {
             off[sp] = off[t]; len[sp] = n2; state[sp] = 0; ++sp;
         }
     }
-    return ret;
+    if (!kEnumerate) *result = ret;
+    return nleaf;
 }
+
+constexpr int kMaxLeaves = 2048;             // covers num_q up to ~130 000 in one pass
 
 __global__ void __launch_bounds__(1024)
 rank_mars_finish_kernel(MarsArgs a, int32_t *hist /*[max_rank+1]*/, double *cmc_out, double *map_out) {
+    __shared__ int2 s_leaf[kMaxLeaves];
+    __shared__ double s_sum[kMaxLeaves];
+    __shared__ int s_nleaf;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int nq = a.num_q, R = a.max_rank;
     for (int r = tid; r <= R; r += nthr) hist[r] = 0;
+    if (tid == 32) s_nleaf = pairwise_walk<true>(nq, s_leaf, nullptr, kMaxLeaves, nullptr);
     __syncthreads();
     for (int q = tid; q < nq; q += nthr) {
         const int fp = a.first_pos[q];
         atomicAdd(&hist[fp < R ? fp : R], 1);
     }
+    const int nleaf = s_nleaf;
+    if (nleaf <= kMaxLeaves)
+        for (int l = tid; l < nleaf; l += nthr) s_sum[l] = pairwise_leaf_f64(a.ap + s_leaf[l].x, s_leaf[l].y);
     __syncthreads();
     if (tid < 32) {
         int carry = 0;
@@ -687,7 +733,43 @@ rank_mars_finish_kernel(MarsArgs a, int32_t *hist /*[max_rank+1]*/, double *cmc_
             carry += __shfl_sync(0xffffffffu, x, 31);
         }
     }
-    if (tid == 32) *map_out = __ddiv_rn(pairwise_sum_f64(a.ap, nq), static_cast<double>(nq));
+    if (tid == 32) {
+        double total = 0.0;
+        if (nleaf <= kMaxLeaves) {
+            pairwise_walk<false>(nq, nullptr, s_sum, kMaxLeaves, &total);
+        } else {
+            // very large num_q: sequential leaves (still the same tree)
+            total = 0.0;
+            int2 one;
+            // fall back to evaluating leaves on the fly
+            constexpr int kDepth = 40;
+            int off[kDepth], len[kDepth], state[kDepth];
+            double left[kDepth];
+            int sp = 1;
+            off[0] = 0; len[0] = nq; state[0] = 0;
+            double ret = 0.0; bool have_ret = false;
+            while (sp > 0) {
+                const int t = sp - 1;
+                if (have_ret) {
+                    have_ret = false;
+                    if (state[t] == 1) {
+                        left[t] = ret; state[t] = 2;
+                        int n2 = len[t] / 2; n2 -= n2 % 8;
+                        off[sp] = off[t] + n2; len[sp] = len[t] - n2; state[sp] = 0; ++sp;
+                    } else { ret = __dadd_rn(left[t], ret); have_ret = true; --sp; }
+                } else if (len[t] <= 128) {
+                    ret = pairwise_leaf_f64(a.ap + off[t], len[t]); have_ret = true; --sp;
+                } else {
+                    state[t] = 1;
+                    int n2 = len[t] / 2; n2 -= n2 % 8;
+                    off[sp] = off[t]; len[sp] = n2; state[sp] = 0; ++sp;
+                }
+            }
+            total = ret;
+            (void)one;
+        }
+        *map_out = __ddiv_rn(total, static_cast<double>(nq));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
