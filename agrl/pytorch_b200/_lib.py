@@ -57,6 +57,9 @@ _SIGNATURES = {
     'agrl_distance_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64, c_int]),
     'agrl_distance_dev': (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                   c_vp, c_sz, c_vp]),
+    'agrl_distance_operand_bytes': (c_sz, [c_i64, c_i64, c_int]),
+    'agrl_distance_prepare_operand_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_sz, c_vp]),
+    'agrl_distance_prepared_dev': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
     'agrl_distance_host': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int]),
     'agrl_head_prepared_bytes': (c_sz, [ctypes.POINTER(HeadParams)]),
     'agrl_head_prepare_dev': (c_int, [ctypes.POINTER(HeadParams), c_vp, c_sz, c_vp]),

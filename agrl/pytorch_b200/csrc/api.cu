@@ -24,6 +24,8 @@ struct Profiler {
 };
 static thread_local Profiler tl_prof;
 
+bool profiling_active() { return tl_prof.on; }
+
 void after_launch(cudaStream_t st, const char *name) {
     ++tl_launches;
     Profiler &p = tl_prof;

@@ -9,31 +9,73 @@
 
 namespace agrl {
 
-struct DistWorkspace {
-    __nv_bfloat16 *q_planes, *g_planes;
-    float *qn, *gn;
+// One prepared operand: bf16 planes [P][rows][K_pad] followed by the per-row squared norms.
+struct Operand {
+    __nv_bfloat16 *planes;
+    float *sumsq;
     size_t bytes;
 };
 
-static DistWorkspace carve_dist(void *ws, int64_t nq, int64_t ng, int64_t dim, int P) {
-    Carver c(ws);
-    DistWorkspace w;
-    const int64_t kp = gemm::pad_k(dim);
-    w.q_planes = c.take<__nv_bfloat16>(static_cast<size_t>(P) * nq * kp);
-    w.g_planes = c.take<__nv_bfloat16>(static_cast<size_t>(P) * ng * kp);
-    w.qn = c.take<float>(nq);
-    w.gn = c.take<float>(ng);
-    w.bytes = c.total();
-    return w;
+static Operand carve_operand(void *buf, int64_t rows, int64_t dim, int P) {
+    Carver c(buf);
+    Operand o;
+    o.planes = c.take<__nv_bfloat16>(static_cast<size_t>(P) * rows * gemm::pad_k(dim));
+    o.sumsq = c.take<float>(rows);
+    o.bytes = c.total();
+    return o;
 }
+
+static bool split_ok(int split) { return split == AGRL_SPLIT_BF16X2 || split == AGRL_SPLIT_BF16X3; }
+static bool metric_ok(int metric) { return metric == AGRL_METRIC_EUCLIDEAN || metric == AGRL_METRIC_COSINE; }
 
 }  // namespace agrl
 
 using namespace agrl;
 
+extern "C" size_t agrl_distance_operand_bytes(int64_t rows, int64_t dim, int split) {
+    if (rows < 0 || dim < 1 || !split_ok(split)) return 0;
+    return carve_operand(nullptr, rows, dim, split).bytes;
+}
+
+extern "C" int agrl_distance_prepare_operand_dev(const float *x, int64_t ld, int64_t rows, int64_t dim,
+                                                 int metric, int split, void *operand, size_t operand_bytes,
+                                                 void *stream) {
+    if (!x || rows < 0 || dim < 1 || ld < dim || !metric_ok(metric) || !split_ok(split)) return AGRL_E_INVALID;
+    if (rows > (1 << 30) || dim > (1 << 24)) return AGRL_E_UNSUPPORTED;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    Operand o = carve_operand(operand, rows, dim, split);
+    if (!operand || operand_bytes < o.bytes) return AGRL_E_WORKSPACE;
+    const int normalize = (metric == AGRL_METRIC_COSINE);
+    gemm::SplitArgs sa{x, ld, o.planes, normalize ? nullptr : o.sumsq, rows, static_cast<int>(dim),
+                       static_cast<int>(gemm::pad_k(dim)), split, normalize};
+    return gemm::launch_split_planes(sa, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int agrl_distance_prepared_dev(const void *q_operand, int64_t num_q, const void *g_operand, int64_t num_g,
+                                          int64_t dim, int metric, int split, float *out, int64_t ld_out, void *stream) {
+    if (!q_operand || !g_operand || !out || num_q < 0 || num_g < 0 || dim < 1 || ld_out < num_g) return AGRL_E_INVALID;
+    if (!metric_ok(metric) || !split_ok(split)) return AGRL_E_INVALID;
+    if (num_q > (1 << 30) || num_g > (1 << 30) || dim > (1 << 24)) return AGRL_E_UNSUPPORTED;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    if (num_q == 0 || num_g == 0) return AGRL_OK;
+    Operand q = carve_operand(const_cast<void *>(q_operand), num_q, dim, split);
+    Operand g = carve_operand(const_cast<void *>(g_operand), num_g, dim, split);
+    const int kp = static_cast<int>(gemm::pad_k(dim));
+    CUtensorMap map_q, map_g;
+    if ((rc = gemm::make_plane_tensor_map(&map_q, q.planes, num_q, kp, split, gemm::BM, num_q))) return rc;
+    if ((rc = gemm::make_plane_tensor_map(&map_g, g.planes, num_g, kp, split, 128, num_g))) return rc;
+    gemm::EpiDistance epi{q.sumsq, g.sumsq, out, ld_out, metric};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (split == AGRL_SPLIT_BF16X3)
+        return gemm::launch_split_gemm<3, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
+    return gemm::launch_split_gemm<2, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
+}
+
 extern "C" size_t agrl_distance_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int split) {
-    if (num_q < 0 || num_g < 0 || dim < 1 || (split != AGRL_SPLIT_BF16X2 && split != AGRL_SPLIT_BF16X3)) return 0;
-    return carve_dist(nullptr, num_q, num_g, dim, split).bytes;
+    if (num_q < 0 || num_g < 0 || dim < 1 || !split_ok(split)) return 0;
+    return agrl_distance_operand_bytes(num_q, dim, split) + agrl_distance_operand_bytes(num_g, dim, split);
 }
 
 extern "C" int agrl_distance_dev(const float *q, int64_t ld_q, const float *g, int64_t ld_g,
@@ -41,29 +83,14 @@ extern "C" int agrl_distance_dev(const float *q, int64_t ld_q, const float *g, i
                                  int metric, int split, void *ws, size_t ws_bytes, void *stream) {
     if (!q || !g || !out) return AGRL_E_INVALID;
     if (num_q < 0 || num_g < 0 || dim < 1 || ld_q < dim || ld_g < dim || ld_out < num_g) return AGRL_E_INVALID;
-    if (metric != AGRL_METRIC_EUCLIDEAN && metric != AGRL_METRIC_COSINE) return AGRL_E_INVALID;
-    if (split != AGRL_SPLIT_BF16X2 && split != AGRL_SPLIT_BF16X3) return AGRL_E_INVALID;
-    if (num_q > (1 << 30) || num_g > (1 << 30) || dim > (1 << 24)) return AGRL_E_UNSUPPORTED;
+    if (!metric_ok(metric) || !split_ok(split)) return AGRL_E_INVALID;
     int rc = agrl_device_ok();
     if (rc) return rc;
     if (num_q == 0 || num_g == 0) return AGRL_OK;
-    DistWorkspace w = carve_dist(ws, num_q, num_g, dim, split);
-    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int kp = static_cast<int>(gemm::pad_k(dim));
-    const int normalize = (metric == AGRL_METRIC_COSINE);
-
-    gemm::SplitArgs sq{q, ld_q, w.q_planes, normalize ? nullptr : w.qn, num_q, static_cast<int>(dim), kp, split, normalize};
-    gemm::SplitArgs sg{g, ld_g, w.g_planes, normalize ? nullptr : w.gn, num_g, static_cast<int>(dim), kp, split, normalize};
-    if ((rc = gemm::launch_split_planes(sq, st))) return rc;
-    if ((rc = gemm::launch_split_planes(sg, st))) return rc;
-
-    CUtensorMap map_q, map_g;
-    if ((rc = gemm::make_plane_tensor_map(&map_q, w.q_planes, num_q, kp, split, gemm::BM))) return rc;
-    if ((rc = gemm::make_plane_tensor_map(&map_g, w.g_planes, num_g, kp, split, 128))) return rc;
-
-    gemm::EpiDistance epi{w.qn, w.gn, out, ld_out, metric};
-    if (split == AGRL_SPLIT_BF16X3)
-        return gemm::launch_split_gemm<3, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
-    return gemm::launch_split_gemm<2, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(num_g), kp, epi, st);
+    const size_t qb = agrl_distance_operand_bytes(num_q, dim, split), gb = agrl_distance_operand_bytes(num_g, dim, split);
+    if (!ws || ws_bytes < qb + gb) return AGRL_E_WORKSPACE;
+    char *qo = static_cast<char *>(ws), *go = qo + qb;
+    if ((rc = agrl_distance_prepare_operand_dev(q, ld_q, num_q, dim, metric, split, qo, qb, stream))) return rc;
+    if ((rc = agrl_distance_prepare_operand_dev(g, ld_g, num_g, dim, metric, split, go, gb, stream))) return rc;
+    return agrl_distance_prepared_dev(qo, num_q, go, num_g, dim, metric, split, out, ld_out, stream);
 }

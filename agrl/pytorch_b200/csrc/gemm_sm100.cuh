@@ -56,8 +56,12 @@ template <int P, int BN, bool kSplit, bool kDirect = false> struct Config {
     static constexpr int kAccCols = kSplit ? 2 * BN : BN;               // columns per accumulator stage
     static constexpr int kNumPairs = (P == 3) ? 6 : (P == 2 ? 3 : 1);
     static_assert(kStages >= 2 && kAccStages * kAccCols <= kTmemCols, "resources");
+    static constexpr int kEpiSmem = kDirect ? 0 : kEpiBytes;
+    // Register cap: leaves room in the register file for a co-resident memory-bound CTA of another
+    // stream (the head overlaps its pooling with this kernel; 384 x 104 = 40 K of the 64 K registers).
+    static constexpr int kMaxRegs = kDirect ? 104 : 168;
     // dynamic smem: stages | epilogue staging | barriers ; +1024 for manual alignment
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 1024;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmem + 256 + 1024;
 };
 
 // plane pairs, least significant products first
@@ -228,7 +232,7 @@ struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <int P, int BN, bool kSplit, class Epi>
-__global__ void __launch_bounds__((Config<P, BN, kSplit, Epi::kDirect>::kThreads), 1)
+__global__ void __maxnreg__((Config<P, BN, kSplit, Epi::kDirect>::kMaxRegs))
 split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   int M, int N, int k_pad, Epi epi) {
     using Cfg = Config<P, BN, kSplit, Epi::kDirect>;
@@ -238,7 +242,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
     float *epi_buf = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes + kEpiBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiSmem);
     // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * Cfg::kStages;
@@ -415,7 +419,9 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // ---- host side -----------------------------------------------------------------------------------
 // 3-D tensor map over planes [P][rows][k_pad] of bf16: box = (BK, box_rows, 1), 128-byte swizzle.
 // box_rows = BM for the A operand, the kernel's BN for the B operand.
-int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows);
+// plane_rows = rows between consecutive planes (>= rows when the map covers a row slice of the planes).
+int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows,
+                          int64_t plane_rows);
 
 template <int P, int BN, bool kSplit, class Epi>
 int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,

@@ -97,11 +97,12 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows) {
+int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows,
+                          int64_t plane_rows) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return AGRL_E_NO_DEVICE;
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(k_pad), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(P)};
-    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(k_pad) * 2, static_cast<cuuint64_t>(rows) * k_pad * 2};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(k_pad) * 2, static_cast<cuuint64_t>(plane_rows) * k_pad * 2};
     const cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(planes), dims, strides, box, estr,

@@ -72,3 +72,43 @@ def compute_distance_matrix(input1, input2, metric='euclidean', split=_lib.SPLIT
                                          out.data_ptr(), out.stride(0), m, n, d, _METRICS[metric], split,
                                          ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream))
     return out
+
+
+class PreparedOperand(object):
+    """A feature matrix already split into the GEMM's bf16 operand planes (+ norms) on its device.
+
+    Retrieval against a fixed gallery prepares the gallery once and reuses it for every query batch
+    (``agrl_distance_prepare_operand_dev`` / ``agrl_distance_prepared_dev``)."""
+
+    def __init__(self, x, metric='euclidean', split=_lib.SPLIT_BF16X3):
+        assert isinstance(x, torch.Tensor) and x.dim() == 2 and x.is_cuda
+        if metric not in _METRICS:
+            raise ValueError('Unknown distance metric: {}. '
+                             'Please choose either "euclidean" or "cosine"'.format(metric))
+        lib = _lib.require_device()
+        x = x.detach().to(torch.float32)
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        self.rows, self.dim, self.metric, self.split, self.device = x.size(0), x.size(1), metric, split, x.device
+        nbytes = lib.agrl_distance_operand_bytes(self.rows, self.dim, split)
+        self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.agrl_distance_prepare_operand_dev(
+                x.data_ptr(), x.stride(0), self.rows, self.dim, _METRICS[metric], split, self.buf.data_ptr(),
+                nbytes, torch.cuda.current_stream(x.device).cuda_stream))
+
+
+def distance_prepared(q, g, out=None):
+    """Distance matrix between two PreparedOperand (same metric, split, dim, device)."""
+    assert isinstance(q, PreparedOperand) and isinstance(g, PreparedOperand)
+    assert (q.metric, q.split, q.dim, q.device) == (g.metric, g.split, g.dim, g.device)
+    lib = _lib.require_device()
+    if out is None:
+        out = torch.empty(q.rows, g.rows, dtype=torch.float32, device=q.device)
+    assert out.shape == (q.rows, g.rows) and out.stride(1) == 1 and out.dtype == torch.float32
+    if q.rows and g.rows:
+        with torch.cuda.device(q.device):
+            _lib.check(lib.agrl_distance_prepared_dev(
+                q.buf.data_ptr(), q.rows, g.buf.data_ptr(), g.rows, q.dim, _METRICS[q.metric], q.split,
+                out.data_ptr(), out.stride(0), torch.cuda.current_stream(q.device).cuda_stream))
+    return out

@@ -176,6 +176,17 @@ AGRL_API int agrl_distance_dev(const float *q_dev, int64_t ld_q, const float *g_
                       int64_t num_q, int64_t num_g, int64_t dim, int metric, int split,
                       void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Retrieval form: an operand (e.g. the gallery) is prepared once -- bf16 planes + norms, or planes
+ * of the L2-normalised rows for the cosine metric -- and reused for many query batches.
+ * agrl_distance_dev(q, g) == prepare(q) + prepare(g) + agrl_distance_prepared_dev. */
+AGRL_API size_t agrl_distance_operand_bytes(int64_t rows, int64_t dim, int split);
+AGRL_API int agrl_distance_prepare_operand_dev(const float *x_dev, int64_t ld, int64_t rows, int64_t dim,
+                                      int metric, int split, void *operand_dev, size_t operand_bytes,
+                                      void *stream);
+AGRL_API int agrl_distance_prepared_dev(const void *q_operand_dev, int64_t num_q,
+                               const void *g_operand_dev, int64_t num_g, int64_t dim, int metric, int split,
+                               float *out_dev, int64_t ld_out, void *stream);
+
 AGRL_API int agrl_distance_host(const float *q_host, const float *g_host, float *out_host,
                        int64_t num_q, int64_t num_g, int64_t dim, int metric, int split);
 
