@@ -525,13 +525,13 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     // 2. graph layers
     const int64_t rows = batch * V;
     CUtensorMap map_y, map_w;
-    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, hwk.y_planes, rows, C, p->split, gemm::BM))) return rc;
+    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, hwk.y_planes, rows, C, p->split, gemm::BM, rows))) return rc;
     int cur = 0;
     for (int l = 0; l < L; ++l) {
         GraphArgs ga{hwk.x[cur], adj, hwk.y_planes, rows * C, V, C, p->split, p->use_pose, p->learn_graph};
         if (V == 56) rc = launch_graph<14>(ga, batch, st); else rc = launch_graph<16>(ga, batch, st);
         if (rc) return rc;
-        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, p->split == AGRL_SPLIT_BF16X3 ? 128 : 256))) return rc;
+        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, p->split == AGRL_SPLIT_BF16X3 ? 128 : 256, C))) return rc;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : hwk.x[cur ^ 1];
         gemm::EpiGraphLayer epi{hwk.x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope};
         if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);

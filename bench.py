@@ -164,7 +164,8 @@ def run_b200(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=180))
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     lib = _lib.require_device()
@@ -229,12 +230,12 @@ def run_b200(args):
         value = world * J / (ms_per_step * 1e-3)
 
         # ---- kernel timeline of one more step (CUDA events after every kernel, same stream) ------
-        timeline = None
-        if rank == 0:
-            torch.cuda.synchronize(dev)
-            with _lib.profile(stream.cuda_stream) as prof:
-                head_pass(); eval_pass()
-            timeline = prof.totals()
+        # (every rank runs the pass -- eval_pass holds collectives at N > 1 -- rank 0's timeline is reported)
+        barrier()
+        with _lib.profile(stream.cuda_stream) as prof:
+            head_pass(); eval_pass()
+        timeline = prof.totals()
+        barrier()
 
         # ---- end to end through host buffers -------------------------------------------------
         e2e = None
@@ -438,7 +439,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--pool', type=int, default=256, help='tracklets in the resident input pool (4.3 GB at 256)')
+    ap.add_argument('--pool', type=int, default=882, help='tracklets per head call = resident input pool (14.8 GB at 882)')
     ap.add_argument('--dist-metric', default='euclidean', choices=['euclidean', 'cosine'])
     ap.add_argument('--e2e-pool', type=int, default=128)
     ap.add_argument('--e2e-chunk', type=int, default=64)

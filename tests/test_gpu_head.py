@@ -116,31 +116,3 @@ def test_training_mode_and_cpu_inputs_fail_loudly():
     with pytest.raises(RuntimeError):
         model.eval().cpu()(x, adj)
 
-
-def test_sub_batched_overlapped_path_matches_oracle(tmp_path):
-    """force tiny sub-batches (AGRL_HEAD_SUB=2) so the side-stream pooling / per-sub-batch slicing of
-    agrl_head_forward_dev is exercised at test size; separate process because the knob is read once"""
-    import subprocess
-    import sys
-    code = r'''
-import sys, torch
-sys.path.insert(0, %r); sys.path.insert(0, %r)
-from oracle import head as ohead
-from agrl.pytorch_b200 import synthetic as synth
-from test_gpu_head import make_model, rel_err
-B, S = 7, 8
-x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=60, scale=2.0)
-adj = synth.pose_adjacency(B, S, 7, seed=61)
-wts = synth.head_weights(2048, 2, seed=62)
-model = make_model(wts)
-ref, _, nref = ohead.head_forward(x1, x2, adj, wts, dtype=torch.float64, return_nodes=True)
-with torch.no_grad():
-    for _ in range(3):                      # repeated calls reuse the side stream / events
-        out, nodes = model.head(x1.cuda(), x2.cuda(), adj.cuda(), S, return_nodes=True)
-e = rel_err(out.cpu(), ref) + rel_err(nodes.cpu(), nref)
-print('ERR', *e)
-assert max(e) < 1e-4, e
-''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, AGRL_HEAD_SUB='2')
-    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
