@@ -42,11 +42,15 @@ constexpr int kEpiBytes = 4 * 32 * kEpiPad * 4;       // transpose staging of th
 // BN     tile width: 128 or 256 (UMMA 128 x BN x 16)
 // kSplit keep the dominant a0.b0 sum and the correction products in separate TMEM accumulators
 //        (needs 2*BN columns per stage, hence BN = 128)
-template <int P, int BN, bool kSplit, bool kDirect = false> struct Config {
+// kChunkKb > 0: the accumulator is drained every kChunkKb k-blocks and summed in registers with
+//        round-to-nearest fp32 adds (the tensor core truncates on accumulate; short chains keep that
+//        bias below the fp32 rounding of the result).  Needs 8 epilogue warps (64 sums per thread).
+template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0> struct Config {
     // epilogue flavour: kDirect = registers -> 16-byte global accesses, 8 warps (two per TMEM lane
     // quarter, half the columns each), no smem; otherwise 4 warps and a padded smem transpose so
     // that stores are coalesced along rows of arbitrary alignment.
-    static constexpr int kEpiWarps = kDirect ? 8 : 4;
+    static_assert(kChunkKb == 0 || (!kDirect && BN == 128), "chunked accumulation: 128-wide tiles, smem-transposed stores");
+    static constexpr int kEpiWarps = (kDirect || kChunkKb > 0) ? 8 : 4;
     static constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
     static_assert(BN == 128 || BN == 256, "tile width");
     static_assert(!kSplit || BN == 128, "two accumulators of 256 columns do not fit twice in TMEM");
@@ -56,10 +60,11 @@ template <int P, int BN, bool kSplit, bool kDirect = false> struct Config {
     static constexpr int kAccCols = kSplit ? 2 * BN : BN;               // columns per accumulator stage
     static constexpr int kNumPairs = (P == 3) ? 6 : (P == 2 ? 3 : 1);
     static_assert(kStages >= 2 && kAccStages * kAccCols <= kTmemCols, "resources");
-    static constexpr int kEpiSmem = kDirect ? 0 : kEpiBytes;
+    static constexpr int kEpiSmem = kDirect ? 0 : (kEpiWarps / 4) * kEpiBytes;
     // Register cap: leaves room in the register file for a co-resident memory-bound CTA of another
     // stream (the head overlaps its pooling with this kernel; 384 x 104 = 40 K of the 64 K registers).
     static constexpr int kMaxRegs = kDirect ? 104 : 168;
+    static constexpr int kChunk = kChunkKb;
     // dynamic smem: stages | epilogue staging | barriers ; +1024 for manual alignment
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmem + 256 + 1024;
 };
@@ -165,6 +170,7 @@ constexpr uint32_t make_idesc(int m, int n) {
 struct EpiDistance {            // distance.py:59-73 / :76-89
     static constexpr const char *kName = "gemm_distance";
     static constexpr bool kDirect = false;      // rows of arbitrary alignment: coalesce through smem
+    static constexpr int kChunkKb = 4;          // drain the accumulator every 256 k (fp32-accurate sums)
     const float *qn, *gn;       // squared norms (euclidean); unused for cosine
     float *out;
     int64_t ld;
@@ -184,6 +190,7 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
 struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) + (1-gamma) * x
     static constexpr const char *kName = "gemm_graph_layer";
     static constexpr bool kDirect = true;       // C % 4 == 0 and 16-byte aligned rows: vector accesses
+    static constexpr int kChunkKb = 0;          // one accumulation over all of K
     // pull this thread's slice of the residual row into L2 before the accumulator is ready
     __device__ __forceinline__ void prefetch(int row, int col0, int ncols, bool valid) const {
         if (!valid) return;
@@ -232,10 +239,10 @@ struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <int P, int BN, bool kSplit, class Epi>
-__global__ void __maxnreg__((Config<P, BN, kSplit, Epi::kDirect>::kMaxRegs))
+__global__ void __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
 split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   int M, int N, int k_pad, Epi epi) {
-    using Cfg = Config<P, BN, kSplit, Epi::kDirect>;
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>;
     constexpr int kAccCols = Cfg::kAccCols;
     extern __shared__ unsigned char smem_dyn[];
     // 128B-swizzled tiles need 1024-byte alignment
@@ -254,6 +261,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = k_pad / BK;
+    const int chunk_kb = Cfg::kChunk > 0 ? Cfg::kChunk : num_kb;       // k-blocks per accumulator drain
     // Raster: the operand with FEWER tiles varies fastest, so the CTAs running at any moment share it
     // (L2-resident) while the larger operand streams through exactly once.
     const bool m_fast = tiles_m <= tiles_n;
@@ -306,61 +314,66 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================= MMA issuer =================
         constexpr uint32_t idesc = make_idesc(BM, BN);
         int stage = 0; uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);        // epilogue has drained this accumulator
-            tc_fence_after();
-            // Two accumulators per stage.  The tensor core truncates (round-toward-zero) on every
-            // accumulate, at the ulp of the running sum; keeping the small correction products out of
-            // the big a0.b0 sum spares it 5/6 (P=3) of those truncations, and the correction sum itself
-            // is ~2^-8 smaller, so its own truncation is negligible.
-            const uint32_t d_main = tmem_base + acc * kAccCols;
-            const uint32_t d_corr = kSplit ? d_main + BN : d_main;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(bar_full + 8 * stage, phase);            // TMA bytes have landed
+        int cit = 0;                                               // accumulator-drain counter (chunks)
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++cit) {
+                const int acc = cit & 1;
+                const uint32_t acc_phase = (cit >> 1) & 1;
+                const int kb_end = (kb0 + chunk_kb < num_kb) ? kb0 + chunk_kb : num_kb;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);    // epilogue has drained this accumulator
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t sb = sa + P * kTileBytesA;
+                // Two accumulators per stage when kSplit.  The tensor core truncates (round-toward-zero)
+                // on every accumulate, at the ulp of the running sum; keeping the small correction
+                // products out of the big a0.b0 sum spares it 5/6 (P=3) of those truncations, and the
+                // correction sum itself is ~2^-8 smaller, so its own truncation is negligible.
+                const uint32_t d_main = tmem_base + acc * kAccCols;
+                const uint32_t d_corr = kSplit ? d_main + BN : d_main;
+                for (int kb = kb0; kb < kb_end; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                        const uint32_t sb = sa + P * kTileBytesA;
+                        const int first = kb - kb0;                // 0 on the chunk's first k-block
 #pragma unroll
-                    for (int i = 0; i < Cfg::kNumPairs; ++i) {
-                        int pa, pb;
-                        pair_of(P, i, pa, pb);
-                        const uint64_t da = make_smem_desc(sa + pa * kTileBytesA);
-                        const uint64_t db = make_smem_desc(sb + pb * Cfg::kTileBytesB);
+                        for (int i = 0; i < Cfg::kNumPairs; ++i) {
+                            int pa, pb;
+                            pair_of(P, i, pa, pb);
+                            const uint64_t da = make_smem_desc(sa + pa * kTileBytesA);
+                            const uint64_t db = make_smem_desc(sb + pb * Cfg::kTileBytesB);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
-                            if (kSplit && i == Cfg::kNumPairs - 1)
-                                tc_mma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                            else
-                                tc_mma_bf16(d_corr, da + 2 * k, db + 2 * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
+                                if (kSplit && i == Cfg::kNumPairs - 1)
+                                    tc_mma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, (first | k) != 0 ? 1u : 0u);
+                                else
+                                    tc_mma_bf16(d_corr, da + 2 * k, db + 2 * k, idesc, (first | i | k) != 0 ? 1u : 0u);
+                            }
                         }
+                        tc_commit(bar_empty + 8 * stage);           // frees the smem stage when the MMAs retire
+                        if (kb == kb_end - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator (chunk) complete
                     }
-                    tc_commit(bar_empty + 8 * stage);               // frees the smem stage when the MMAs retire
-                    if (kb == num_kb - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
+                    __syncwarp();
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= kCtrlWarps) {
         // ================= epilogue =================
         const int ew = warp - kCtrlWarps;
         const int quarter = ew & 3;                                // == warp % 4: the TMEM lane quarter
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        int cit = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m0, n0;
             tile_origin(tile, m0, n0);
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
             const int row_base = m0 + quarter * 32;
-            const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
+            const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
             if constexpr (Epi::kDirect) {
                 // thread = one output row, 16-byte accesses straight from registers; warps 4-7 of the
                 // group take the upper half of the tile's columns
+                const int acc = cit & 1;
+                const uint32_t acc_phase = (cit >> 1) & 1;
+                const uint32_t tq = tlane + acc * kAccCols;
                 const int col_half = (ew >> 2) * (BN / 2);
                 const int row = row_base + lane;
                 epi.prefetch(row, n0 + col_half, BN / 2, row < M);     // residual tile -> L2 while the MMAs run
@@ -373,7 +386,59 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tmem_ld_wait();
                     if (row < M) epi.store_row32(row, n0 + col_half + c, N, r);
                 }
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                ++cit;
+            } else if constexpr (Cfg::kChunk > 0) {
+                // chunked accumulation: this warp owns 32 rows x 64 columns; every chunk's partial
+                // (main + correction) is added into registers with round-to-nearest
+                const int col_half = (ew >> 2) * (BN / 2);
+                float sum[BN / 2];
+#pragma unroll
+                for (int j = 0; j < BN / 2; ++j) sum[j] = 0.f;
+                for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++cit) {
+                    const int acc = cit & 1;
+                    const uint32_t acc_phase = (cit >> 1) & 1;
+                    const uint32_t tq = tlane + acc * kAccCols + col_half;
+                    mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < BN / 2; c += 32) {
+                        uint32_t r[32], rc[32];
+                        tmem_ld_32x32(tq + c, r);
+                        if (kSplit) tmem_ld_32x32(tq + BN + c, rc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float part = kSplit ? __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]))
+                                                      : __uint_as_float(r[j]);
+                            sum[c + j] = __fadd_rn(sum[c + j], part);
+                        }
+                    }
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                }
+                float *buf = epi_buf + ew * 32 * kEpiPad;
+#pragma unroll
+                for (int c = 0; c < BN / 2; c += 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) buf[lane * kEpiPad + j] = sum[c + j];
+                    __syncwarp();
+                    const int col = n0 + col_half + c + lane;
+                    if (col < N) {
+                        const typename Epi::Col cs = epi.col_state(col);
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const int row = row_base + rr;
+                            if (row < M) epi.store(row, col, buf[rr * kEpiPad + lane], cs);
+                        }
+                    }
+                    __syncwarp();
+                }
             } else {
+                const int acc = cit & 1;
+                const uint32_t acc_phase = (cit >> 1) & 1;
+                const uint32_t tq = tlane + acc * kAccCols;
                 float *buf = epi_buf + quarter * 32 * kEpiPad;
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
@@ -405,9 +470,10 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     __syncwarp();
                 }
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                ++cit;
             }
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
     }
 
@@ -426,7 +492,7 @@ int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, in
 template <int P, int BN, bool kSplit, class Epi>
 int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,
                       const Epi &epi, cudaStream_t st) {
-    using Cfg = Config<P, BN, kSplit, Epi::kDirect>;
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>;
     static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
     auto kern = split_gemm_kernel<P, BN, kSplit, Epi>;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

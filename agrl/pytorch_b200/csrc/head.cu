@@ -177,27 +177,38 @@ __device__ __forceinline__ void stage_chunk_async(float *xs, const float *x, int
     cp_async_commit();
 }
 
-// Run `body(buffer)` over all channel chunks of x with the next chunk in flight (cp.async).
-template <class F>
+// Run `body(buffer)` over all channel chunks of x.  kBufs = 2: the next chunk is in flight (cp.async)
+// while the current one is consumed; kBufs = 1: single buffer, latency hidden by the other resident CTAs.
+template <int kBufs, class F>
 __device__ __forceinline__ void for_each_chunk(float *xs0, float *xs1, const float *x, int V, int C, int tid, F &&body) {
     const int n = C / kChunk;
-    stage_chunk_async(xs0, x, V, C, 0, tid);
-    for (int i = 0; i < n; ++i) {
-        float *cur = (i & 1) ? xs1 : xs0;
-        if (i + 1 < n) {
-            stage_chunk_async((i & 1) ? xs0 : xs1, x, V, C, (i + 1) * kChunk, tid);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    if (kBufs == 2) {
+        stage_chunk_async(xs0, x, V, C, 0, tid);
+        for (int i = 0; i < n; ++i) {
+            float *cur = (i & 1) ? xs1 : xs0;
+            if (i + 1 < n) {
+                stage_chunk_async((i & 1) ? xs0 : xs1, x, V, C, (i + 1) * kChunk, tid);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();                       // chunk i is visible to every thread
+            body(cur, i * kChunk);
+            __syncthreads();                       // everyone is done with `cur` before it is refilled
         }
-        __syncthreads();                       // chunk i is visible to every thread
-        body(cur, i * kChunk);
-        __syncthreads();                       // everyone is done with `cur` before it is refilled
+    } else {
+        for (int i = 0; i < n; ++i) {
+            stage_chunk_async(xs0, x, V, C, i * kChunk, tid);
+            cp_async_wait<0>();
+            __syncthreads();
+            body(xs0, i * kChunk);
+            __syncthreads();
+        }
     }
 }
 
-template <int NT>                            // NT = ceil(V/4): 14 for the canonical V = 56
-__global__ void __launch_bounds__(kHeadThreads, 2)
+template <int NT, int kBufs, int kMinBlocks>   // NT = ceil(V/4): 14 for the canonical V = 56
+__global__ void __launch_bounds__(kHeadThreads, kMinBlocks)
 graph_kernel(GraphArgs a) {
     constexpr int kRows = 4 * NT;                      // staged rows (>= V; the rest stay zero)
     constexpr int kTiles = NT * (NT + 1) / 2;          // 4x4 Gram tiles of the upper triangle
@@ -205,16 +216,16 @@ graph_kernel(GraphArgs a) {
     constexpr int kRpg = NT / 2;                       // rows per thread in Y = G.X (8 row groups)
     static_assert(NT % 2 == 0 && kTiles <= kHeadThreads, "tiling");
     extern __shared__ __align__(16) float smem_f[];
-    float *xs0 = smem_f;                               // [kRows][kXsLd] x 2
-    float *xs1 = xs0 + kRows * kXsLd;
-    float *g = xs1 + kRows * kXsLd;                    // [64][68]: Gram, then the mixed graph
+    float *xs0 = smem_f;                               // [kRows][kXsLd] x kBufs
+    float *xs1 = xs0 + (kBufs - 1) * kRows * kXsLd;
+    float *g = xs0 + kBufs * kRows * kXsLd;            // [64][68]: Gram, then the mixed graph
     float *sq = g + kMaxNodes * kGLd;                  // [64]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = a.V, C = a.C;
     const int b = blockIdx.x;
     const float *x = a.x + static_cast<size_t>(b) * V * C;
 
-    for (int i = tid; i < 2 * kRows * kXsLd; i += kHeadThreads) xs0[i] = 0.f;   // pad rows stay zero
+    for (int i = tid; i < kBufs * kRows * kXsLd; i += kHeadThreads) xs0[i] = 0.f;   // pad rows stay zero
     for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
     __syncthreads();
 
@@ -230,7 +241,7 @@ graph_kernel(GraphArgs a) {
         for (int e = 0; e < 4; ++e)
 #pragma unroll
             for (int f = 0; f < 4; ++f) acc[e][f] = 0.f;
-        for_each_chunk(xs0, xs1, x, V, C, tid, [&](const float *xs, int) {
+        for_each_chunk<kBufs>(xs0, xs1, x, V, C, tid, [&](const float *xs, int) {
             if (!active) return;
             const int k0 = kg * (kChunk / kGroups);
 #pragma unroll 2
@@ -305,7 +316,7 @@ graph_kernel(GraphArgs a) {
     const int rg = tid >> 5, cq = tid & 31;              // a warp shares rg -> graph weights broadcast
     const size_t row0 = static_cast<size_t>(b) * V;
     const int jmax = (V + 3) & ~3;
-    for_each_chunk(xs0, xs1, x, V, C, tid, [&](const float *xs, int c0) {
+    for_each_chunk<kBufs>(xs0, xs1, x, V, C, tid, [&](const float *xs, int c0) {
         float acc[kRpg][4];
 #pragma unroll
         for (int r = 0; r < kRpg; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
@@ -441,13 +452,31 @@ static int check_params(const agrl_head_params *p) {
     return AGRL_OK;
 }
 
-template <int NT>
-static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
-    const size_t smem = (static_cast<size_t>(2 * 4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
-    AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    graph_kernel<NT><<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
+template <int NT, int kBufs, int kMinBlocks>
+static int launch_graph_variant(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
+    const size_t smem = (static_cast<size_t>(kBufs * 4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
+    auto kern = graph_kernel<NT, kBufs, kMinBlocks>;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
     AGRL_LAUNCH_CHECK(st, "graph");
     return AGRL_OK;
+}
+
+// AGRL_GRAPH_VARIANT (tuning knob): 0 = double-buffered, 2 CTAs/SM; 1 = single buffer, 3 CTAs/SM;
+// 2 = single buffer, 2 CTAs/SM; 3 = double-buffered, 3 CTAs/SM register budget
+static int graph_variant() {
+    static int v = [] { const char *e = getenv("AGRL_GRAPH_VARIANT"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <int NT>
+static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
+    switch (graph_variant()) {
+        case 1: return launch_graph_variant<NT, 1, 3>(ga, batch, st);
+        case 2: return launch_graph_variant<NT, 1, 2>(ga, batch, st);
+        case 3: return launch_graph_variant<NT, 2, 3>(ga, batch, st);
+        default: return launch_graph_variant<NT, 2, 2>(ga, batch, st);
+    }
 }
 
 }  // namespace agrl

@@ -73,7 +73,7 @@ def test_two_plane_split_meets_the_bar(cdm):
 def test_clustered_small_distances(cdm):
     """near-duplicate rows: the Gram form cancels, so the absolute error is set by the norms.  The
     tensor core truncates on accumulate (a small systematic bias on all-positive sums), hence the
-    bound is stated against |q|^2+|g|^2: 4e-6 relative, i.e. 25x inside the 1e-4 bar."""
+    bound is stated against |q|^2+|g|^2: 1.5e-6 relative (the accumulator is drained every 256 k and summed in fp32)."""
     g = torch.Generator().manual_seed(9)
     base = torch.randn(64, 1024, generator=g)
     a = base + 1e-3 * torch.randn(64, 1024, generator=g)
@@ -83,7 +83,7 @@ def test_clustered_small_distances(cdm):
     norms = (a.double() ** 2).sum(1).numpy()[:, None] + (base.double() ** 2).sum(1).numpy()[None, :]
     e_ours, e_ref = np.abs(out - ref64) / norms, np.abs(ref32 - ref64) / norms
     print('clustered: ours %.3e  reference fp32 %.3e (relative to the norms)' % (e_ours.max(), e_ref.max()))
-    assert e_ours.max() < 4e-6
+    assert e_ours.max() < 1.5e-6
 
 
 def test_non_contiguous_and_strided_inputs(cdm):
