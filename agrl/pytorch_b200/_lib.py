@@ -51,6 +51,14 @@ _SIGNATURES = {
                                            c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'agrl_rank_mars_merge_dev': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
                                          c_vp, c_sz, c_vp]),
+    'agrl_rank_market1501_count_dev': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'agrl_rank_market1501_gather_dev': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64,
+                                                c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'agrl_rank_market1501_list_len': (c_i64, [c_i64, c_i64]),
+    'agrl_rank_market1501_bin_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'agrl_rank_market1501_finalize_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64, c_i64]),
+    'agrl_rank_market1501_finalize_dev': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'agrl_rank_market1501_host': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                           c_vp, c_vp, c_vp, c_vp, c_vp]),
     'agrl_rank_mars_host': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),

@@ -410,6 +410,180 @@ rank_market_finish_kernel(MarketArgs a, int32_t *hist /*[rank_len+1], zeroed her
 }
 
 // ------------------------------------------------------------------------------------------------
+// market1501, gallery sharded over GPUs: the same rank-by-counting, cut at the
+// two points where the shards have to talk.
+//   gather   each shard lists, per query, its same-pid gallery items as keys
+//            (order-preserving distance bits << 32 | global index << 1 | junk bit)      -> all-gather
+//   bin      every shard sorts the gathered lists (identically) and counts, per list item, how many of
+//            ITS row elements sort before it                                            -> all-reduce(sum)
+//   finalize prefix sums -> kept ranks -> AP / first hit, exactly as in rank_market_kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t shard_key(float d, uint32_t global_idx, uint32_t junk) {
+    return (static_cast<uint64_t>(mono_key(d)) << 32) | (static_cast<uint64_t>(global_idx) << 1) | junk;
+}
+
+struct MarketShardArgs {
+    const float   *dist;
+    int64_t        ld;
+    const int32_t *q_pid, *q_cam, *g_pid, *g_cam;
+    int            num_q, num_g;
+    uint32_t       index_offset;
+    int            cap;                 // slots per query and shard
+    uint64_t      *keys;                // gather: [num_q][cap]; bin: gathered [parts][num_q][cap]
+    int32_t       *npos, *njunk;        // gather out: per query counts of this shard
+    int32_t       *max_count;           // count pass: max over queries of this shard's same-pid items
+    // bin
+    int            parts, n2;           // n2 = power of two >= parts * cap
+    int32_t       *cnt;                 // [num_q][n2] elements of this shard sorting before each sorted list item
+    uint64_t      *sorted;              // [num_q][n2] the sorted list (identical on every shard)
+};
+
+// count pass (cap unknown yet) / gather pass
+template <bool kCountOnly>
+__global__ void __launch_bounds__(kRankThreads)
+rank_market_gather_kernel(MarketShardArgs a) {
+    __shared__ int s_m, s_njunk, s_npos;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int ng = a.num_g;
+    const int pid = a.q_pid[q], cam = a.q_cam[q];
+    const float *row = a.dist + static_cast<size_t>(q) * a.ld;
+    uint64_t *out = kCountOnly ? nullptr : a.keys + static_cast<size_t>(q) * a.cap;
+    if (tid == 0) { s_m = 0; s_njunk = 0; s_npos = 0; }
+    if (!kCountOnly) for (int i = tid; i < a.cap; i += kRankThreads) out[i] = kKeyMax;
+    __syncthreads();
+    const int nvec = ng >> 2;
+    const int4 *p4 = reinterpret_cast<const int4 *>(a.g_pid);
+    auto hit = [&](int j) {
+        const int slot = atomicAdd(&s_m, 1);
+        if (kCountOnly) return;
+        const bool junk = (a.g_cam[j] == cam);
+        atomicAdd(junk ? &s_njunk : &s_npos, 1);
+        if (slot < a.cap) out[slot] = shard_key(row[j], a.index_offset + static_cast<uint32_t>(j), junk ? 1u : 0u);
+    };
+    for (int v = tid; v < nvec; v += kRankThreads) {
+        const int4 p = __ldg(p4 + v);
+        if (p.x == pid) hit(4 * v);
+        if (p.y == pid) hit(4 * v + 1);
+        if (p.z == pid) hit(4 * v + 2);
+        if (p.w == pid) hit(4 * v + 3);
+    }
+    const int j = (nvec << 2) + tid;
+    if (j < ng && a.g_pid[j] == pid) hit(j);
+    __syncthreads();
+    if (tid == 0) {
+        if (kCountOnly) atomicMax(a.max_count, s_m);
+        else { a.npos[q] = s_npos; a.njunk[q] = s_njunk; }
+    }
+}
+
+__global__ void __launch_bounds__(kRankThreads)
+rank_market_bin_kernel(MarketShardArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *list = reinterpret_cast<uint64_t *>(smem_raw);                         // n2 keys
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw + static_cast<size_t>(a.n2) * 8);   // n2 + 1 bins
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int n2 = a.n2, total = a.parts * a.cap;
+    for (int i = tid; i < n2; i += kRankThreads) {
+        uint64_t k = kKeyMax;
+        if (i < total) k = a.keys[(static_cast<size_t>(i / a.cap) * a.num_q + q) * a.cap + (i % a.cap)];
+        list[i] = k;
+    }
+    for (int i = tid; i <= n2; i += kRankThreads) hist[i] = 0;
+    __syncthreads();
+    bitonic_sort_u64<false>(list, n2, tid, kRankThreads);
+    // (keys are unique, so every shard obtains the same order)
+    const uint64_t last = list[n2 - 1];
+    int m = n2;                                         // number of real items: first pad position
+    if (last == kKeyMax) {                              // binary search for the first pad
+        int lo = 0, hi = n2 - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (list[mid] == kKeyMax) hi = mid; else lo = mid + 1; }
+        m = lo;
+    }
+    uint64_t *sorted = a.sorted + static_cast<size_t>(q) * n2;
+    for (int i = tid; i < n2; i += kRankThreads) sorted[i] = list[i];
+    if (m > 0) {
+        const uint64_t key_max = list[m - 1] & ~1ull;
+        const float *row = a.dist + static_cast<size_t>(q) * a.ld;
+        for_each_in_row(row, a.num_g, tid, kRankThreads, [&](float d, int j) {
+            const uint64_t key = shard_key(d, a.index_offset + static_cast<uint32_t>(j), 0u);
+            if (key < key_max) {
+                int t = 0;                              // t = #{i : (list[i] without junk bit) <= key}
+                for (int s = n2 >> 1; s > 0; s >>= 1)
+                    if ((list[t + s - 1] & ~1ull) <= key) t += s;
+                atomicAdd(&hist[t], 1u);
+            }
+        });
+    }
+    __syncthreads();
+    int32_t *cnt = a.cnt + static_cast<size_t>(q) * n2;
+    for (int i = tid; i < n2; i += kRankThreads) cnt[i] = static_cast<int32_t>(hist[i]);
+}
+
+struct MarketFinalArgs {
+    const int32_t  *cnt;                // [num_q][n2] summed over shards
+    const uint64_t *sorted;             // [num_q][n2]
+    const int32_t  *npos, *njunk;       // [num_q] summed over shards
+    int             num_q, n2, rank_len;
+    int64_t         num_g_total;
+    float          *ap;
+    int32_t        *first_hit, *kept;
+    uint32_t       *flags;
+    double         *terms;              // [num_q][n2] scratch
+};
+
+// one warp per query
+__global__ void __launch_bounds__(kRankThreads)
+rank_market_finalize_kernel(MarketFinalArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (kRankThreads / 32) + (threadIdx.x >> 5);
+    if (q >= a.num_q) return;
+    const int npos = a.npos[q], njunk = a.njunk[q];
+    const int kept = static_cast<int>(a.num_g_total - njunk);
+    if (npos == 0) {
+        if (lane == 0) { a.ap[q] = 0.f; a.first_hit[q] = INT_MAX; a.kept[q] = kept; }
+        return;
+    }
+    const int m = npos + njunk;
+    const int32_t *cnt = a.cnt + static_cast<size_t>(q) * a.n2;
+    const uint64_t *sorted = a.sorted + static_cast<size_t>(q) * a.n2;
+    double *terms = a.terms + static_cast<size_t>(q) * a.n2;
+    int carry_rank = 0, carry_junk = 0, carry_pos = 0, first_hit = INT_MAX;
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const bool in = i < m;
+        const int c = in ? cnt[i] : 0;
+        const bool is_junk = in && (sorted[i] & 1ull);
+        const bool is_pos = in && !is_junk;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const uint32_t jm = __ballot_sync(0xffffffffu, is_junk);
+        const uint32_t pm = __ballot_sync(0xffffffffu, is_pos);
+        const uint32_t below = (1u << lane) - 1u;
+        const int kept_rank = carry_rank + incl - (carry_junk + __popc(jm & below));
+        const int pos_before = carry_pos + __popc(pm & below);
+        if (is_pos) {
+            terms[pos_before] = __ddiv_rn(static_cast<double>(pos_before + 1), static_cast<double>(kept_rank + 1));
+            if (pos_before == 0) first_hit = kept_rank;
+        }
+        carry_rank += __shfl_sync(0xffffffffu, incl, 31);
+        carry_junk += __popc(jm);
+        carry_pos += __popc(pm);
+    }
+    first_hit = __reduce_min_sync(0xffffffffu, first_hit);
+    __syncwarp();
+    if (lane == 0) {
+        a.ap[q] = ap_from_terms(terms, npos);
+        a.first_hit[q] = first_hit;
+        a.kept[q] = kept;
+        if (kept < a.rank_len) atomicOr(a.flags, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // MARS metric: one CTA per query
 // ------------------------------------------------------------------------------------------------
 struct MarsArgs {
@@ -991,4 +1165,134 @@ extern "C" int agrl_rank_mars_merge_dev(const uint64_t *keys, const uint8_t *cls
     rank_mars_finish_kernel<<<1, 1024, 0, st>>>(a, w.hist, cmc, map);
     AGRL_LAUNCH_CHECK(st, "rank_mars_finish");
     return AGRL_OK;
+}
+
+// ---- gallery-sharded market1501 metric ---------------------------------------------------------------
+static int fill_shard_args(MarketShardArgs &a, const RankWorkspace &w, const float *distmat, int64_t ld,
+                           int64_t num_q, int64_t num_g, int64_t index_offset) {
+    memset(&a, 0, sizeof(a));
+    a.dist = distmat; a.ld = ld;
+    a.q_pid = w.q_pid; a.q_cam = w.q_cam; a.g_pid = w.g_pid; a.g_cam = w.g_cam;
+    a.num_q = static_cast<int>(num_q); a.num_g = static_cast<int>(num_g);
+    a.index_offset = static_cast<uint32_t>(index_offset);
+    return AGRL_OK;
+}
+
+extern "C" int agrl_rank_market1501_count_dev(const int64_t *q_pids, const int64_t *g_pids,
+                                              const int64_t *q_camids, const int64_t *g_camids,
+                                              int64_t num_q, int64_t num_g, int32_t *max_count, uint32_t *status,
+                                              void *ws, size_t ws_bytes, void *stream) {
+    if (!q_pids || !g_pids || !q_camids || !g_camids || !max_count || !status) return AGRL_E_INVALID;
+    if (num_q < 1 || num_g < 1 || num_q > INT32_MAX / 2 || num_g > INT32_MAX / 2) return AGRL_E_INVALID;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    RankWorkspace w = carve_rank(ws, num_q, num_g, 1);
+    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AGRL_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(uint32_t), st));
+    AGRL_CUDA_TRY(cudaMemsetAsync(max_count, 0, sizeof(int32_t), st));
+    if ((rc = narrow_labels(w, q_pids, g_pids, q_camids, g_camids, num_q, num_g, status, st))) return rc;
+    MarketShardArgs a;
+    fill_shard_args(a, w, nullptr, 0, num_q, num_g, 0);
+    a.max_count = max_count;
+    rank_market_gather_kernel<true><<<static_cast<unsigned>(num_q), kRankThreads, 0, st>>>(a);
+    AGRL_LAUNCH_CHECK(st, "rank_market_count");
+    return AGRL_OK;
+}
+
+extern "C" int agrl_rank_market1501_gather_dev(const float *distmat, int64_t ld,
+                                               const int64_t *q_pids, const int64_t *g_pids,
+                                               const int64_t *q_camids, const int64_t *g_camids,
+                                               int64_t num_q, int64_t num_g, int64_t index_offset, int64_t cap,
+                                               uint64_t *keys, int32_t *npos, int32_t *njunk, uint32_t *status,
+                                               void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_rank_args(distmat, q_pids, g_pids, q_camids, g_camids, num_q, num_g, 1, ld);
+    if (rc) return rc;
+    if (!keys || !npos || !njunk || !status || num_q < 1 || cap < 1 || index_offset < 0) return AGRL_E_INVALID;
+    if (index_offset + num_g > 0x7FFFFFFFll) return AGRL_E_UNSUPPORTED;
+    if ((rc = agrl_device_ok())) return rc;
+    RankWorkspace w = carve_rank(ws, num_q, num_g, 1);
+    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AGRL_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(uint32_t), st));
+    if ((rc = narrow_labels(w, q_pids, g_pids, q_camids, g_camids, num_q, num_g, status, st))) return rc;
+    MarketShardArgs a;
+    fill_shard_args(a, w, distmat, ld, num_q, num_g, index_offset);
+    a.cap = static_cast<int>(cap); a.keys = keys; a.npos = npos; a.njunk = njunk;
+    rank_market_gather_kernel<false><<<static_cast<unsigned>(num_q), kRankThreads, 0, st>>>(a);
+    AGRL_LAUNCH_CHECK(st, "rank_market_gather");
+    return AGRL_OK;
+}
+
+static int market_n2(int64_t parts, int64_t cap) {
+    int n2 = 2;
+    while (n2 < parts * cap) n2 <<= 1;
+    return n2;
+}
+
+extern "C" int agrl_rank_market1501_bin_dev(const float *distmat, int64_t ld, int64_t num_q, int64_t num_g,
+                                            int64_t index_offset, const uint64_t *keys_all, int64_t parts, int64_t cap,
+                                            int32_t *cnt, uint64_t *sorted, void *stream) {
+    if (!distmat || !keys_all || !cnt || !sorted || num_q < 1 || num_g < 1 || parts < 1 || cap < 1 || ld < num_g) return AGRL_E_INVALID;
+    if (parts * cap > 8192 || index_offset + num_g > 0x7FFFFFFFll) return AGRL_E_UNSUPPORTED;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MarketShardArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dist = distmat; a.ld = ld; a.num_q = static_cast<int>(num_q); a.num_g = static_cast<int>(num_g);
+    a.index_offset = static_cast<uint32_t>(index_offset);
+    a.cap = static_cast<int>(cap); a.parts = static_cast<int>(parts); a.n2 = market_n2(parts, cap);
+    a.keys = const_cast<uint64_t *>(keys_all); a.cnt = cnt; a.sorted = sorted;
+    const size_t smem = static_cast<size_t>(a.n2) * 8 + (static_cast<size_t>(a.n2) + 1) * 4;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_market_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    rank_market_bin_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
+    AGRL_LAUNCH_CHECK(st, "rank_market_bin");
+    return AGRL_OK;
+}
+
+extern "C" int64_t agrl_rank_market1501_list_len(int64_t parts, int64_t cap) {
+    if (parts < 1 || cap < 1 || parts * cap > 8192) return 0;
+    return market_n2(parts, cap);
+}
+
+extern "C" int agrl_rank_market1501_finalize_dev(const int32_t *cnt_total, const uint64_t *sorted,
+                                                 const int32_t *npos_total, const int32_t *njunk_total,
+                                                 int64_t num_q, int64_t num_g_total, int64_t parts, int64_t cap, int64_t max_rank,
+                                                 float *cmc, float *map, float *all_ap, int64_t *num_valid, uint32_t *status,
+                                                 void *ws, size_t ws_bytes, void *stream) {
+    if (!cnt_total || !sorted || !npos_total || !njunk_total || !cmc || !map || !status) return AGRL_E_INVALID;
+    if (num_q < 1 || num_g_total < 1 || parts < 1 || cap < 1 || max_rank < 1 || parts * cap > 8192) return AGRL_E_INVALID;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    const int64_t rank_len = max_rank < num_g_total ? max_rank : num_g_total;
+    const int n2 = market_n2(parts, cap);
+    Carver c(ws);
+    RankWorkspace w = carve_rank(ws, num_q, 0, rank_len);
+    c.off = w.bytes;
+    double *terms = c.take<double>(static_cast<size_t>(num_q) * n2);
+    if (!ws || ws_bytes < c.total()) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AGRL_CUDA_TRY(cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), st));
+    MarketFinalArgs f;
+    f.cnt = cnt_total; f.sorted = sorted; f.npos = npos_total; f.njunk = njunk_total;
+    f.num_q = static_cast<int>(num_q); f.n2 = n2; f.rank_len = static_cast<int>(rank_len);
+    f.num_g_total = num_g_total;
+    f.ap = all_ap ? all_ap : w.ap_f32; f.first_hit = w.first; f.kept = w.kept;
+    f.flags = reinterpret_cast<uint32_t *>(w.counters + 1);
+    f.terms = terms;
+    const int wpb = kRankThreads / 32;
+    rank_market_finalize_kernel<<<static_cast<unsigned>((num_q + wpb - 1) / wpb), kRankThreads, 0, st>>>(f);
+    AGRL_LAUNCH_CHECK(st, "rank_market_finalize");
+    MarketArgs a;
+    memset(&a, 0, sizeof(a));
+    a.num_q = f.num_q; a.rank_len = f.rank_len; a.ap = f.ap; a.first_hit = f.first_hit; a.kept = f.kept; a.flags = f.flags;
+    rank_market_finish_kernel<<<1, 1024, 0, st>>>(a, w.hist, cmc, map, num_valid, status);
+    AGRL_LAUNCH_CHECK(st, "rank_market_finish");
+    return AGRL_OK;
+}
+
+extern "C" size_t agrl_rank_market1501_finalize_workspace_bytes(int64_t num_q, int64_t parts, int64_t cap, int64_t max_rank) {
+    if (num_q < 1 || parts < 1 || cap < 1 || max_rank < 1 || parts * cap > 8192) return 0;
+    return carve_rank(nullptr, num_q, 0, max_rank).bytes + align_up(static_cast<size_t>(num_q) * market_n2(parts, cap) * 8, 256) + 256;
 }

@@ -83,6 +83,69 @@ class CudaOps(object):
         return host[:max_rank].numpy().copy(), np.float64(host[max_rank])
 
 
+    # ---- market1501 metric -------------------------------------------------------------------------
+    def market_count(self, q_pids, g_pids, q_camids, g_camids):
+        dev = g_pids.device
+        nq, ng = q_pids.numel(), g_pids.numel()
+        out = torch.zeros(2, dtype=torch.int32, device=dev)                   # [max_count, status]
+        wsb = self.lib.agrl_rank_workspace_bytes(nq, ng, 1)
+        ws = self._workspace(dev, wsb)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.agrl_rank_market1501_count_dev(
+                q_pids.data_ptr(), g_pids.data_ptr(), q_camids.data_ptr(), g_camids.data_ptr(), nq, ng,
+                out.data_ptr(), out.data_ptr() + 4, ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream))
+        return out[0:1], out[1:2]
+
+    def market_gather(self, d, q_pids, g_pids, q_camids, g_camids, offset, cap):
+        dev = d.device
+        nq, ng = d.shape
+        keys = torch.empty(nq, cap, dtype=torch.int64, device=dev)
+        counts = torch.empty(2, nq, dtype=torch.int32, device=dev)            # [npos, njunk]
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        wsb = self.lib.agrl_rank_workspace_bytes(nq, ng, 1)
+        ws = self._workspace(dev, wsb)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.agrl_rank_market1501_gather_dev(
+                d.data_ptr(), d.stride(0), q_pids.data_ptr(), g_pids.data_ptr(), q_camids.data_ptr(), g_camids.data_ptr(),
+                nq, ng, offset, cap, keys.data_ptr(), counts[0].data_ptr(), counts[1].data_ptr(), status.data_ptr(),
+                ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream))
+        return keys, counts, status
+
+    def market_bin(self, d, offset, keys_all):
+        dev = d.device
+        nq, ng = d.shape
+        parts, cap = keys_all.shape[0], keys_all.shape[2]
+        n2 = self.lib.agrl_rank_market1501_list_len(parts, cap)
+        if n2 == 0:
+            _lib.check(_lib.E_UNSUPPORTED)
+        cnt = torch.empty(nq, n2, dtype=torch.int32, device=dev)
+        srt = torch.empty(nq, n2, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.agrl_rank_market1501_bin_dev(
+                d.data_ptr(), d.stride(0), nq, ng, offset, keys_all.data_ptr(), parts, cap, cnt.data_ptr(), srt.data_ptr(),
+                torch.cuda.current_stream(dev).cuda_stream))
+        return cnt, srt
+
+    def market_finalize(self, cnt, srt, counts, ng_total, parts, cap, max_rank, status_parts):
+        dev = cnt.device
+        nq = cnt.shape[0]
+        rank_len = min(max_rank, ng_total)
+        cmc = torch.empty(rank_len, dtype=torch.float32, device=dev)
+        scal = torch.zeros(4, dtype=torch.float32, device=dev)               # [mAP, status(u32), num_valid(i64)]
+        wsb = self.lib.agrl_rank_market1501_finalize_workspace_bytes(nq, parts, cap, max_rank)
+        ws = self._workspace(dev, wsb)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.agrl_rank_market1501_finalize_dev(
+                cnt.data_ptr(), srt.data_ptr(), counts[0].data_ptr(), counts[1].data_ptr(), nq, ng_total, parts, cap, max_rank,
+                cmc.data_ptr(), scal.data_ptr(), None, scal.data_ptr() + 8, scal.data_ptr() + 4, ws.data_ptr(), wsb,
+                torch.cuda.current_stream(dev).cuda_stream))
+            host = scal.cpu()
+            st_parts = int(status_parts.cpu())
+        from .metrics.rank import _raise_status
+        _raise_status(int(host.view(torch.int32)[1]) | st_parts)
+        return cmc.cpu().numpy(), float(host[0])
+
+
 def _as_dev_i64(x, dev):
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=torch.int64).contiguous()
@@ -135,3 +198,55 @@ def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids
     else:
         keys_all, cls_all = keys.unsqueeze(0), cls.unsqueeze(0)
     return ops.merge(keys_all, cls_all, ngood, max_rank, status)
+
+
+def evaluate_market1501_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids_local, metric='euclidean',
+                                max_rank=50, group=None, broadcast_queries=True, ops=None):
+    """market1501-metric CMC/mAP (rank_cy.pyx:154-241 semantics) of ``qf`` against the union of every
+    rank's gallery shard: same arguments as evaluate_mars_sharded, returns (numpy.float32[rank_len], float)
+    on every rank, bit-identical to the unsharded evaluator (ties by global gallery index).
+
+    Exchanges: all-reduce(max) of one int, all-gather of the per-query same-pid key lists, all-reduce(sum)
+    of their positive / junk counts, all-reduce(sum) of the per-list-item rank counts."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = qf.device
+    ops = ops or CudaOps()
+    qp, qc = _as_dev_i64(q_pids, dev), _as_dev_i64(q_camids, dev)
+    gp, gc = _as_dev_i64(g_pids_local, dev), _as_dev_i64(g_camids_local, dev)
+    qf = qf.contiguous()
+    if world > 1 and broadcast_queries:
+        for t in (qf, qp, qc):
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    n_local = torch.tensor([gf_local.shape[0]], dtype=torch.int64, device=dev)
+    if world > 1:
+        counts_g = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts_g, n_local, group=group)
+        counts_g = counts_g.cpu().tolist()
+        rank = dist.get_rank(group)
+    else:
+        counts_g, rank = [int(n_local)], 0
+    ng_total, offset = sum(counts_g), sum(counts_g[:rank])
+    if ng_total < max_rank:
+        print('Note: number of gallery samples is quite small, got {}'.format(ng_total))     # rank_cy.pyx:160-162
+
+    max_count, status = ops.market_count(qp, gp, qc, gc)
+    if world > 1:
+        dist.all_reduce(max_count, op=dist.ReduceOp.MAX, group=group)
+    cap = max(8, (int(max_count.cpu()) + 7) // 8 * 8)
+
+    d = ops.distance(qf, gf_local, metric)
+    keys, counts, st2 = ops.market_gather(d, qp, gp, qc, gc, offset, cap)
+    status = torch.maximum(status, st2)
+    nq = keys.shape[0]
+    if world > 1:
+        keys_all = torch.empty((world * nq, cap), dtype=keys.dtype, device=dev)
+        dist.all_gather_into_tensor(keys_all, keys, group=group)
+        keys_all = keys_all.view(world, nq, cap)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
+    else:
+        keys_all = keys.unsqueeze(0)
+    cnt, srt = ops.market_bin(d, offset, keys_all)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    return ops.market_finalize(cnt, srt, counts, ng_total, world, cap, max_rank, status)

@@ -268,7 +268,16 @@ def run_b200(args):
         roof = dict(kernel=top, bound='hbm', unit='GB/s', peak=pk['hbm_gbs'],
                     achieved=(J * 56 * C * 4 * 2) / (ms_top * 1e-3) / 1e9)
     roof['frac'] = roof['achieved'] / roof['peak']
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/traffic.json),
+    # scaled to this run's units per launch
     roof['traffic'] = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))[top]
+        per_unit = tr['dram_bytes_per_launch'] / tr['units_per_launch']
+        roof['traffic'] = per_unit * (pool_n if tr['unit'] == 'tracklet' else 1)
+        roof['algorithmic_bytes_per_launch'] = pool_n * BYTES_PER_TRACKLET if top == 'pool' else None
+    except Exception:
+        pass
     roof['peak_source'] = pk['source']
     roof['launches'] = n_top
     roof['avg_launch_ms'] = ms_top / n_top

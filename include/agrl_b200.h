@@ -148,6 +148,39 @@ AGRL_API int agrl_rank_mars_merge_dev(const uint64_t *keys_dev, const uint8_t *c
                              uint32_t *status_dev,
                              void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/*
+ * Gallery-sharded market1501 metric (last row).  Per shard:
+ *   _count     max over queries of this shard's same-pid gallery items  (host: all-reduce MAX -> cap)
+ *   _gather    per query the shard's same-pid items as keys (distance bits << 32 | global index << 1 |
+ *              junk bit; all-ones = empty), positive / junk counts       (all-gather keys [part][query][cap],
+ *                                                                        all-reduce(sum) counts)
+ *   _bin       sorts the gathered list (same order on every shard) and counts, per list item, the
+ *              shard's row elements sorting before it -> cnt [query][len], sorted [query][len]
+ *              with len = agrl_rank_market1501_list_len(parts, cap)       (all-reduce(sum) cnt)
+ *   _finalize  kept ranks -> AP / CMC / mAP, bit-identical to agrl_rank_market1501_dev on the whole gallery
+ * parts * cap <= 8192; global gallery indices < 2^31.
+ */
+AGRL_API int agrl_rank_market1501_count_dev(const int64_t *q_pids_dev, const int64_t *g_pids_dev,
+                                   const int64_t *q_camids_dev, const int64_t *g_camids_dev,
+                                   int64_t num_q, int64_t num_g, int32_t *max_count_dev, uint32_t *status_dev,
+                                   void *workspace_dev, size_t workspace_bytes, void *stream);
+AGRL_API int agrl_rank_market1501_gather_dev(const float *distmat_dev, int64_t ld_dist,
+                                    const int64_t *q_pids_dev, const int64_t *g_pids_dev,
+                                    const int64_t *q_camids_dev, const int64_t *g_camids_dev,
+                                    int64_t num_q, int64_t num_g, int64_t index_offset, int64_t cap,
+                                    uint64_t *keys_dev, int32_t *npos_dev, int32_t *njunk_dev, uint32_t *status_dev,
+                                    void *workspace_dev, size_t workspace_bytes, void *stream);
+AGRL_API int64_t agrl_rank_market1501_list_len(int64_t parts, int64_t cap);
+AGRL_API int agrl_rank_market1501_bin_dev(const float *distmat_dev, int64_t ld_dist, int64_t num_q, int64_t num_g,
+                                 int64_t index_offset, const uint64_t *keys_all_dev, int64_t parts, int64_t cap,
+                                 int32_t *cnt_dev, uint64_t *sorted_dev, void *stream);
+AGRL_API size_t agrl_rank_market1501_finalize_workspace_bytes(int64_t num_q, int64_t parts, int64_t cap, int64_t max_rank);
+AGRL_API int agrl_rank_market1501_finalize_dev(const int32_t *cnt_total_dev, const uint64_t *sorted_dev,
+                                      const int32_t *npos_total_dev, const int32_t *njunk_total_dev,
+                                      int64_t num_q, int64_t num_g_total, int64_t parts, int64_t cap, int64_t max_rank,
+                                      float *cmc_dev, float *map_dev, float *all_ap_dev, int64_t *num_valid_dev,
+                                      uint32_t *status_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Host-buffer forms (numpy in / numpy out like the reference).  cmc_host must hold max_rank
  * entries; *rank_len_out receives min(max_rank, num_g) for the market1501 metric. */
 AGRL_API int agrl_rank_market1501_host(const float *distmat_host,

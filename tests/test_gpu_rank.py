@@ -155,3 +155,39 @@ def test_sharded_partial_and_merge_kernels(shape, seed, kind, parts):
     cmc, mAP = ops.merge(torch.stack(keys), torch.stack(cls), ngood, K, st)
     assert np.array_equal(_bits64(cmc), _bits64(ref_cmc))
     assert _bits64(mAP) == _bits64(ref_map)
+
+
+@pytest.mark.parametrize('shape,seed,kind,parts', [('dukev', 31, 'randn', 3), ((100, 2049, 40, 4), 32, 'ties', 2),
+                                                   ('mars', 33, 'randn', 8), ((25, 12, 4, 2), 34, 'randn', 2),
+                                                   ((257, 5000, 9, 3), 35, 'ties', 4)])
+def test_sharded_market1501_kernels(shape, seed, kind, parts):
+    """count / gather / bin / finalize kernels of the gallery-sharded market1501 metric, single process:
+    shards are column slices of one distance matrix, the 'collectives' are plain sums / stacks"""
+    from agrl.pytorch_b200 import sharded
+    qp, qc, gp, gc = synth.eval_labels(shape, seed=seed)
+    d = _distmat(kind, len(qp), len(gp), seed)
+    K = 50
+    ref_cmc, ref_map = orank.market1501_port(d, qp, gp, qc, gc, K)
+    ops = sharded.CudaOps()
+    dev = torch.device('cuda')
+    dd = torch.from_numpy(d).to(dev)
+    tq, tqc = torch.as_tensor(qp).to(dev), torch.as_tensor(qc).to(dev)
+    bounds = sharded.shard_bounds(len(gp), parts)
+    lab = [(torch.as_tensor(gp[lo:hi]).to(dev), torch.as_tensor(gc[lo:hi]).to(dev)) for lo, hi in bounds]
+    cap = 0
+    for (lo, hi), (tg, tgc) in zip(bounds, lab):
+        if hi > lo:
+            cap = max(cap, int(ops.market_count(tq, tg, tqc, tgc)[0].cpu()))
+    cap = max(8, (cap + 7) // 8 * 8)
+    keys, counts = [], 0
+    for (lo, hi), (tg, tgc) in zip(bounds, lab):
+        k, c, st = ops.market_gather(dd[:, lo:hi].contiguous(), tq, tg, tqc, tgc, lo, cap)
+        keys.append(k); counts = counts + c
+    keys_all = torch.stack(keys)
+    cnt = 0
+    for (lo, hi), (tg, tgc) in zip(bounds, lab):
+        c, srt = ops.market_bin(dd[:, lo:hi].contiguous(), lo, keys_all)
+        cnt = cnt + c
+    cmc, mAP = ops.market_finalize(cnt, srt, counts, len(gp), parts, cap, K, st)
+    assert np.array_equal(_bits32(cmc), _bits32(ref_cmc))
+    assert mAP == ref_map

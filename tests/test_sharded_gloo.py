@@ -67,6 +67,82 @@ class CpuOps(object):
         return np.mean(cmc, axis=0), np.mean(ap)
 
 
+    # ---- market1501 metric stand-ins (same key / count contracts as csrc/rank.cu) ---------------------
+    def market_count(self, qp, gp, qc, gc):
+        qp, gp = qp.numpy(), gp.numpy()
+        m = max(int(np.sum(gp == p)) for p in qp)
+        return torch.tensor([m], dtype=torch.int32), torch.zeros(1, dtype=torch.int32)
+
+    def market_gather(self, d, qp, gp, qc, gc, offset, cap):
+        d, qp, gp, qc, gc = d.numpy(), qp.numpy(), gp.numpy(), qc.numpy(), gc.numpy()
+        nq, ng = d.shape
+        keys = np.full((nq, cap), KEY_MAX, np.uint64)
+        counts = np.zeros((2, nq), np.int32)
+        for q in range(nq):
+            idx = np.nonzero(gp == qp[q])[0]
+            junk = (gc[idx] == qc[q])
+            k = (mono_keys(d[q, idx]) << np.uint64(32)) | ((idx.astype(np.uint64) + np.uint64(offset)) << np.uint64(1)) \
+                | junk.astype(np.uint64)
+            keys[q, :len(idx)] = k
+            counts[0, q], counts[1, q] = np.sum(~junk), np.sum(junk)
+        return torch.from_numpy(keys.view(np.int64)), torch.from_numpy(counts), torch.zeros(1, dtype=torch.int32)
+
+    def market_bin(self, d, offset, keys_all):
+        d = d.numpy()
+        keys = keys_all.numpy().view(np.uint64)
+        parts, nq, cap = keys.shape
+        n2 = 2
+        while n2 < parts * cap:
+            n2 *= 2
+        cnt = np.zeros((nq, n2), np.int32)
+        srt = np.full((nq, n2), KEY_MAX, np.uint64)
+        ng = d.shape[1]
+        for q in range(nq):
+            lst = np.sort(keys[:, q, :].reshape(-1))
+            srt[q, :len(lst)] = lst
+            real = lst[lst != KEY_MAX] & ~np.uint64(1)
+            ek = (mono_keys(d[q]) << np.uint64(32)) | ((np.arange(ng, dtype=np.uint64) + np.uint64(offset)) << np.uint64(1))
+            if len(real):
+                t = np.searchsorted(real, ek, side='right')          # number of list items <= element
+                t = t[ek < real[-1]]
+                np.add.at(cnt[q], t, 1)
+        return torch.from_numpy(cnt), torch.from_numpy(srt.view(np.int64))
+
+    def market_finalize(self, cnt, srt, counts, ng_total, parts, cap, max_rank, status):
+        cnt, srt, counts = cnt.numpy(), srt.numpy().view(np.uint64), counts.numpy()
+        nq = cnt.shape[0]
+        R = min(max_rank, ng_total)
+        all_cmc, all_ap, nvalid, scratch = np.zeros((nq, R), np.float32), np.zeros(nq, np.float32), 0, np.zeros(max(ng_total, R), np.float32)
+        for q in range(nq):
+            npos, njunk = int(counts[0, q]), int(counts[1, q])
+            if npos == 0:
+                continue
+            m = npos + njunk
+            full = np.cumsum(cnt[q, :m])
+            junk = (srt[q, :m] & np.uint64(1)).astype(bool)
+            kept_rank = full - np.concatenate([[0], np.cumsum(junk)[:-1]])
+            pos_ranks = kept_rank[~junk]
+            kept = ng_total - njunk
+            row = np.zeros(kept, np.float32)
+            row[pos_ranks[0]:] = 1
+            scratch[:kept] = row
+            all_cmc[q] = scratch[:R]                                   # stale tail semantics (rank_cy.pyx:177)
+            acc = np.float32(0)
+            for c, r in enumerate(pos_ranks):
+                acc = np.float32(np.float64(acc) + np.float64(c + 1) / np.float64(r + 1))
+            all_ap[q] = acc / np.float32(npos)
+            nvalid += 1
+        assert nvalid > 0, 'Error: all query identities do not appear in gallery'
+        fv = np.float32(nvalid)
+        cmc = np.zeros(R, np.float32)
+        for q in range(nq):
+            cmc += all_cmc[q]
+        mAP = np.float32(0)
+        for q in range(nq):
+            mAP = np.float32(mAP + all_ap[q])
+        return (cmc / fv).astype(np.float32), float(np.float32(mAP / fv))
+
+
 def compute_ap(cls, ngood, K):
     """Compute_AP (rank.py:180-212) on class bytes (bit0 good, bit1 junk)."""
     cmc = np.zeros(K)
@@ -104,7 +180,9 @@ def _worker(rank, world, port, case, out_dir):
         qc_r = qc if rank == 0 else np.zeros_like(qc)
         cmc, mAP = sharded.evaluate_mars_sharded(qf_r, gf[lo:hi], qp_r, gp[lo:hi], qc_r, gc[lo:hi],
                                                  metric=metric, max_rank=K, ops=CpuOps())
-        np.savez(os.path.join(out_dir, 'r%d.npz' % rank), cmc=cmc, mAP=mAP)
+        mcmc, mmAP = sharded.evaluate_market1501_sharded(qf_r, gf[lo:hi], qp_r, gp[lo:hi], qc_r, gc[lo:hi],
+                                                         metric=metric, max_rank=K, ops=CpuOps())
+        np.savez(os.path.join(out_dir, 'r%d.npz' % rank), cmc=cmc, mAP=mAP, mcmc=mcmc, mmAP=mmAP)
     finally:
         dist.destroy_process_group()
 
@@ -130,10 +208,13 @@ def test_sharded_mars_matches_unsharded_oracle(tmp_path, world, shape, metric, t
              nprocs=world, join=True)
     d = odist.distance_matrix(qf, gf, metric).numpy()
     ref_cmc, ref_map = orank.mars_port(d, qp, gp, qc, gc, K)
+    mref_cmc, mref_map = orank.market1501_port(d, qp, gp, qc, gc, K)
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), 'r%d.npz' % r))
         assert np.array_equal(got['cmc'], ref_cmc), r
         assert float(got['mAP']) == float(ref_map), r
+        assert np.array_equal(got['mcmc'].view(np.uint32), mref_cmc.view(np.uint32)), r
+        assert float(got['mmAP']) == mref_map, r
 
 
 def test_shard_bounds():
