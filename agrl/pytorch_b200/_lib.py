@@ -16,6 +16,7 @@ E_NO_VALID_QUERY, E_ZERO_DIVISION, E_LABEL_RANGE = -6, -7, -8
 ST_NO_VALID_QUERY, ST_ZERO_DIVISION, ST_LABEL_RANGE = 1, 2, 4
 METRIC_EUCLIDEAN, METRIC_COSINE = 0, 1
 SPLIT_BF16X3, SPLIT_BF16X2 = 3, 2
+CLIP_POOL_AVG, CLIP_POOL_MAX = 0, 1
 HEAD_MAX_LAYERS = 4
 
 c_i64, c_i32, c_sz, c_vp, c_int = ctypes.c_int64, ctypes.c_int32, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
@@ -69,6 +70,7 @@ _SIGNATURES = {
     'agrl_distance_prepare_operand_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_sz, c_vp]),
     'agrl_distance_prepared_dev': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
     'agrl_distance_host': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int]),
+    'agrl_clip_pool_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_vp]),
     'agrl_head_prepared_bytes': (c_sz, [ctypes.POINTER(HeadParams)]),
     'agrl_head_prepare_dev': (c_int, [ctypes.POINTER(HeadParams), c_vp, c_sz, c_vp]),
     'agrl_head_workspace_bytes': (c_sz, [ctypes.POINTER(HeadParams), c_i64, c_i32]),

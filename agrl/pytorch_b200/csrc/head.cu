@@ -578,3 +578,48 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     AGRL_LAUNCH_CHECK(st, "attn");
     return AGRL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// clip pooling for the `dense` / `skipdense` test sampling:
+// train_vidreid_xent_htri.py:461-476 folds the clips of a tracklet into the batch, runs the model,
+// then reduces the per-clip features with torch.mean(features, 0) or torch.max(features, 0).
+// feats (tracklets, clips, dim) -> out (tracklets, dim); one thread per output element, clips in order.
+// ------------------------------------------------------------------------------------------------
+namespace agrl {
+__global__ void clip_pool_kernel(const float *__restrict__ feats, float *__restrict__ out, int64_t tracklets,
+                                 int clips, int64_t dim, int64_t ld_feat, int64_t ld_out, int mode) {
+    const int64_t n = tracklets * dim;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t t = i / dim, c = i % dim;
+        const float *p = feats + t * clips * ld_feat + c;
+        float acc = p[0];
+        if (mode == AGRL_CLIP_POOL_MAX) {
+            // torch.max propagates NaN
+            for (int k = 1; k < clips; ++k) { const float v = p[k * ld_feat]; acc = (v > acc || v != v) ? v : acc; }
+        } else {
+            for (int k = 1; k < clips; ++k) acc = __fadd_rn(acc, p[k * ld_feat]);
+            acc = __fdiv_rn(acc, static_cast<float>(clips));
+        }
+        out[t * ld_out + c] = acc;
+    }
+}
+}  // namespace agrl
+
+extern "C" int agrl_clip_pool_dev(const float *feats, int64_t ld_feat, int64_t tracklets, int64_t clips, int64_t dim,
+                                  int mode, float *out, int64_t ld_out, void *stream) {
+    if (!feats || !out || tracklets < 0 || clips < 1 || dim < 1 || ld_feat < dim || ld_out < dim) return AGRL_E_INVALID;
+    if (mode != AGRL_CLIP_POOL_AVG && mode != AGRL_CLIP_POOL_MAX) return AGRL_E_INVALID;
+    if (clips > (1 << 20)) return AGRL_E_UNSUPPORTED;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    if (tracklets == 0) return AGRL_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n = tracklets * dim;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    clip_pool_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(feats, out, tracklets, static_cast<int>(clips), dim,
+                                                                   ld_feat, ld_out, mode);
+    AGRL_LAUNCH_CHECK(st, "clip_pool");
+    return AGRL_OK;
+}

@@ -8,11 +8,11 @@ import os
 import shutil
 
 from . import vmgn as vmgn_module
-from .vmgn import vmgn, VMGN
+from .vmgn import vmgn, VMGN, pool_clips
 
 _FACTORY = {'vmgn': vmgn}
 
-__all__ = ['init_model', 'get_names', 'vmgn', 'VMGN']
+__all__ = ['init_model', 'get_names', 'vmgn', 'VMGN', 'pool_clips']
 
 
 def get_names():

@@ -19,7 +19,7 @@ from torch import nn
 
 from .. import _lib
 
-__all__ = ['vmgn', 'VMGN']
+__all__ = ['vmgn', 'VMGN', 'pool_clips']
 
 RESNET50_URL = 'https://download.pytorch.org/models/resnet50-19c8e357.pth'
 
@@ -221,6 +221,13 @@ class VMGN(nn.Module):
                 self._ws.data_ptr(), wsb, stream))
         return (out, nodes) if return_nodes else out
 
+    def forward_clips(self, imgs, adj, pool='avg'):
+        """The dense / skipdense branch of the reference's test() (train_vidreid_xent_htri.py:461-476):
+        imgs (b, n, s, c, h, w), adj (b, n, V, V) -> clip-pooled features (b, 4096)."""
+        b, n, s, c, h, w = imgs.size()
+        feats = self.forward(imgs.view(b * n, s, c, h, w), adj.view(b * n, adj.size(-1), adj.size(-1)))
+        return pool_clips(feats, n, pool)
+
     def forward(self, x, adj, *args):
         if self.training:
             raise NotImplementedError('agrl.pytorch_b200 covers the test-time path only (model.eval()); '
@@ -228,6 +235,26 @@ class VMGN(nn.Module):
         B, S, C, H, W = x.size()
         x4_1, x4_2 = self.featuremaps(x.view(B * S, C, H, W))
         return self.head(x4_1, x4_2, adj, S)
+
+
+def pool_clips(features, num_clips, pool='avg'):
+    """Clip pooling of the reference's dense / skipdense test sampling (train_vidreid_xent_htri.py:471-476):
+    features (tracklets * num_clips, D) on a CUDA device, the clips of a tracklet consecutive ->
+    (tracklets, D); ``pool='avg'`` is torch.mean over the clips, anything else torch.max (as in the reference)."""
+    lib = _lib.require_device()
+    if not features.is_cuda:
+        raise RuntimeError('agrl.pytorch_b200 has no CPU path: move the features to a B200')
+    assert features.dim() == 2 and features.size(0) % num_clips == 0
+    f = features.detach().float()
+    if f.stride(1) != 1:
+        f = f.contiguous()
+    t, d = f.size(0) // num_clips, f.size(1)
+    out = torch.empty(t, d, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        _lib.check(lib.agrl_clip_pool_dev(f.data_ptr(), f.stride(0), t, num_clips, d,
+                                          _lib.CLIP_POOL_AVG if pool == 'avg' else _lib.CLIP_POOL_MAX,
+                                          out.data_ptr(), out.stride(0), torch.cuda.current_stream(f.device).cuda_stream))
+    return out
 
 
 def vmgn(num_classes, loss, last_stride, num_split, num_gb, num_scale, pyramid_part, use_pose, learn_graph,

@@ -276,6 +276,18 @@ AGRL_API int agrl_head_forward_dev(const agrl_head_params *p, const void *prepar
                           int64_t batch, int32_t seq_len, int32_t h, int32_t w,
                           void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* =============================================================================================
+ * SURVEY.md section 8(f) rows ("next"): the callers / data formats either side of the path.
+ * ============================================================================================= */
+
+/* Clip pooling of the `dense` / `skipdense` test sampling (train_vidreid_xent_htri.py:461-476):
+ * feats (tracklets * clips, dim) with the clips of a tracklet consecutive -> out (tracklets, dim),
+ * torch.mean(features, 0) (AVG) or torch.max(features, 0) values (MAX) over the clip axis. */
+#define AGRL_CLIP_POOL_AVG 0
+#define AGRL_CLIP_POOL_MAX 1
+AGRL_API int agrl_clip_pool_dev(const float *feats_dev, int64_t ld_feat, int64_t tracklets, int64_t clips,
+                       int64_t dim, int mode, float *out_dev, int64_t ld_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

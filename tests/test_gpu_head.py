@@ -116,3 +116,37 @@ def test_training_mode_and_cpu_inputs_fail_loudly():
     with pytest.raises(RuntimeError):
         model.eval().cpu()(x, adj)
 
+
+
+@pytest.mark.parametrize('pool', ['avg', 'max'])
+@pytest.mark.parametrize('tracklets,clips,dim', [(1, 1, 4096), (3, 4, 4096), (7, 13, 100), (2, 64, 4096)])
+def test_clip_pooling_matches_the_reference_lines(pool, tracklets, clips, dim):
+    """dense / skipdense test sampling (train_vidreid_xent_htri.py:471-476): features.view(n, 1, -1) then
+    torch.mean(features, 0) or torch.max(features, 0) per tracklet.  max is exact; mean to fp32 rounding."""
+    from agrl.pytorch_b200 import models
+    gen = torch.Generator().manual_seed(1000 * tracklets + clips)
+    feats = torch.randn(tracklets * clips, dim, generator=gen)
+    if pool == 'max' and clips > 1:
+        feats[1, 3] = float('nan')                       # torch.max propagates NaN
+    ref = []
+    for t in range(tracklets):
+        f = feats[t * clips:(t + 1) * clips].view(clips, 1, -1)
+        ref.append(torch.mean(f, 0) if pool == 'avg' else torch.max(f, 0)[0])
+    ref = torch.cat(ref, 0)
+    out = models.pool_clips(feats.cuda(), clips, pool).cpu()
+    assert out.shape == ref.shape
+    if pool == 'max':
+        assert torch.equal(torch.nan_to_num(out, nan=-7.0), torch.nan_to_num(ref, nan=-7.0))
+    else:
+        assert float((out - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+
+
+def test_clip_pooling_strided_rows_and_cpu_input():
+    from agrl.pytorch_b200 import models
+    big = torch.randn(12, 300, device='cuda')
+    view = big[:, 10:110]                                # row stride 300, unit column stride
+    out = models.pool_clips(view, 3, 'avg').cpu()
+    ref = view.cpu().view(4, 3, 100).mean(1)
+    assert float((out - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    with pytest.raises(RuntimeError):
+        models.pool_clips(torch.zeros(4, 8), 2)
