@@ -43,6 +43,8 @@ _SIGNATURES = {
     'agrl_launch_count': (ctypes.c_uint64, []),
     'agrl_profile_begin': (c_int, [c_vp]),
     'agrl_profile_end': (c_int, [ctypes.c_char_p, c_sz]),
+    'agrl_set_option': (c_int, [ctypes.c_char_p, c_i64]),
+    'agrl_get_option': (c_i64, [ctypes.c_char_p]),
     'agrl_rank_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64]),
     'agrl_rank_market1501_dev': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
@@ -136,6 +138,15 @@ def require_device():
     if rc != OK:
         raise AgrlError(rc, lib.agrl_status_string(rc).decode())
     return lib
+
+
+def set_option(name, value):
+    """Tuning knob of the library (agrl_set_option): e.g. ``set_option('head_sub_batch', 0)``."""
+    check(load().agrl_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(load().agrl_get_option(name.encode()))
 
 
 def launch_count():

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 namespace agrl {
@@ -20,11 +21,25 @@ struct Profiler {
     bool on = false;
     int n = 0;
     cudaEvent_t ev[kMax + 1];
+    cudaEvent_t begin[kMax + 1];       // optional explicit start of launch i (before_launch), else ev[i - 1]
+    bool has_begin[kMax + 1];
     const char *name[kMax + 1];
 };
 static thread_local Profiler tl_prof;
 
 bool profiling_active() { return tl_prof.on; }
+
+void before_launch(cudaStream_t st) {
+    Profiler &p = tl_prof;
+    if (!p.on || p.n >= Profiler::kMax || p.has_begin[p.n + 1]) return;
+    if (cudaEventCreate(&p.begin[p.n + 1]) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    if (cudaEventRecord(p.begin[p.n + 1], st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaEventDestroy(p.begin[p.n + 1]);
+        return;
+    }
+    p.has_begin[p.n + 1] = true;
+}
 
 void after_launch(cudaStream_t st, const char *name) {
     ++tl_launches;
@@ -33,11 +48,57 @@ void after_launch(cudaStream_t st, const char *name) {
         ++p.n;
         if (cudaEventCreate(&p.ev[p.n]) != cudaSuccess || cudaEventRecord(p.ev[p.n], st) != cudaSuccess) {
             (void)cudaGetLastError();
+            if (p.has_begin[p.n]) { cudaEventDestroy(p.begin[p.n]); p.has_begin[p.n] = false; }
             --p.n;
             return;
         }
         p.name[p.n] = name;
+        if (p.n < Profiler::kMax) p.has_begin[p.n + 1] = false;
     }
+}
+
+// ---- tuning knobs ---------------------------------------------------------------------------------
+struct OptionDef { const char *name, *env; int64_t def, lo, hi; };
+static const OptionDef kOptionDefs[kOptCount] = {
+    // tracklets per internal sub-batch of agrl_head_forward_dev (pooling of sub-batch i+1 runs on a side
+    // stream under the graph layers of sub-batch i); 0 = one pass, no side stream.  Measured on B200
+    // (profiles/r1/overlap_experiment.txt): co-running the pooling with the GEMM saturates L2, with the graph
+    // kernel the shared-memory pipe -- no net gain, so the default is one pass.
+    {"head_sub_batch", "AGRL_HEAD_SUB", 0, 0, 1 << 20},
+    // 1: persistent bulk-copy (TMA) pooling kernel; 0: the register-load pooling kernel
+    {"pool_tma", "AGRL_POOL_TMA", 1, 0, 1},
+    {"pool_stages", "AGRL_POOL_STAGES", 4, 2, 12},            // 16 KiB ring stages per pooling CTA
+    {"pool_ctas_per_sm", "AGRL_POOL_CTAS", 1, 1, 4},
+    {"graph_variant", "AGRL_GRAPH_VARIANT", 0, 0, 7},
+    {"pool_l2_hint", "AGRL_POOL_HINT", 1, 0, 1},              // evict-first hint on the pooling bulk copies
+    // sub-batched pipeline: 0 = poolings free-run on the side stream; 1 = pooling of sub-batch i+1 is cut into
+    // pieces that run only under the graph / attention kernels of sub-batch i (the GEMMs wait for their piece)
+    {"overlap_mode", "AGRL_OVERLAP_MODE", 1, 0, 1},
+};
+static std::atomic<int64_t> g_options[kOptCount];
+static std::atomic<int> g_options_init{0};
+
+static void init_options() {
+    if (g_options_init.load(std::memory_order_acquire) == 2) return;
+    int expect = 0;
+    if (g_options_init.compare_exchange_strong(expect, 1)) {
+        for (int i = 0; i < kOptCount; ++i) {
+            int64_t v = kOptionDefs[i].def;
+            const char *e = getenv(kOptionDefs[i].env);
+            if (e && *e) v = atoll(e);
+            if (v < kOptionDefs[i].lo) v = kOptionDefs[i].lo;
+            if (v > kOptionDefs[i].hi) v = kOptionDefs[i].hi;
+            g_options[i].store(v, std::memory_order_relaxed);
+        }
+        g_options_init.store(2, std::memory_order_release);
+    } else {
+        while (g_options_init.load(std::memory_order_acquire) != 2) {}
+    }
+}
+
+int64_t option(Option o) {
+    init_options();
+    return g_options[o].load(std::memory_order_relaxed);
 }
 
 // per-thread stream + stream-ordered scratch for the *_host entry points
@@ -106,6 +167,27 @@ extern "C" const char *agrl_status_string(int code) {
 }
 
 extern "C" const char *agrl_last_cuda_error(void) { return tl_error; }
+
+extern "C" int agrl_set_option(const char *name, int64_t value) {
+    if (!name) return AGRL_E_INVALID;
+    init_options();
+    for (int i = 0; i < kOptCount; ++i) {
+        if (strcmp(name, kOptionDefs[i].name) == 0) {
+            if (value < kOptionDefs[i].lo || value > kOptionDefs[i].hi) return AGRL_E_INVALID;
+            g_options[i].store(value, std::memory_order_relaxed);
+            return AGRL_OK;
+        }
+    }
+    return AGRL_E_INVALID;
+}
+
+extern "C" int64_t agrl_get_option(const char *name) {
+    if (!name) return -1;
+    init_options();
+    for (int i = 0; i < kOptCount; ++i)
+        if (strcmp(name, kOptionDefs[i].name) == 0) return g_options[i].load(std::memory_order_relaxed);
+    return -1;
+}
 extern "C" uint64_t agrl_launch_count(void) { return tl_launches; }
 
 extern "C" int agrl_device_ok(void) {
@@ -252,6 +334,7 @@ extern "C" int agrl_profile_begin(void *stream) {
     Profiler &p = tl_prof;
     if (p.on) return AGRL_E_INVALID;
     p.n = 0;
+    p.has_begin[0] = p.has_begin[1] = false;
     AGRL_CUDA_TRY(cudaEventCreate(&p.ev[0]));
     AGRL_CUDA_TRY(cudaEventRecord(p.ev[0], static_cast<cudaStream_t>(stream)));
     p.name[0] = "begin";
@@ -266,13 +349,18 @@ extern "C" int agrl_profile_end(char *text, size_t cap) {
     size_t off = 0;
     if (text && cap) text[0] = 0;
     int rc = AGRL_OK;
-    if (p.n > 0 && cudaEventSynchronize(p.ev[p.n]) != cudaSuccess) rc = AGRL_E_CUDA;
+    for (int i = 1; i <= p.n && rc == AGRL_OK; ++i)          // launches of one call may sit on several streams
+        if (cudaEventSynchronize(p.ev[i]) != cudaSuccess) rc = AGRL_E_CUDA;
     for (int i = 1; i <= p.n && rc == AGRL_OK; ++i) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, p.ev[i - 1], p.ev[i]) != cudaSuccess) { rc = AGRL_E_CUDA; break; }
+        if (cudaEventElapsedTime(&ms, p.has_begin[i] ? p.begin[i] : p.ev[i - 1], p.ev[i]) != cudaSuccess) { rc = AGRL_E_CUDA; break; }
         if (text && off + 64 < cap) off += snprintf(text + off, cap - off, "%s:%.6f;", p.name[i], ms);
     }
-    for (int i = 0; i <= p.n; ++i) cudaEventDestroy(p.ev[i]);
+    for (int i = 0; i <= p.n; ++i) {
+        cudaEventDestroy(p.ev[i]);
+        if (p.has_begin[i]) { cudaEventDestroy(p.begin[i]); p.has_begin[i] = false; }
+    }
+    if (p.n < Profiler::kMax && p.has_begin[p.n + 1]) { cudaEventDestroy(p.begin[p.n + 1]); p.has_begin[p.n + 1] = false; }
     p.n = 0;
     if (rc != AGRL_OK) (void)cudaGetLastError();
     return rc;

@@ -15,6 +15,14 @@ namespace agrl {
 // ---- host-side error plumbing --------------------------------------------------------------
 void        set_cuda_error(cudaError_t e, const char *what, const char *file, int line);
 void        after_launch(cudaStream_t st, const char *name);   // counts; records a profiling event when enabled
+// Optional: marks the start of the next launch on `st` (profiling only).  Launch sites that run kernels of
+// one call on several streams use it so that a kernel's time is begin->end on ITS stream; without it the
+// kernel is timed from the previous event (consecutive launches on one busy stream).
+void        before_launch(cudaStream_t st);
+
+// Process-wide tuning knobs (agrl_set_option / agrl_get_option; defaults may come from AGRL_* env vars).
+enum Option { kOptHeadSubBatch = 0, kOptPoolTma, kOptPoolStages, kOptPoolCtasPerSm, kOptGraphVariant, kOptPoolHint, kOptOverlapMode, kOptCount };
+int64_t     option(Option o);
 
 #define AGRL_CUDA_TRY(expr)                                                            \
     do {                                                                               \
@@ -26,6 +34,7 @@ void        after_launch(cudaStream_t st, const char *name);   // counts; record
     } while (0)
 
 // check the launch that just happened (configuration errors surface here without a sync)
+#define AGRL_LAUNCH_BEGIN(stream) ::agrl::before_launch(stream)
 #define AGRL_LAUNCH_CHECK(stream, name)                                                \
     do {                                                                               \
         AGRL_CUDA_TRY(cudaGetLastError());                                             \

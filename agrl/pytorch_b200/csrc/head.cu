@@ -146,6 +146,181 @@ pool_kernel(PoolArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// pooling, bulk-copy (TMA) flavour: a persistent, deliberately small CTA (1 producer + 4 consumer
+// warps, < 64 registers) that keeps its loads in flight in a shared-memory ring instead of in
+// registers, so that it can sit NEXT TO the graph / GEMM CTAs of the previous sub-batch on the same SM
+// and stream the maps at HBM speed underneath them.
+//   work unit   (tracklet b, 32-channel chunk): 2*S ring stages of 16 KiB, each one frame of one map
+//               (32 channels x 128 floats are contiguous in NCHW), fetched with one cp.async.bulk
+//               (L2 evict-first) that completes on the stage's mbarrier
+//   consumers   warp w owns channels 8w..8w+7 of the chunk: one conflict-free LDS.128 per lane covers a
+//               16x8 plane, strip sums by shuffles exactly as in pool_kernel
+//   output      node rows staged in (double-buffered) smem -> full 128-byte row segments
+// Requires h*w == 128 (the canonical 16x8 maps) and 16-byte aligned maps; otherwise pool_kernel runs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTpCh = 32;
+constexpr int kTpStageBytes = kTpCh * 128 * 4;
+constexpr int kTpConsumerWarps = 4;
+constexpr int kTpThreads = 32 * (1 + kTpConsumerWarps);
+
+struct PoolTmaArgs {
+    const float *x41, *x42;            // (batch*S, C, 128), already offset to this sub-batch
+    float *nodes;                      // (batch, V, C)
+    float *out; int64_t ld_out;        // (batch, 2C)
+    const float *g_scale, *g_shift;
+    int S, C, stages;
+    int unit0, unit1;                  // work units [unit0, unit1) of this launch (unit = tracklet * C/32 + chunk)
+    int l2_hint;                       // 1: evict-first cache hint on the bulk copies
+};
+
+static size_t pool_tma_smem(int S, int stages) {
+    return static_cast<size_t>(stages) * kTpStageBytes + 2 * static_cast<size_t>(S) * kParts * kTpCh * sizeof(float) +
+           2 * static_cast<size_t>(stages) * 8 + 128;
+}
+
+__device__ __forceinline__ void bulk_load_evict_first(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
+                                                      uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+
+// Sum 8 per-lane values over the 8 lanes of each 8-lane group in 7 shuffles (instead of 24): after the xor-4 / 2 / 1
+// exchange steps lane `sub` of a group holds the group's total of a[sub].  Pairing order == plain butterflies.
+__device__ __forceinline__ float group8_transpose_sum(const float (&a)[8], int sub) {
+    float b[4], c[2];
+    const bool h4 = (sub & 4) != 0, h2 = (sub & 2) != 0, h1 = (sub & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float send = h4 ? a[j] : a[j + 4], keep = h4 ? a[j + 4] : a[j];
+        b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = h2 ? b[j] : b[j + 2], keep = h2 ? b[j + 2] : b[j];
+        c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float send = h1 ? c[0] : c[1], keep = h1 ? c[1] : c[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __maxnreg__(48)
+pool_tma_kernel(PoolTmaArgs a) {
+    extern __shared__ __align__(16) unsigned char tp_smem_dyn[];
+    // align to 128 B by OFFSET (not by casting through an integer) so that the compiler keeps emitting LDS / STS
+    unsigned char *smem = tp_smem_dyn + ((128u - (gemm::smem_u32(tp_smem_dyn) & 127u)) & 127u);
+    const int stages = a.stages, S = a.S, C = a.C, V = S * kParts;
+    const float4 *ring_f4 = reinterpret_cast<const float4 *>(smem);
+    float *s_nodes = reinterpret_cast<float *>(smem + stages * kTpStageBytes);   // [2][V][32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_nodes + 2 * V * kTpCh);
+    const uint32_t ring = gemm::smem_u32(smem);
+    const uint32_t bar_full = gemm::smem_u32(bars), bar_empty = bar_full + 8 * stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = C / kTpCh;
+    const int units = a.unit1;
+    const int first = a.unit0 + blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { gemm::mbar_init(bar_full + 8 * i, 1); gemm::mbar_init(bar_empty + 8 * i, kTpConsumerWarps); }
+        gemm::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= producer: one thread issues every bulk copy of this CTA =================
+        if (lane == 0) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            int stage = 0; uint32_t phase = 0;
+            for (int u = first; u < units; u += gridDim.x) {
+                const int b = u / chunks, cc = u % chunks;
+                for (int s = 0; s < S; ++s) {
+                    const size_t off = ((static_cast<size_t>(b) * S + s) * C + static_cast<size_t>(cc) * kTpCh) * 128;
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        gemm::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        gemm::mbar_arrive_expect_tx(full, kTpStageBytes);
+                        if (a.l2_hint) bulk_load_evict_first(ring + stage * kTpStageBytes, (m ? a.x42 : a.x41) + off, kTpStageBytes, full, policy);
+                        else bulk_load(ring + stage * kTpStageBytes, (m ? a.x42 : a.x41) + off, kTpStageBytes, full);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= consumers =================
+        const int cw = warp - 1, ct = threadIdx.x - 32;           // consumer warp / thread index
+        const int grp = lane >> 3, sub = lane & 7;                // 8-lane group <-> quarter strip (4 rows of 8)
+        const float inv_all = 1.0f / (static_cast<float>(S) * 128.0f);
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int u = first; u < units; u += gridDim.x, ++it) {
+            const int b = u / chunks, c0 = (u % chunks) * kTpCh;
+            float *sn = s_nodes + (it & 1) * V * kTpCh;
+            float gsum[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gsum[i] = 0.f;
+            for (int s = 0; s < S; ++s) {
+                // ---- layer4_1 frame: only the global mean needs it -> per-lane partial sums ----
+                gemm::mbar_wait(bar_full + 8 * stage, phase);
+                {
+                    const float4 *p = ring_f4 + stage * (kTpStageBytes / 16) + (cw * 8) * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 v = p[i * 32];
+                        gsum[i] += (v.x + v.y) + (v.z + v.w);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) gemm::mbar_arrive(bar_empty + 8 * stage);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+                // ---- layer4_2 frame: quarter / half / whole strip means -> node rows ----
+                gemm::mbar_wait(bar_full + 8 * stage, phase);
+                {
+                    const float4 *p = ring_f4 + stage * (kTpStageBytes / 16) + (cw * 8) * 32 + lane;
+                    float q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 v = p[i * 32];
+                        q[i] = (v.x + v.y) + (v.z + v.w);
+                    }
+                    __syncwarp();
+                    if (lane == 0) gemm::mbar_arrive(bar_empty + 8 * stage);      // values are in registers
+                    // lane (grp, sub) ends with channel `sub`'s sum over quarter strip `grp`
+                    const float v2 = group8_transpose_sum(q, sub);
+                    const float h2 = v2 + __shfl_xor_sync(0xffffffffu, v2, 8);       // half strips
+                    const float w2 = h2 + __shfl_xor_sync(0xffffffffu, h2, 16);      // whole map
+                    float *dst = sn + (s * kParts) * kTpCh + cw * 8 + sub;
+                    dst[grp * kTpCh] = v2 * (1.0f / 32.0f);                          // parts 0..3
+                    if ((grp & 1) == 0) dst[(4 + (grp >> 1)) * kTpCh] = h2 * (1.0f / 64.0f);
+                    if (grp == 0) dst[6 * kTpCh] = w2 * (1.0f / 128.0f);
+                }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            // global branch: mean over (S, h, w), BN neck; lane (grp, sub) ends with channel `sub`'s total
+            {
+                float t = group8_transpose_sum(gsum, sub);
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                if (grp == 0) {
+                    const int c = c0 + cw * 8 + sub;
+                    a.out[static_cast<size_t>(b) * a.ld_out + c] = fmaf(t * inv_all, a.g_scale[c], a.g_shift[c]);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kTpConsumerWarps) : "memory");   // node tile complete
+            float *nodes = a.nodes + static_cast<size_t>(b) * V * C + c0;
+            for (int v = ct >> 5; v < V; v += kTpConsumerWarps) nodes[static_cast<size_t>(v) * C + lane] = sn[v * kTpCh + lane];
+            // (the other s_nodes buffer is used next; this one is rewritten only after the next unit's barrier)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // graph kernel: one CTA per tracklet
 // ------------------------------------------------------------------------------------------------
 constexpr int kChunk = 128;                 // channels staged per step (double buffered)
@@ -207,8 +382,8 @@ __device__ __forceinline__ void for_each_chunk(float *xs0, float *xs1, const flo
     }
 }
 
-template <int NT, int kBufs, int kMinBlocks>   // NT = ceil(V/4): 14 for the canonical V = 56
-__global__ void __launch_bounds__(kHeadThreads, kMinBlocks)
+template <int NT, int kBufs, int kMaxRegs>     // NT = ceil(V/4): 14 for the canonical V = 56
+__global__ void __maxnreg__(kMaxRegs)
 graph_kernel(GraphArgs a) {
     constexpr int kRows = 4 * NT;                      // staged rows (>= V; the rest stay zero)
     constexpr int kTiles = NT * (NT + 1) / 2;          // 4x4 Gram tiles of the upper triangle
@@ -452,30 +627,30 @@ static int check_params(const agrl_head_params *p) {
     return AGRL_OK;
 }
 
-template <int NT, int kBufs, int kMinBlocks>
+template <int NT, int kBufs, int kMaxRegs>
 static int launch_graph_variant(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
     const size_t smem = (static_cast<size_t>(kBufs * 4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
-    auto kern = graph_kernel<NT, kBufs, kMinBlocks>;
+    auto kern = graph_kernel<NT, kBufs, kMaxRegs>;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
     AGRL_LAUNCH_CHECK(st, "graph");
     return AGRL_OK;
 }
 
-// AGRL_GRAPH_VARIANT (tuning knob): 0 = double-buffered, 2 CTAs/SM; 1 = single buffer, 3 CTAs/SM;
-// 2 = single buffer, 2 CTAs/SM; 3 = double-buffered, 3 CTAs/SM register budget
-static int graph_variant() {
-    static int v = [] { const char *e = getenv("AGRL_GRAPH_VARIANT"); return e ? atoi(e) : 0; }();
-    return v;
-}
+// option "graph_variant" (staging buffers, register cap -> CTAs per SM; 77 KiB smem double-buffered, 47 KiB single):
+//   0 = double, 128 (2/SM)   1 = single, 80 (3/SM)   2 = single, 128 (2/SM)   3 = double, 80
+//   4 = double, 112 and 5 = single, 112: two CTAs per SM NEXT TO a resident pooling CTA (48 regs x 160 threads)
+static int graph_variant() { return static_cast<int>(option(kOptGraphVariant)); }
 
 template <int NT>
 static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
     switch (graph_variant()) {
-        case 1: return launch_graph_variant<NT, 1, 3>(ga, batch, st);
-        case 2: return launch_graph_variant<NT, 1, 2>(ga, batch, st);
-        case 3: return launch_graph_variant<NT, 2, 3>(ga, batch, st);
-        default: return launch_graph_variant<NT, 2, 2>(ga, batch, st);
+        case 1: return launch_graph_variant<NT, 1, 80>(ga, batch, st);
+        case 2: return launch_graph_variant<NT, 1, 128>(ga, batch, st);
+        case 3: return launch_graph_variant<NT, 2, 80>(ga, batch, st);
+        case 4: return launch_graph_variant<NT, 2, 112>(ga, batch, st);
+        case 5: return launch_graph_variant<NT, 1, 112>(ga, batch, st);
+        default: return launch_graph_variant<NT, 2, 128>(ga, batch, st);
     }
 }
 
@@ -522,6 +697,163 @@ extern "C" size_t agrl_head_workspace_bytes(const agrl_head_params *p, int64_t b
     return carve_head(p, nullptr, batch, seq_len).bytes;
 }
 
+namespace agrl {
+
+// Side stream + events of the sub-batched pipeline: one set per host thread (the ABI is re-entrant: one
+// host thread per GPU), created at first use and kept.
+constexpr int kMaxSubBatches = 64;
+struct HeadCtx {
+    cudaStream_t side = nullptr;
+    cudaEvent_t entry = nullptr, pooled[kMaxSubBatches] = {};
+    // gated pipeline: per sub-batch and partner kernel (graph layers.., attention) a "partner may start" event on the
+    // caller's stream and a "pooling piece done" event on the side stream
+    cudaEvent_t start[kMaxSubBatches][AGRL_HEAD_MAX_LAYERS + 1] = {}, piece[kMaxSubBatches][AGRL_HEAD_MAX_LAYERS + 1] = {};
+    int device = -1;
+    int ensure() {
+        int dev = -1;
+        AGRL_CUDA_TRY(cudaGetDevice(&dev));
+        if (side && dev == device) return AGRL_OK;
+        if (side) {
+            cudaStreamDestroy(side); side = nullptr;
+            cudaEventDestroy(entry);
+            for (int i = 0; i < kMaxSubBatches; ++i) {
+                cudaEventDestroy(pooled[i]);
+                for (int k = 0; k <= AGRL_HEAD_MAX_LAYERS; ++k) { cudaEventDestroy(start[i][k]); cudaEventDestroy(piece[i][k]); }
+            }
+        }
+        int lo = 0, hi = 0;
+        AGRL_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        AGRL_CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));     // highest priority
+        AGRL_CUDA_TRY(cudaEventCreateWithFlags(&entry, cudaEventDisableTiming));
+        for (int i = 0; i < kMaxSubBatches; ++i) {
+            AGRL_CUDA_TRY(cudaEventCreateWithFlags(&pooled[i], cudaEventDisableTiming));
+            for (int k = 0; k <= AGRL_HEAD_MAX_LAYERS; ++k) {
+                AGRL_CUDA_TRY(cudaEventCreateWithFlags(&start[i][k], cudaEventDisableTiming));
+                AGRL_CUDA_TRY(cudaEventCreateWithFlags(&piece[i][k], cudaEventDisableTiming));
+            }
+        }
+        device = dev;
+        return AGRL_OK;
+    }
+};
+static thread_local HeadCtx tl_head_ctx;
+
+// pooling of `n` tracklets starting at tracklet `b0`, on stream `st`
+// (TMA flavour only: `part` / `parts` selects a contiguous slice of the work units, see the gated pipeline)
+static int launch_pool(const agrl_head_params *p, const Prepared &pr, const HeadWorkspace &hwk, const float *x4_1,
+                       const float *x4_2, float *out, int64_t ld_out, int64_t b0, int64_t n, int S, int hw, bool tma,
+                       int ctas_per_sm, cudaStream_t st, int64_t unit_lo = 0, int64_t unit_hi = -1) {
+    const int C = p->channels, V = S * kParts, L = p->num_layers;
+    const size_t in_off = static_cast<size_t>(b0) * S * C * hw;
+    float *nodes = hwk.x[0] + static_cast<size_t>(b0) * V * C;
+    float *o = out + static_cast<size_t>(b0) * ld_out;
+    AGRL_LAUNCH_BEGIN(st);
+    if (tma) {
+        const int64_t all_units = n * (C / kTpCh);
+        if (unit_hi < 0) unit_hi = all_units;
+        if (unit_hi <= unit_lo) return AGRL_OK;
+        PoolTmaArgs ta{x4_1 + in_off, x4_2 + in_off, nodes, o, ld_out, pr.scale[L], pr.shift[L], S, C,
+                       static_cast<int>(option(kOptPoolStages)), static_cast<int>(unit_lo), static_cast<int>(unit_hi),
+                       static_cast<int>(option(kOptPoolHint))};
+        const size_t smem = pool_tma_smem(S, ta.stages);
+        AGRL_CUDA_TRY(cudaFuncSetAttribute(pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const int64_t units = unit_hi - unit_lo;
+        int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+        if (grid > units) grid = units;
+        pool_tma_kernel<<<static_cast<unsigned>(grid), kTpThreads, smem, st>>>(ta);
+        AGRL_LAUNCH_CHECK(st, "pool");
+        return AGRL_OK;
+    }
+    PoolArgs pa{x4_1 + in_off, x4_2 + in_off, nodes, o, ld_out, pr.scale[L], pr.shift[L], S, C, hw};
+    const size_t pool_smem = static_cast<size_t>(S) * kParts * kPoolCh * sizeof(float);
+    const dim3 pgrid(C / kPoolCh, static_cast<unsigned>(n));
+    const bool vec = (hw == 128) && ((reinterpret_cast<uintptr_t>(x4_1) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(x4_2) & 15u) == 0);
+    if (vec) pool_kernel<true><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
+    else pool_kernel<false><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
+    AGRL_LAUNCH_CHECK(st, "pool");
+    return AGRL_OK;
+}
+
+// Gated pipeline hook: the pooling of the NEXT sub-batch is cut into one piece per "partner" kernel of this
+// sub-batch (graph kernel of each layer, attention).  A piece starts when its partner may start and the GEMM
+// that follows the partner waits for the piece: the HBM stream runs under the CUDA-core kernels only, never
+// under the GEMMs (GEMM and pooling together exceed the L2 throughput and evict each other's lines).
+struct Gate {
+    HeadCtx *ctx;
+    int j;                                   // this sub-batch
+    int64_t next_b0, next_n;                 // the sub-batch whose pooling is hidden here (next_n == 0: none)
+    const agrl_head_params *p; const Prepared *pr; const HeadWorkspace *hwk;
+    const float *x4_1, *x4_2; float *out; int64_t ld_out; int S, hw, ctas;
+    // partner k of L+1: units [lo, hi) of the next sub-batch's pooling
+    int partner(int k, int L, cudaStream_t st) const {
+        if (next_n == 0) return AGRL_OK;
+        const int64_t units = next_n * (p->channels / kTpCh);
+        const double wa = 0.25, tot = L + wa;                       // graph kernels weigh 1, attention 0.25
+        auto edge = [&](int i) { return i >= L + 1 ? units : static_cast<int64_t>(units * (i / tot)); };
+        AGRL_CUDA_TRY(cudaEventRecord(ctx->start[j][k], st));
+        AGRL_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->start[j][k], 0));
+        int rc = launch_pool(p, *pr, *hwk, x4_1, x4_2, out, ld_out, next_b0, next_n, S, hw, true, ctas, ctx->side, edge(k), edge(k + 1));
+        if (rc) return rc;
+        AGRL_CUDA_TRY(cudaEventRecord(ctx->piece[j][k], ctx->side));
+        return AGRL_OK;
+    }
+    int join(int k, cudaStream_t st) const {                      // the caller's stream waits for piece k
+        if (next_n == 0) return AGRL_OK;
+        AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx->piece[j][k], 0));
+        return AGRL_OK;
+    }
+};
+
+// graph layers + attention of `n` tracklets starting at tracklet `b0` (their nodes are in hwk.x[0])
+static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWorkspace hwk, const float *adj, float *out,
+                         int64_t ld_out, float *nodes_out, int64_t b0, int64_t n, int64_t batch, int S, cudaStream_t st,
+                         const Gate *gate = nullptr) {
+    const int C = p->channels, V = S * kParts, L = p->num_layers;
+    const int64_t rows = n * V, row0 = b0 * V, all_rows = batch * V;
+    float *x[2] = {hwk.x[0] + row0 * C, hwk.x[1] + row0 * C};
+    __nv_bfloat16 *y = hwk.y_planes + row0 * C;
+    if (nodes_out) nodes_out += row0 * C;
+    if (adj) adj += b0 * V * V;
+    int rc;
+    CUtensorMap map_y, map_w;
+    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, y, rows, C, p->split, gemm::BM, all_rows))) return rc;
+    int cur = 0;
+    for (int l = 0; l < L; ++l) {
+        GraphArgs ga{x[cur], adj, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph};
+        if (gate && (rc = gate->partner(l, L, st))) return rc;
+        AGRL_LAUNCH_BEGIN(st);
+        if (V == 56) rc = launch_graph<14>(ga, n, st); else rc = launch_graph<16>(ga, n, st);
+        if (rc) return rc;
+        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, p->split == AGRL_SPLIT_BF16X3 ? 128 : 256, C))) return rc;
+        float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
+        gemm::EpiGraphLayer epi{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope};
+        if (gate && (rc = gate->join(l, st))) return rc;
+        AGRL_LAUNCH_BEGIN(st);
+        if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        else rc = gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        if (rc) return rc;
+        if (dst == nodes_out) x[cur ^ 1] = nodes_out;
+        cur ^= 1;
+    }
+    if (L == 0 && nodes_out)
+        AGRL_CUDA_TRY(cudaMemcpyAsync(nodes_out, x[0], sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
+    AttnArgs aa{x[cur], out + static_cast<size_t>(b0) * ld_out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C};
+    if (gate && (rc = gate->partner(L, L, st))) return rc;
+    AGRL_LAUNCH_BEGIN(st);
+    attn_kernel<<<static_cast<unsigned>(n), kHeadThreads, 0, st>>>(aa);
+    AGRL_LAUNCH_CHECK(st, "attn");
+    if (gate && (rc = gate->join(L, st))) return rc;              // the next sub-batch's nodes are complete
+    return AGRL_OK;
+}
+
+}  // namespace agrl
+
+// Pipeline.  The maps are the only HBM-heavy input; everything after the pooling works on the 27x smaller
+// node tensor and is bound by the tensor pipe / CUDA cores.  With batch > head_sub_batch the batch is cut
+// into sub-batches: all poolings are queued on a high-priority side stream (persistent, small CTAs), the
+// graph layers + attention of sub-batch i wait for pooling i on the caller's stream -- so pooling i+1
+// streams from HBM underneath the compute of sub-batch i.  The caller's stream observes every kernel of
+// the call (it waits on each pooling event), so stream-ordered use of `out` stays valid.
 extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prepared,
                                      const float *x4_1, const float *x4_2, const float *adj,
                                      float *out, int64_t ld_out, float *nodes_out,
@@ -533,49 +865,60 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     if (p->use_pose && !adj) return AGRL_E_INVALID;
     const int C = p->channels, V = S * kParts, hw = h * w;
     if (ld_out < 2 * C) return AGRL_E_INVALID;
-    if (V > kMaxNodes || h % 4 != 0 || batch > 65535) return AGRL_E_UNSUPPORTED;
+    if (V > kMaxNodes || h % 4 != 0) return AGRL_E_UNSUPPORTED;
     if ((rc = agrl_device_ok())) return rc;
     if (batch == 0) return AGRL_OK;
     HeadWorkspace hwk = carve_head(p, ws, batch, S);
     if (!ws || ws_bytes < hwk.bytes) return AGRL_E_WORKSPACE;
     Prepared pr = carve_prepared(p, const_cast<void *>(prepared));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int L = p->num_layers;
+    if (!p->use_pose) adj = nullptr;
 
-    // 1. pooling (+ global branch)
-    PoolArgs pa{x4_1, x4_2, hwk.x[0], out, ld_out, pr.scale[L], pr.shift[L], S, C, hw};
-    const size_t pool_smem = static_cast<size_t>(S) * kParts * kPoolCh * sizeof(float);
-    const dim3 pgrid(C / kPoolCh, static_cast<unsigned>(batch));
-    const bool vec = (hw == 128) && ((reinterpret_cast<uintptr_t>(x4_1) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(x4_2) & 15u) == 0);
-    if (vec) pool_kernel<true><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
-    else pool_kernel<false><<<pgrid, kHeadThreads, pool_smem, st>>>(pa);
-    AGRL_LAUNCH_CHECK(st, "pool");
+    const bool tma = option(kOptPoolTma) != 0 && hw == 128 && C % kTpCh == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x4_1) | reinterpret_cast<uintptr_t>(x4_2)) & 15u) == 0;
+    int64_t sub = option(kOptHeadSubBatch);
+    if (sub > 0 && (batch + sub - 1) / sub > kMaxSubBatches) sub = (batch + kMaxSubBatches - 1) / kMaxSubBatches;
+    const int ctas = static_cast<int>(option(kOptPoolCtasPerSm));
+    constexpr int64_t kMaxPerLaunch = 32768;           // grid.y / int index limits of the per-tracklet kernels
 
-    // 2. graph layers
-    const int64_t rows = batch * V;
-    CUtensorMap map_y, map_w;
-    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, hwk.y_planes, rows, C, p->split, gemm::BM, rows))) return rc;
-    int cur = 0;
-    for (int l = 0; l < L; ++l) {
-        GraphArgs ga{hwk.x[cur], adj, hwk.y_planes, rows * C, V, C, p->split, p->use_pose, p->learn_graph};
-        if (V == 56) rc = launch_graph<14>(ga, batch, st); else rc = launch_graph<16>(ga, batch, st);
-        if (rc) return rc;
-        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, p->split == AGRL_SPLIT_BF16X3 ? 128 : 256, C))) return rc;
-        float *dst = (l == L - 1 && nodes_out) ? nodes_out : hwk.x[cur ^ 1];
-        gemm::EpiGraphLayer epi{hwk.x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope};
-        if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
-        else rc = gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
-        if (rc) return rc;
-        if (dst == nodes_out) { hwk.x[cur ^ 1] = nodes_out; }
-        cur ^= 1;
+    if (sub <= 0 || batch <= sub) {
+        // one pass on the caller's stream
+        for (int64_t b0 = 0; b0 < batch; b0 += kMaxPerLaunch) {
+            const int64_t n = batch - b0 < kMaxPerLaunch ? batch - b0 : kMaxPerLaunch;
+            if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, tma ? 2 : 1, st))) return rc;
+            if ((rc = launch_layers(p, pr, hwk, adj, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
+        }
+        return AGRL_OK;
     }
-    if (L == 0 && nodes_out)
-        AGRL_CUDA_TRY(cudaMemcpyAsync(nodes_out, hwk.x[0], sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
-
-    // 3. attention + neck
-    AttnArgs aa{hwk.x[cur], out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C};
-    attn_kernel<<<static_cast<unsigned>(batch), kHeadThreads, 0, st>>>(aa);
-    AGRL_LAUNCH_CHECK(st, "attn");
+    HeadCtx &ctx = tl_head_ctx;
+    if ((rc = ctx.ensure())) return rc;
+    const int nsub = static_cast<int>((batch + sub - 1) / sub);
+    AGRL_CUDA_TRY(cudaEventRecord(ctx.entry, st));
+    AGRL_CUDA_TRY(cudaStreamWaitEvent(ctx.side, ctx.entry, 0));
+    if (tma && option(kOptOverlapMode) == 1) {
+        // gated: pooling 0 alone (2 CTAs per SM), then every sub-batch hides the next one's pooling pieces
+        const int64_t n0 = batch < sub ? batch : sub;
+        if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, 0, n0, S, hw, true, 2, ctx.side))) return rc;
+        AGRL_CUDA_TRY(cudaEventRecord(ctx.pooled[0], ctx.side));
+        AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx.pooled[0], 0));
+        for (int j = 0; j < nsub; ++j) {
+            const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
+            const int64_t nb0 = b0 + n, nn = j + 1 < nsub ? (batch - nb0 < sub ? batch - nb0 : sub) : 0;
+            Gate gate{&ctx, j, nb0, nn, p, &pr, &hwk, x4_1, x4_2, out, ld_out, S, hw, ctas};
+            if ((rc = launch_layers(p, pr, hwk, adj, out, ld_out, nodes_out, b0, n, batch, S, st, &gate))) return rc;
+        }
+        return AGRL_OK;
+    }
+    for (int j = 0; j < nsub; ++j) {
+        const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
+        if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, ctas, ctx.side))) return rc;
+        AGRL_CUDA_TRY(cudaEventRecord(ctx.pooled[j], ctx.side));
+    }
+    for (int j = 0; j < nsub; ++j) {
+        const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
+        AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx.pooled[j], 0));
+        if ((rc = launch_layers(p, pr, hwk, adj, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
+    }
     return AGRL_OK;
 }
 

@@ -190,8 +190,9 @@ class VMGN(nn.Module):
             self._prep_key, self._prep_buf = key, buf
         return self._prep_buf
 
-    def head(self, x4_1, x4_2, adj, seq_len, return_nodes=False):
-        """vmgn.py:296-321 on the GPU: (B*S,C,h,w) x2 + (B,V,V) -> (B, 2C)."""
+    def head(self, x4_1, x4_2, adj, seq_len, return_nodes=False, out=None):
+        """vmgn.py:296-321 on the GPU: (B*S,C,h,w) x2 + (B,V,V) -> (B, 2C).
+        ``out``: optional preallocated (B, 2C) fp32 CUDA tensor (unit column stride) to write into."""
         lib = _lib.require_device()
         if not x4_1.is_cuda:
             raise RuntimeError('agrl.pytorch_b200 has no CPU path: move the model and inputs to a B200')
@@ -212,7 +213,11 @@ class VMGN(nn.Module):
             wsb = lib.agrl_head_workspace_bytes(ctypes.byref(P), B, seq_len)
             if self._ws is None or self._ws.device != dev or self._ws.numel() < wsb:
                 self._ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-            out = torch.empty(B, 2 * C, dtype=torch.float32, device=dev)
+            if out is None:
+                out = torch.empty(B, 2 * C, dtype=torch.float32, device=dev)
+            else:
+                assert out.dtype == torch.float32 and out.device == dev and tuple(out.shape) == (B, 2 * C) \
+                    and out.stride(1) == 1, 'out must be a (B, 2C) fp32 tensor on the input device'
             nodes = torch.empty(B, V, C, dtype=torch.float32, device=dev) if return_nodes else None
             _lib.check(lib.agrl_head_forward_dev(
                 ctypes.byref(P), prepared.data_ptr(), x4_1.data_ptr(), x4_2.data_ptr(),

@@ -184,7 +184,7 @@ def run_b200(args):
 
     def head_pass():
         for off, n in chunks:
-            feats[off:off + n] = model.head(x1[:n * S], x2[:n * S], adj[:n], S)
+            model.head(x1[:n * S], x2[:n * S], adj[:n], S, out=feats[off:off + n])
 
     def eval_pass():
         if world == 1:

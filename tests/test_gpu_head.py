@@ -150,3 +150,86 @@ def test_clip_pooling_strided_rows_and_cpu_input():
     assert float((out - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
     with pytest.raises(RuntimeError):
         models.pool_clips(torch.zeros(4, 8), 2)
+
+
+@pytest.fixture
+def restore_options():
+    from agrl.pytorch_b200 import _lib
+    names = ('head_sub_batch', 'pool_tma', 'pool_stages', 'pool_ctas_per_sm', 'graph_variant', 'pool_l2_hint',
+             'overlap_mode')
+    saved = {n: _lib.get_option(n) for n in names}
+    yield _lib
+    for n, v in saved.items():
+        _lib.set_option(n, v)
+
+
+def test_pipeline_modes_agree(restore_options):
+    """One pass vs sub-batched (pooling on the side stream), bulk-copy vs register-load pooling, every graph
+    variant: the sub-batched run is bit-identical to the one-pass run with the same kernels; the two pooling
+    kernels differ only in the summation order of the global mean."""
+    lib = restore_options
+    S, B = 8, 11
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=60, scale=2.0)
+    adj = synth.pose_adjacency(B, S, 7, seed=61)
+    wts = synth.head_weights(2048, 2, seed=62, randomise_bn=True)
+    model = make_model(wts)
+    ref = ohead.head_forward(x1, x2, adj, wts, dtype=torch.float64)
+    x1, x2, adj = x1.cuda(), x2.cuda(), adj.cuda()
+    outs = {}
+    for tma in (0, 1):
+        for sub in (0, 1, 3, 4, 11):
+            for stages in ((2, 5) if tma else (4,)):
+                lib.set_option('pool_tma', tma); lib.set_option('head_sub_batch', sub); lib.set_option('pool_stages', stages)
+                lib.set_option('overlap_mode', stages == 5)          # gated pieces / free-running side stream
+                lib.set_option('pool_l2_hint', sub % 2)
+                for _ in range(2):                                   # twice: the side stream / events are reused
+                    with torch.no_grad():
+                        out = model.head(x1, x2, adj, S)
+                torch.cuda.synchronize()
+                emax, enrm = rel_err(out.cpu(), ref)
+                assert emax < TOL and enrm < TOL, (tma, sub, stages, emax, enrm)
+                outs[(tma, sub, stages)] = out.cpu()
+    for tma in (0, 1):
+        base = outs[(tma, 0, 2 if tma else 4)]
+        for key, o in outs.items():
+            if key[0] == tma:
+                assert torch.equal(o, base), key
+    emax, _ = rel_err(outs[(1, 0, 2)], outs[(0, 0, 4)])
+    assert emax < 2e-6
+    lib.set_option('head_sub_batch', 4)
+    for variant in range(6):
+        lib.set_option('graph_variant', variant)
+        with torch.no_grad():
+            out = model.head(x1, x2, adj, S)
+        emax, enrm = rel_err(out.cpu(), ref)
+        assert emax < TOL and enrm < TOL, (variant, emax, enrm)
+
+
+def test_sub_batched_head_into_preallocated_rows_and_nodes(restore_options):
+    """out= view of a larger feature matrix (what bench.py and a test loop do), nodes copy, ragged last sub-batch"""
+    lib = restore_options
+    S, B = 8, 7
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=70)
+    adj = synth.pose_adjacency(B, S, 7, seed=71)
+    wts = synth.head_weights(2048, 2, seed=72, randomise_bn=True)
+    model = make_model(wts)
+    ref, _, nodes_ref = ohead.head_forward(x1, x2, adj, wts, dtype=torch.float64, return_nodes=True)
+    lib.set_option('head_sub_batch', 3)
+    feats = torch.full((B + 4, 4096), 7.0, device='cuda')
+    with torch.no_grad():
+        out, nodes = model.head(x1.cuda(), x2.cuda(), adj.cuda(), S, return_nodes=True, out=feats[2:2 + B])
+    assert out.data_ptr() == feats[2:].data_ptr()
+    emax, enrm = rel_err(feats[2:2 + B].cpu(), ref)
+    assert emax < TOL and enrm < TOL
+    nmax, nnrm = rel_err(nodes.cpu(), nodes_ref)
+    assert nmax < TOL and nnrm < TOL
+    assert float(feats[:2].min()) == 7.0 and float(feats[2 + B:].min()) == 7.0      # neighbours untouched
+
+
+def test_options_api():
+    from agrl.pytorch_b200 import _lib
+    assert _lib.get_option('no_such_option') == -1
+    with pytest.raises(ValueError):
+        _lib.set_option('no_such_option', 1)
+    with pytest.raises(ValueError):
+        _lib.set_option('pool_stages', 1000)

@@ -1,0 +1,68 @@
+"""Head-pipeline variants on one resident input pool (one process, options switched at run time).
+usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint call)
+`call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from agrl.pytorch_b200 import _lib
+
+KEYS = {'sub': 'head_sub_batch', 'tma': 'pool_tma', 'stages': 'pool_stages', 'ctas': 'pool_ctas_per_sm', 'graph': 'graph_variant',
+        'mode': 'overlap_mode', 'hint': 'pool_l2_hint'}
+
+
+def main():
+    pool_n = int(sys.argv[1])
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    _lib.require_device()
+    model = bench.make_model(dev, bench.make_head_weights())
+    x1, x2, adj = bench.make_pool(pool_n, dev, seed=1)
+    J, S = int(os.environ.get('HV_TRACKLETS', bench.NQ + bench.NG)), bench.S
+    feats = torch.empty(J, 2 * bench.C, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    defaults = {k: _lib.get_option(v) for k, v in KEYS.items()}
+    for spec in sys.argv[2:]:
+        cfg = dict(defaults)
+        cfg['call'] = pool_n
+        for kv in spec.split(','):
+            if kv:
+                k, v = kv.split('=')
+                cfg[k] = int(v)
+        for k, name in KEYS.items():
+            _lib.set_option(name, cfg[k])
+        call = min(cfg['call'], pool_n)
+        chunks = [(o, min(call, J - o)) for o in range(0, J, call)]
+
+        def head_pass():
+            for off, n in chunks:
+                model.head(x1[:n * S], x2[:n * S], adj[:n], S, out=feats[off:off + n])
+        try:
+            with torch.no_grad():
+                for _ in range(2):
+                    head_pass()
+                torch.cuda.synchronize()
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                for i in range(3):
+                    e[i].record(stream); head_pass()
+                e[3].record(stream)
+                torch.cuda.synchronize()
+                ms = [e[i].elapsed_time(e[i + 1]) for i in range(3)]
+                with _lib.profile(stream.cuda_stream) as prof:
+                    head_pass()
+                tot = {k: round(t, 3) for k, (n, t) in prof.totals().items()}
+            best = min(ms)
+            print(json.dumps({'spec': spec, 'head_ms': round(best, 3), 'all': [round(m, 3) for m in ms],
+                              'ktracklets_s': round(J / best, 1),
+                              'hbm_frac': round(J * bench.BYTES_PER_TRACKLET / (best * 1e-3) / 1e9 / 6545.9, 4),
+                              'checksum': float(feats.double().sum()), 'kernels': tot}), flush=True)
+        except Exception as ex:  # noqa
+            print(json.dumps({'spec': spec, 'error': repr(ex)}), flush=True)
+
+
+if __name__ == '__main__':
+    main()
