@@ -15,7 +15,7 @@ E_INVALID, E_NO_DEVICE, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 E_NO_VALID_QUERY, E_ZERO_DIVISION, E_LABEL_RANGE = -6, -7, -8
 ST_NO_VALID_QUERY, ST_ZERO_DIVISION, ST_LABEL_RANGE = 1, 2, 4
 METRIC_EUCLIDEAN, METRIC_COSINE = 0, 1
-SPLIT_BF16X3, SPLIT_BF16X2 = 3, 2
+SPLIT_BF16X3, SPLIT_BF16X2, SPLIT_FP16X1 = 3, 2, 1
 CLIP_POOL_AVG, CLIP_POOL_MAX = 0, 1
 HEAD_MAX_LAYERS = 4
 

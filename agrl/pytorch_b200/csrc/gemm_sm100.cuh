@@ -160,15 +160,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                          // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D fp32, A/B bf16, both K-major, dense
-constexpr uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// instruction descriptor: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, dense
+constexpr uint32_t make_idesc(int m, int n, bool f16 = false) {
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ---- epilogue functors: value for output element (row, col) given the accumulator -------------
 struct EpiDistance {            // distance.py:59-73 / :76-89
     static constexpr const char *kName = "gemm_distance";
+    static constexpr bool kF16 = false;
     static constexpr bool kDirect = false;      // rows of arbitrary alignment: coalesce through smem
     static constexpr int kChunkKb = 4;          // drain the accumulator every 256 k (fp32-accurate sums)
     const float *qn, *gn;       // squared norms (euclidean); unused for cosine
@@ -187,8 +188,12 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
     }
 };
 
-struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) + (1-gamma) * x
+// kScaled: single-plane fp16 operands (AGRL_SPLIT_FP16X1).  Both operands were multiplied by powers of two to sit
+// in the middle of the fp16 range (per tracklet for Y, per layer for W); the epilogue undoes that exactly.
+template <bool kScaled>
+struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) + (1-gamma) * x
     static constexpr const char *kName = "gemm_graph_layer";
+    static constexpr bool kF16 = kScaled;
     static constexpr bool kDirect = true;       // C % 4 == 0 and 16-byte aligned rows: vector accesses
     static constexpr int kChunkKb = 0;          // one accumulation over all of K
     // pull this thread's slice of the residual row into L2 before the accumulator is ready
@@ -204,6 +209,7 @@ struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
         const float4 *sc = reinterpret_cast<const float4 *>(scale + col0);
         const float4 *sh = reinterpret_cast<const float4 *>(shift + col0);
         if (col0 + 32 > n_cols) return;                       // N is a multiple of 32 for this epilogue
+        const float unscale = kScaled ? __ldg(row_unscale + row / nodes) * __ldg(w_unscale) : 1.0f;
         float4 xin[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) xin[q] = __ldg(xr + q);
@@ -213,10 +219,10 @@ struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
             const float4 s4 = __ldg(sc + q), t4 = __ldg(sh + q);
             float4 o;
             float h;
-            h = fmaf(__uint_as_float(acc[4 * q + 0]), s4.x, t4.x); h = h >= 0.f ? h : h * slope; o.x = fmaf(gamma, h, keep * xin[q].x);
-            h = fmaf(__uint_as_float(acc[4 * q + 1]), s4.y, t4.y); h = h >= 0.f ? h : h * slope; o.y = fmaf(gamma, h, keep * xin[q].y);
-            h = fmaf(__uint_as_float(acc[4 * q + 2]), s4.z, t4.z); h = h >= 0.f ? h : h * slope; o.z = fmaf(gamma, h, keep * xin[q].z);
-            h = fmaf(__uint_as_float(acc[4 * q + 3]), s4.w, t4.w); h = h >= 0.f ? h : h * slope; o.w = fmaf(gamma, h, keep * xin[q].w);
+            h = fmaf(kScaled ? __uint_as_float(acc[4 * q + 0]) * unscale : __uint_as_float(acc[4 * q + 0]), s4.x, t4.x); h = h >= 0.f ? h : h * slope; o.x = fmaf(gamma, h, keep * xin[q].x);
+            h = fmaf(kScaled ? __uint_as_float(acc[4 * q + 1]) * unscale : __uint_as_float(acc[4 * q + 1]), s4.y, t4.y); h = h >= 0.f ? h : h * slope; o.y = fmaf(gamma, h, keep * xin[q].y);
+            h = fmaf(kScaled ? __uint_as_float(acc[4 * q + 2]) * unscale : __uint_as_float(acc[4 * q + 2]), s4.z, t4.z); h = h >= 0.f ? h : h * slope; o.z = fmaf(gamma, h, keep * xin[q].z);
+            h = fmaf(kScaled ? __uint_as_float(acc[4 * q + 3]) * unscale : __uint_as_float(acc[4 * q + 3]), s4.w, t4.w); h = h >= 0.f ? h : h * slope; o.w = fmaf(gamma, h, keep * xin[q].w);
             orow[q] = o;
         }
     }
@@ -225,17 +231,23 @@ struct EpiGraphLayer {          // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
     float *out;
     int64_t ldx, ldo;
     float gamma, slope;
+    const float *row_unscale;   // kScaled: 2^-k of each tracklet's Y rows (one float per tracklet)
+    const float *w_unscale;     // kScaled: 2^-k of this layer's W (one float)
+    int nodes;                  // rows per tracklet
     struct Col { float scale, shift; };
     __device__ __forceinline__ Col col_state(int col) const {
         Col c; c.scale = __ldg(scale + col); c.shift = __ldg(shift + col); return c;
     }
     __device__ __forceinline__ void store(int row, int col, float acc, const Col &c) const {
+        if (kScaled) acc *= __ldg(row_unscale + row / nodes) * __ldg(w_unscale);
         float h = fmaf(acc, c.scale, c.shift);
         h = h >= 0.f ? h : h * slope;
         const float xin = __ldg(x + static_cast<size_t>(row) * ldx + col);
         out[static_cast<size_t>(row) * ldo + col] = fmaf(gamma, h, (1.0f - gamma) * xin);
     }
 };
+using EpiGraphLayer = EpiGraphLayerT<false>;
+using EpiGraphLayerF16 = EpiGraphLayerT<true>;
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <int P, int BN, bool kSplit, class Epi>
@@ -312,7 +324,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc(BM, BN);
+        constexpr uint32_t idesc = make_idesc(BM, BN, Epi::kF16);
         int stage = 0; uint32_t phase = 0;
         int cit = 0;                                               // accumulator-drain counter (chunks)
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -510,6 +522,8 @@ struct SplitArgs {
     float *sumsq;                      // optional: per-row sum of squares (of the un-normalised row)
     int64_t rows; int dim; int k_pad; int P;
     int normalize;                     // 1: split x / max(||x||, 1e-12) instead of x (cosine_distance)
+    int fp16 = 0;                      // 1: ONE fp16 plane of x * (*prescale) instead of bf16 planes
+    const float *prescale = nullptr;   // device, a power of two (fp16 mode)
 };
 int launch_split_planes(const SplitArgs &a, cudaStream_t st);
 

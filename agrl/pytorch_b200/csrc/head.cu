@@ -16,6 +16,8 @@
 //   attn_kernel        temporal attention (vmgn.py:276-277), part mean, BN neck -> out[:, C:] (:317-321).
 #include "gemm_sm100.cuh"
 
+#include <cuda_fp16.h>
+
 namespace agrl {
 
 constexpr int kParts = 7;              // calc_splits(4) = [4,2,1] (utils/reidtools.py:13-15)
@@ -42,9 +44,32 @@ __global__ void fold_bn_kernel(FoldArgs a) {
     }
 }
 
+// fp16 mode: W is multiplied by the power of two that puts max|W| just below 2^14 before it is rounded to fp16
+// (fp16 keeps 11 significant bits only between 2^-14 and 2^15), and the GEMM epilogue multiplies by its inverse.
+__global__ void absmax_kernel(const float *__restrict__ w, size_t n, float *slot) {
+    float m = 0.f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = fabsf(w[i]);
+        if (v < 3.0e38f) m = fmaxf(m, v);              // ignore inf / NaN
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int *>(slot + 2), __float_as_uint(m));
+}
+__device__ __forceinline__ void pow2_scales(float bound, float *up, float *down) {
+    int e = 0;
+    if (bound > 0.f) frexpf(bound, &e);                // bound = m * 2^e, m in [0.5, 1)
+    else e = 14;
+    e = max(-100, min(100, e));
+    *up = ldexpf(1.0f, 14 - e);
+    *down = ldexpf(1.0f, e - 14);
+}
+__global__ void w_scale_kernel(float *slot) { pow2_scales(slot[2], slot, slot + 1); }
+
 struct Prepared {                       // layout of the caller-owned "prepared" buffer
     __nv_bfloat16 *w_planes[AGRL_HEAD_MAX_LAYERS];     // [P][C][C]
     float *scale[AGRL_HEAD_MAX_LAYERS + 2], *shift[AGRL_HEAD_MAX_LAYERS + 2];   // layers.., global, att
+    float *w_scale;                                    // fp16 mode: per layer {2^k, 2^-k, max|W| bits}
     size_t bytes;
 };
 
@@ -54,6 +79,7 @@ static Prepared carve_prepared(const agrl_head_params *p, void *buf) {
     const size_t C = static_cast<size_t>(p->channels);
     for (int l = 0; l < p->num_layers; ++l) r.w_planes[l] = c.take<__nv_bfloat16>(p->split * C * C);
     for (int l = 0; l < p->num_layers + 2; ++l) { r.scale[l] = c.take<float>(C); r.shift[l] = c.take<float>(C); }
+    r.w_scale = c.take<float>(4 * AGRL_HEAD_MAX_LAYERS);
     r.bytes = c.total();
     return r;
 }
@@ -334,6 +360,8 @@ struct GraphArgs {
     int64_t plane_stride;              // B*V*C
     int V, C, P;
     int use_pose, learn_graph;
+    int fp16;                          // P == 1: one fp16 plane of y * 2^k, k per tracklet
+    float *y_unscale;                  // (B): 2^-k
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -486,6 +514,37 @@ graph_kernel(GraphArgs a) {
     }
     // graph rows >= V are never stored; graph columns >= V are zero
     __syncthreads();
+    // fp16 plane: |y_ij| <= max_v ||x_v|| (rows of G have L1 norm <= 1), so one power of two per tracklet
+    // puts every y below 2^14; the GEMM epilogue undoes it (y_unscale)
+    float y_scale = 1.0f;
+    if (a.fp16) {
+        __shared__ float s_scale[2];
+        if (!a.learn_graph) {                            // no Gram diagonal: one norm pass over the rows (L2-resident)
+            for (int r = warp; r < V; r += kHeadThreads / 32) {
+                const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
+                float t = 0.f;
+                for (int i = lane; i < C / 4; i += 32) {
+                    const float4 v = __ldg(row + i);
+                    t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+                }
+                t = warp_sum(t);
+                if (lane == 0) sq[r] = t;
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            float m = fmaxf(lane < V ? sq[lane] : 0.f, lane + 32 < V ? sq[lane + 32] : 0.f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) {
+                m = (m < 3.0e38f) ? sqrtf(m) : 0.f;       // inf / NaN rows: leave unscaled
+                pow2_scales(m, &s_scale[0], &s_scale[1]);
+                a.y_unscale[b] = s_scale[1];
+            }
+        }
+        __syncthreads();
+        y_scale = s_scale[0];
+    }
 
     // ---- Y = G . X : thread (rg, cq) owns rows {rg*kRpg ..+kRpg-1} x 4 channels of the chunk ----
     const int rg = tid >> 5, cq = tid & 31;              // a warp shares rg -> graph weights broadcast
@@ -518,6 +577,14 @@ graph_kernel(GraphArgs a) {
             if (row < V) {
                 float v0 = acc[r][0], v1 = acc[r][1], v2 = acc[r][2], v3 = acc[r][3];
                 __nv_bfloat16 *dst = a.y_planes + (row0 + row) * C + c0 + cq * 4;
+                if (a.fp16) {
+                    const __half2 lo = __floats2half2_rn(v0 * y_scale, v1 * y_scale), hi = __floats2half2_rn(v2 * y_scale, v3 * y_scale);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                    *reinterpret_cast<uint2 *>(dst) = pk;
+                    continue;
+                }
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     if (p < a.P) {
@@ -604,6 +671,7 @@ attn_kernel(AttnArgs a) {
 struct HeadWorkspace {
     float *x[2];
     __nv_bfloat16 *y_planes;
+    float *y_unscale;                  // (batch) fp16 mode
     size_t bytes;
 };
 
@@ -614,6 +682,7 @@ static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t bat
     w.x[0] = c.take<float>(n);
     w.x[1] = c.take<float>(n);
     w.y_planes = c.take<__nv_bfloat16>(static_cast<size_t>(p->split) * n);
+    w.y_unscale = c.take<float>(static_cast<size_t>(batch));
     w.bytes = c.total();
     return w;
 }
@@ -621,7 +690,7 @@ static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t bat
 static int check_params(const agrl_head_params *p) {
     if (!p) return AGRL_E_INVALID;
     if (p->num_layers < 0 || p->num_layers > AGRL_HEAD_MAX_LAYERS) return AGRL_E_INVALID;
-    if (p->split != AGRL_SPLIT_BF16X2 && p->split != AGRL_SPLIT_BF16X3) return AGRL_E_INVALID;
+    if (p->split != AGRL_SPLIT_BF16X2 && p->split != AGRL_SPLIT_BF16X3 && p->split != AGRL_SPLIT_FP16X1) return AGRL_E_INVALID;
     if (p->channels < kChunk || p->channels % kChunk != 0) return AGRL_E_UNSUPPORTED;
     if (!p->use_pose && !p->learn_graph) return AGRL_E_INVALID;            // vmgn.py:92 assert
     return AGRL_OK;
@@ -678,6 +747,15 @@ extern "C" int agrl_head_prepare_dev(const agrl_head_params *p, void *prepared, 
         if (!p->linear_weight[l] || !p->bn_weight[l] || !p->bn_bias[l] || !p->bn_mean[l] || !p->bn_var[l]) return AGRL_E_INVALID;
         fa.w[l] = p->bn_weight[l]; fa.b[l] = p->bn_bias[l]; fa.mean[l] = p->bn_mean[l]; fa.var[l] = p->bn_var[l];
         gemm::SplitArgs sa{p->linear_weight[l], C, pr.w_planes[l], nullptr, C, C, C, p->split, 0};
+        if (p->split == AGRL_SPLIT_FP16X1) {
+            float *slot = pr.w_scale + 4 * l;
+            AGRL_CUDA_TRY(cudaMemsetAsync(slot, 0, 4 * sizeof(float), st));
+            absmax_kernel<<<4 * kNumSMs, 256, 0, st>>>(p->linear_weight[l], static_cast<size_t>(C) * C, slot);
+            AGRL_LAUNCH_CHECK(st, "absmax");
+            w_scale_kernel<<<1, 1, 0, st>>>(slot);
+            AGRL_LAUNCH_CHECK(st, "w_scale");
+            sa.fp16 = 1; sa.prescale = slot;
+        }
         if ((rc = gemm::launch_split_planes(sa, st))) return rc;
     }
     const float *const *extra[2] = {p->global_bn, p->att_bn};
@@ -819,17 +897,22 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
     if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, y, rows, C, p->split, gemm::BM, all_rows))) return rc;
     int cur = 0;
     for (int l = 0; l < L; ++l) {
-        GraphArgs ga{x[cur], adj, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph};
+        const int fp16 = p->split == AGRL_SPLIT_FP16X1;
+        GraphArgs ga{x[cur], adj, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph, fp16, hwk.y_unscale + b0};
         if (gate && (rc = gate->partner(l, L, st))) return rc;
         AGRL_LAUNCH_BEGIN(st);
         if (V == 56) rc = launch_graph<14>(ga, n, st); else rc = launch_graph<16>(ga, n, st);
         if (rc) return rc;
         if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, p->split == AGRL_SPLIT_BF16X3 ? 128 : 256, C))) return rc;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
-        gemm::EpiGraphLayer epi{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope};
+        gemm::EpiGraphLayer epi{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope, nullptr, nullptr, V};
         if (gate && (rc = gate->join(l, st))) return rc;
         AGRL_LAUNCH_BEGIN(st);
-        if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        if (fp16) {
+            gemm::EpiGraphLayerF16 epi16{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
+                                         hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
+            rc = gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st);
+        } else if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
         else rc = gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
         if (rc) return rc;
         if (dst == nodes_out) x[cur ^ 1] = nodes_out;

@@ -7,6 +7,7 @@
 // (cosine_distance, distance.py:86-87: F.normalize then mm).
 #include "gemm_sm100.cuh"
 
+#include <cuda_fp16.h>
 #include <mutex>
 
 namespace agrl {
@@ -57,6 +58,11 @@ split_planes_kernel(SplitArgs a) {
         float x0 = (i < a.dim) ? src[i] : 0.f;
         float x1 = (i + 1 < a.dim) ? src[i + 1] : 0.f;
         if (a.normalize) { x0 = __fdiv_rn(x0, inv); x1 = __fdiv_rn(x1, inv); }
+        if (a.fp16) {
+            const float ps = __ldg(a.prescale);
+            *reinterpret_cast<__half2 *>(dst + i) = __floats2half2_rn(x0 * ps, x1 * ps);
+            continue;
+        }
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             if (p < a.P) {

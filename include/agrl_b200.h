@@ -69,6 +69,12 @@ extern "C" {
 #define AGRL_SPLIT_BF16X2     2   /* 2 planes, 3 products: ~2^-17 relative per product (default for
                                      the graph layers, whose output enters with gamma = 0.1)       */
 
+#define AGRL_SPLIT_FP16X1      1   /* graph layers only, opt-in: ONE fp16 plane per operand (11 significant
+                                     bits, the precision class of TF32), operands pre-scaled by exact powers
+                                     of two (per tracklet / per layer) into the fp16 range; one product
+                                     instead of three.  Measured head error 1e-5 norm-relative, 3e-5
+                                     max-scaled (bar 1e-4); not offered for the distance matrix            */
+
 AGRL_API int         agrl_abi_version(void);
 AGRL_API const char *agrl_status_string(int code);
 AGRL_API const char *agrl_last_cuda_error(void);           /* thread-local text of the last CUDA failure   */
@@ -252,7 +258,7 @@ typedef struct agrl_head_params {
     float   gamma;                /* 0.1 (vmgn.py:74,172)                                          */
     float   leaky_slope;          /* 0.1 (vmgn.py:95)                                              */
     float   bn_eps;               /* 1e-5                                                          */
-    int32_t split;                /* AGRL_SPLIT_BF16X2 (default) or AGRL_SPLIT_BF16X3              */
+    int32_t split;                /* AGRL_SPLIT_BF16X2 (default), AGRL_SPLIT_BF16X3 or AGRL_SPLIT_FP16X1 */
     /* device pointers, fp32; BN vectors have C entries, linear weights are (C, C) row-major [out,in] */
     const float *linear_weight[AGRL_HEAD_MAX_LAYERS];      /* graph_layers.i.linear.weight          */
     const float *bn_weight[AGRL_HEAD_MAX_LAYERS];          /* graph_layers.i.bn.{weight,bias,...}    */

@@ -1,5 +1,5 @@
 """Head-pipeline variants on one resident input pool (one process, options switched at run time).
-usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint call)
+usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split call)
 `call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
 import json
 import os
@@ -35,6 +35,7 @@ def main():
                 cfg[k] = int(v)
         for k, name in KEYS.items():
             _lib.set_option(name, cfg[k])
+        model.head_split = cfg.get('split', 2)
         call = min(cfg['call'], pool_n)
         chunks = [(o, min(call, J - o)) for o in range(0, J, call)]
 
