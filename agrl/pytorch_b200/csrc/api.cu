@@ -69,11 +69,15 @@ static const OptionDef kOptionDefs[kOptCount] = {
     {"pool_tma", "AGRL_POOL_TMA", 1, 0, 1},
     {"pool_stages", "AGRL_POOL_STAGES", 4, 2, 12},            // 16 KiB ring stages per pooling CTA
     {"pool_ctas_per_sm", "AGRL_POOL_CTAS", 1, 1, 4},
-    {"graph_variant", "AGRL_GRAPH_VARIANT", 0, 0, 7},
+    {"graph_variant", "AGRL_GRAPH_VARIANT", 6, 0, 7},
     {"pool_l2_hint", "AGRL_POOL_HINT", 1, 0, 1},              // evict-first hint on the pooling bulk copies
     // sub-batched pipeline: 0 = poolings free-run on the side stream; 1 = pooling of sub-batch i+1 is cut into
     // pieces that run only under the graph / attention kernels of sub-batch i (the GEMMs wait for their piece)
     {"overlap_mode", "AGRL_OVERLAP_MODE", 1, 0, 1},
+    // 1: the tcgen05 GEMMs run as CTA pairs (cta_group::2, 256-row tiles, each CTA loads half of the B tile).
+    // Parity-tested; measured SLOWER than one CTA per tile on B200 (24.6 vs 23.3 ms, fp16 plane 19.8 vs 11.9 ms per
+    // pass; tensor pipe 68 % vs 79 % active, a third less L2->SM traffic) -- default off, see DESIGN.md
+    {"gemm_pair", "AGRL_GEMM_PAIR", 0, 0, 1},
 };
 static std::atomic<int64_t> g_options[kOptCount];
 static std::atomic<int> g_options_init{0};

@@ -45,7 +45,10 @@ constexpr int kEpiBytes = 4 * 32 * kEpiPad * 4;       // transpose staging of th
 // kChunkKb > 0: the accumulator is drained every kChunkKb k-blocks and summed in registers with
 //        round-to-nearest fp32 adds (the tensor core truncates on accumulate; short chains keep that
 //        bias below the fp32 rounding of the result).  Needs 8 epilogue warps (64 sums per thread).
-template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0> struct Config {
+// kPair  CTA pair (cluster of 2, tcgen05 cta_group::2): the pair owns a 256 x BN tile; each CTA loads its 128 rows
+//        of A and HALF of the B tile, the MMA reads both halves -- a third less L2 -> SM traffic per flop, which is
+//        what bounds the single-CTA kernel (11.7 TB/s of TMA fills = the measured L2 throughput cap).
+template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0, bool kPair = false> struct Config {
     // epilogue flavour: kDirect = registers -> 16-byte global accesses, 8 warps (two per TMEM lane
     // quarter, half the columns each), no smem; otherwise 4 warps and a padded smem transpose so
     // that stores are coalesced along rows of arbitrary alignment.
@@ -54,19 +57,21 @@ template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0> st
     static constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
     static_assert(BN == 128 || BN == 256, "tile width");
     static_assert(!kSplit || BN == 128, "two accumulators of 256 columns do not fit twice in TMEM");
-    static constexpr int kTileBytesB = BN * BK * 2;
+    static constexpr int kLoadN = kPair ? BN / 2 : BN;                  // rows of the B tile this CTA loads
+    static constexpr int kTileBytesB = kLoadN * BK * 2;
     static constexpr int kStageBytes = P * (kTileBytesA + kTileBytesB);
+    static constexpr int kTileM = kPair ? 2 * BM : BM;                  // rows per scheduled tile
     static constexpr int kStages = (200 * 1024) / kStageBytes;          // 96 KiB stages -> 2, 64 KiB -> 3
     static constexpr int kAccCols = kSplit ? 2 * BN : BN;               // columns per accumulator stage
     static constexpr int kNumPairs = (P == 3) ? 6 : (P == 2 ? 3 : 1);
     static_assert(kStages >= 2 && kAccStages * kAccCols <= kTmemCols, "resources");
     static constexpr int kEpiSmem = kDirect ? 0 : (kEpiWarps / 4) * kEpiBytes;
-    // Register cap: leaves room in the register file for a co-resident memory-bound CTA of another
-    // stream (the head overlaps its pooling with this kernel; 384 x 104 = 40 K of the 64 K registers).
-    static constexpr int kMaxRegs = kDirect ? 104 : 168;
+    // Register cap (384 threads x 144 / 168 registers fit the 64 K file; one CTA per SM).
+    static constexpr int kMaxRegs = 168;
     static constexpr int kChunk = kChunkKb;
     // dynamic smem: stages | epilogue staging | barriers ; +1024 for manual alignment
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiSmem + 256 + 1024;
+    static_assert(8 * (3 * kStages + 2 * kAccStages + 1) <= 256, "barrier area");
 };
 
 // plane pairs, least significant products first
@@ -137,6 +142,51 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- CTA-pair (cta_group::2) flavours ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {      // same offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit: arrive on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -202,17 +252,19 @@ struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
         const float *p = x + static_cast<size_t>(row) * ldx + col0;
         for (int c = 0; c < ncols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c));
     }
-    // 32 consecutive columns of one row: all residual loads first, then the math, then the stores
-    __device__ __forceinline__ void store_row32(int row, int col0, int n_cols, const uint32_t (&acc)[32]) const {
+    // residual of 32 consecutive columns of one row (independent of the accumulator: issued a round ahead)
+    __device__ __forceinline__ void load_row32(int row, int col0, float4 (&xin)[8]) const {
         const float4 *xr = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * ldx + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xin[q] = __ldg(xr + q);
+    }
+    // 32 consecutive columns of one row: the math, then the stores
+    __device__ __forceinline__ void store_row32(int row, int col0, int n_cols, const uint32_t (&acc)[32], const float4 (&xin)[8]) const {
         float4 *orow = reinterpret_cast<float4 *>(out + static_cast<size_t>(row) * ldo + col0);
         const float4 *sc = reinterpret_cast<const float4 *>(scale + col0);
         const float4 *sh = reinterpret_cast<const float4 *>(shift + col0);
         if (col0 + 32 > n_cols) return;                       // N is a multiple of 32 for this epilogue
         const float unscale = kScaled ? __ldg(row_unscale + row / nodes) * __ldg(w_unscale) : 1.0f;
-        float4 xin[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) xin[q] = __ldg(xr + q);
         const float keep = 1.0f - gamma;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -250,11 +302,10 @@ using EpiGraphLayer = EpiGraphLayerT<false>;
 using EpiGraphLayerF16 = EpiGraphLayerT<true>;
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int P, int BN, bool kSplit, class Epi>
-__global__ void __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
-split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  int M, int N, int k_pad, Epi epi) {
-    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>;
+template <int P, int BN, bool kSplit, class Epi, bool kPair>
+__device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const CUtensorMap &map_b,
+                                                int M, int N, int k_pad, const Epi &epi) {
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, kPair>;
     constexpr int kAccCols = Cfg::kAccCols;
     extern __shared__ unsigned char smem_dyn[];
     // 128B-swizzled tiles need 1024-byte alignment
@@ -268,9 +319,14 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t bar_tfull = bar_empty + 8 * Cfg::kStages;
     const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::kStages + 2 * kAccStages);
+    // pair: "the peer's stage has landed" -- lives in the leader, arrived on by a relay warp of the peer CTA
+    const uint32_t bar_pfull = bar_tempty + 8 * kAccStages + 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;             // 0 = the pair's leader (issues the MMAs)
+    const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int tiles_m = (M + Cfg::kTileM - 1) / Cfg::kTileM, tiles_n = (N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = k_pad / BK;
     const int chunk_kb = Cfg::kChunk > 0 ? Cfg::kChunk : num_kb;       // k-blocks per accumulator drain
@@ -278,8 +334,9 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // (L2-resident) while the larger operand streams through exactly once.
     const bool m_fast = tiles_m <= tiles_n;
     auto tile_origin = [&](int tile, int &m0, int &n0) {
-        if (m_fast) { m0 = (tile % tiles_m) * BM; n0 = (tile / tiles_m) * BN; }
-        else        { n0 = (tile % tiles_n) * BN; m0 = (tile / tiles_n) * BM; }
+        if (m_fast) { m0 = (tile % tiles_m) * Cfg::kTileM; n0 = (tile / tiles_m) * BN; }
+        else        { n0 = (tile % tiles_n) * BN; m0 = (tile / tiles_n) * Cfg::kTileM; }
+        m0 += static_cast<int>(rank) * BM;                            // this CTA's 128 rows of the tile
     };
 
     if (warp == 0 && lane == 0) {
@@ -287,47 +344,73 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         prefetch_tensormap(&map_b);
     }
     if (warp == 1 && lane == 0) {
+        // pair: the leader's full barrier takes one arrive per CTA (producers), its tmem_empty barrier the
+        // epilogue warps of both CTAs; empty / tmem_full are signalled in both CTAs by the leader's commits
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps); }
+        if (kPair) for (int s = 0; s < Cfg::kStages; ++s) mbar_init(bar_pfull + 8 * s, 1);
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps * (kPair ? 2 : 1)); }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-        tmem_relinquish();
+        if (kPair) { tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols); tmem_relinquish_pair(); }
+        else { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ================= TMA producer =================
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int m0, n0;
             tile_origin(tile, m0, n0);
+            const int nb = n0 + static_cast<int>(rank) * Cfg::kLoadN;          // this CTA's half of the B tile
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (lane == 0) {
-                    const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                     const uint32_t sb = sa + P * kTileBytesA;
-                    mbar_arrive_expect_tx(full, Cfg::kStageBytes);
+                    if (kPair) {
+                        // every CTA's loads complete on its OWN full barrier (local signalling); the peer's relay warp
+                        // forwards "landed" to the leader
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_arrive_expect_tx(full, Cfg::kStageBytes);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kTileBytesA, &map_a, full, kb * BK, m0, p);
+                        for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kTileBytesA, &map_a, full, kb * BK, m0, p);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::kTileBytesB, &map_b, full, kb * BK, n0, p);
+                        for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::kTileBytesB, &map_b, full, kb * BK, nb, p);
+                    } else {
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_arrive_expect_tx(full, Cfg::kStageBytes);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kTileBytesA, &map_a, full, kb * BK, m0, p);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::kTileBytesB, &map_b, full, kb * BK, n0, p);
+                    }
                 }
                 __syncwarp();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc(BM, BN, Epi::kF16);
+    } else if (kPair && warp == 3 && rank == 1) {
+        // ================= relay (peer CTA): stage landed here -> tell the leader =================
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(bar_pfull + 8 * stage, 0));
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ================= MMA issuer (the pair's leader only) =================
+        constexpr uint32_t idesc = make_idesc(Cfg::kTileM, BN, Epi::kF16);
         int stage = 0; uint32_t phase = 0;
         int cit = 0;                                               // accumulator-drain counter (chunks)
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++cit) {
                 const int acc = cit & 1;
                 const uint32_t acc_phase = (cit >> 1) & 1;
@@ -342,6 +425,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t d_corr = kSplit ? d_main + BN : d_main;
                 for (int kb = kb0; kb < kb_end; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
+                    if (kPair) mbar_wait(bar_pfull + 8 * stage, phase);   // ... in the peer CTA too
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -356,14 +440,21 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; ++k) {
                                 // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
-                                if (kSplit && i == Cfg::kNumPairs - 1)
-                                    tc_mma_bf16(d_main, da + 2 * k, db + 2 * k, idesc, (first | k) != 0 ? 1u : 0u);
-                                else
-                                    tc_mma_bf16(d_corr, da + 2 * k, db + 2 * k, idesc, (first | i | k) != 0 ? 1u : 0u);
+                                const bool main_acc = kSplit && i == Cfg::kNumPairs - 1;
+                                const uint32_t d = main_acc ? d_main : d_corr;
+                                const uint32_t accum = main_acc ? ((first | k) != 0 ? 1u : 0u) : ((first | i | k) != 0 ? 1u : 0u);
+                                if (kPair) tc_mma_bf16_pair(d, da + 2 * k, db + 2 * k, idesc, accum);
+                                else tc_mma_bf16(d, da + 2 * k, db + 2 * k, idesc, accum);
                             }
                         }
-                        tc_commit(bar_empty + 8 * stage);           // frees the smem stage when the MMAs retire
-                        if (kb == kb_end - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator (chunk) complete
+                        // frees the smem stage when the MMAs retire; publishes the accumulator (chunk) when complete
+                        if (kPair) {
+                            tc_commit_pair(bar_empty + 8 * stage);
+                            if (kb == kb_end - 1) tc_commit_pair(bar_tfull + 8 * acc);
+                        } else {
+                            tc_commit(bar_empty + 8 * stage);
+                            if (kb == kb_end - 1) tc_commit(bar_tfull + 8 * acc);
+                        }
                     }
                     __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -374,8 +465,13 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ================= epilogue =================
         const int ew = warp - kCtrlWarps;
         const int quarter = ew & 3;                                // == warp % 4: the TMEM lane quarter
+        // "accumulator drained" goes to the barrier the MMA issuer waits on: the leader's
+        auto release_acc = [&](int acc) {
+            if (kPair) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));
+            else mbar_arrive(bar_tempty + 8 * acc);
+        };
         int cit = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int m0, n0;
             tile_origin(tile, m0, n0);
             const int row_base = m0 + quarter * 32;
@@ -388,18 +484,30 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t tq = tlane + acc * kAccCols;
                 const int col_half = (ew >> 2) * (BN / 2);
                 const int row = row_base + lane;
-                epi.prefetch(row, n0 + col_half, BN / 2, row < M);     // residual tile -> L2 while the MMAs run
+                const bool live = row < M && n0 + col_half + BN / 2 <= N;
+                epi.prefetch(row, n0 + col_half, BN / 2, live);        // residual tile -> L2 while the MMAs run
+                // the residual of round c + 1 is in flight while round c is computed and stored; round 0's loads
+                // are issued before the wait for the accumulator
+                float4 xa[8], xb[8];
+                if (live) epi.load_row32(row, n0 + col_half, xa);
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < BN / 2; c += 32) {
+#pragma unroll
+                for (int c = 0; c < BN / 2; c += 64) {
                     uint32_t r[32];
                     tmem_ld_32x32(tq + col_half + c, r);
+                    if (live && c + 32 < BN / 2) epi.load_row32(row, n0 + col_half + c + 32, xb);
                     tmem_ld_wait();
-                    if (row < M) epi.store_row32(row, n0 + col_half + c, N, r);
+                    if (live) epi.store_row32(row, n0 + col_half + c, N, r, xa);
+                    if (c + 32 < BN / 2) {
+                        tmem_ld_32x32(tq + col_half + c + 32, r);
+                        if (live && c + 64 < BN / 2) epi.load_row32(row, n0 + col_half + c + 64, xa);
+                        tmem_ld_wait();
+                        if (live) epi.store_row32(row, n0 + col_half + c + 32, N, r, xb);
+                    }
                 }
                 tc_fence_before();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (lane == 0) release_acc(acc);
                 ++cit;
             } else if constexpr (Cfg::kChunk > 0) {
                 // chunked accumulation: this warp owns 32 rows x 64 columns; every chunk's partial
@@ -428,7 +536,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         }
                     }
                     tc_fence_before();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (lane == 0) release_acc(acc);
                 }
                 float *buf = epi_buf + ew * 32 * kEpiPad;
 #pragma unroll
@@ -483,15 +591,32 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     __syncwarp();
                 }
                 tc_fence_before();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (lane == 0) release_acc(acc);
                 ++cit;
             }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <int P, int BN, bool kSplit, class Epi>
+__global__ void __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
+split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  int M, int N, int k_pad, Epi epi) {
+    split_gemm_body<P, BN, kSplit, Epi, false>(map_a, map_b, M, N, k_pad, epi);
+}
+
+template <int P, int BN, bool kSplit, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
+pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 int M, int N, int k_pad, Epi epi) {
+    split_gemm_body<P, BN, kSplit, Epi, true>(map_a, map_b, M, N, k_pad, epi);
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -500,6 +625,34 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // plane_rows = rows between consecutive planes (>= rows when the map covers a row slice of the planes).
 int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows,
                           int64_t plane_rows);
+
+// CTA-pair flavour; map_b must have been built with box_rows = BN / 2.
+template <int P, int BN, bool kSplit, class Epi>
+int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,
+                     const Epi &epi, cudaStream_t st) {
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, true>;
+    static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
+    auto kern = pair_gemm_kernel<P, BN, kSplit, Epi>;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    // persistent grid = the number of CTA pairs that can be resident at once (a GPC with an odd SM left over
+    // hosts no pair there), asked once per kernel
+    static const int max_pairs = [&] {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kNumSMs & ~1); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = kNumSMs / 2; }
+        return n < kNumSMs / 2 ? n : kNumSMs / 2;
+    }();
+    const int tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + BN - 1) / BN);
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
+    AGRL_LAUNCH_CHECK(st, Epi::kName);
+    return AGRL_OK;
+}
 
 template <int P, int BN, bool kSplit, class Epi>
 int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,

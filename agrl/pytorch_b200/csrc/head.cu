@@ -605,6 +605,218 @@ graph_kernel(GraphArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// graph kernel, second tiling (V <= 56, C % 256 == 0): same algorithm and shared-memory footprint as
+// graph_kernel, larger register tiles so that the shared-memory pipe is no longer the limit.
+//   Gram   lane = one of the 28 (i <= j) pairs of 8x8 tiles over rows {i + 7e} x {j + 7f}; the 8 warps split
+//          the k range of every 128-channel chunk.  16 conflict-free LDS.64 per 128 FMA (was 8 LDS.128 per 64).
+//   Y=G.X  warp = (14-row group, one of two 128-channel buffers), lane = 4 channels: 14x4 register tile,
+//          4 LDS.128 of X + 14 broadcast LDS.128 of G per 224 FMA (was 4 + 7 per 112); the next pair of
+//          chunks is fetched (cp.async) while the current one is rounded to operand planes and stored.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNB = 7;                     // 8x8 tiles: rows i + 7e, e = 0..7 -> 56 rows
+constexpr int kV2Rows = 8 * kNB;
+
+template <int kMaxRegs>
+__global__ void __maxnreg__(kMaxRegs)
+graph_kernel_v2(GraphArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    float *xs0 = smem_f;                               // [56][kXsLd] x 2
+    float *xs1 = xs0 + kV2Rows * kXsLd;
+    float *g = xs1 + kV2Rows * kXsLd;                  // [64][68]: Gram, then the mixed graph
+    float *sq = g + kMaxNodes * kGLd;                  // [64]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.V, C = a.C;
+    const int b = blockIdx.x;
+    const float *x = a.x + static_cast<size_t>(b) * V * C;
+
+    for (int i = tid; i < 2 * kV2Rows * kXsLd; i += kHeadThreads) xs0[i] = 0.f;     // pad rows stay zero
+    for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
+    __syncthreads();
+
+    if (a.learn_graph) {
+        int pi = 0, pj = lane;
+        const bool active = lane < kNB * (kNB + 1) / 2;
+        if (active) { while (pj >= kNB - pi) { pj -= kNB - pi; ++pi; } pj += pi; } else { pj = 0; }
+        float acc[8][8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[e][f] = 0.f;
+        for_each_chunk<2>(xs0, xs1, x, V, C, tid, [&](const float *xs, int) {
+            if (!active) return;
+            const float *pa = xs + pi * kXsLd + warp * (kChunk / 8);
+            const float *pb = xs + pj * kXsLd + warp * (kChunk / 8);
+#pragma unroll 1
+            for (int k = 0; k < kChunk / 8; k += 2) {
+                float2 av[8], bv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    av[e] = *reinterpret_cast<const float2 *>(pa + e * kNB * kXsLd + k);
+                    bv[e] = *reinterpret_cast<const float2 *>(pb + e * kNB * kXsLd + k);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) {
+                        acc[e][f] = fmaf(av[e].x, bv[f].x, acc[e][f]);
+                        acc[e][f] = fmaf(av[e].y, bv[f].y, acc[e][f]);
+                    }
+            }
+        });
+        // combine the 8 k groups in a fixed order (deterministic sums)
+#pragma unroll 1
+        for (int w = 0; w < kHeadThreads / 32; ++w) {
+            if (warp == w && active) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) {
+                        float *dst = g + (pi + kNB * e) * kGLd + pj + kNB * f;
+                        *dst = (w == 0) ? acc[e][f] : *dst + acc[e][f];
+                    }
+            }
+            __syncthreads();
+        }
+        if (warp == 0 && active && pi != pj) {                  // mirror into the lower triangle
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int f = 0; f < 8; ++f) g[(pj + kNB * f) * kGLd + pi + kNB * e] = g[(pi + kNB * e) * kGLd + pj + kNB * f];
+        }
+        __syncthreads();
+        if (tid < V) sq[tid] = g[tid * kGLd + tid];
+        __syncthreads();
+        for (int i = tid; i < V * V; i += kHeadThreads) {       // affinity (vmgn.py:116-120)
+            const int r = i / V, c = i % V;
+            float d2 = __fadd_rn(sq[c], sq[r]);
+            d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
+            const float d = sqrtf(fmaxf(d2, 1e-12f));
+            g[r * kGLd + c] = __fdiv_rn(2.0f, expf(d) + 1.0f);
+        }
+        __syncthreads();
+    }
+    // ---- L1 row normalisation + mixing: one warp per row ----
+    const float *adj = a.use_pose ? a.adj + static_cast<size_t>(b) * V * V : nullptr;
+    for (int r = warp; r < V; r += kHeadThreads / 32) {
+        float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
+        const int c1 = lane + 32;
+        if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
+        if (a.use_pose) { a0 = (lane < V) ? adj[r * V + lane] : 0.f; a1 = (c1 < V) ? adj[r * V + c1] : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
+        rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);
+        float m0, m1;
+        if (a.learn_graph && a.use_pose) {
+            m0 = __fdiv_rn(__fdiv_rn(a0, ra) + __fdiv_rn(s0, rs), 2.0f);
+            m1 = __fdiv_rn(__fdiv_rn(a1, ra) + __fdiv_rn(s1, rs), 2.0f);
+        } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
+        else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
+        __syncwarp();
+        g[r * kGLd + lane] = (lane < V) ? m0 : 0.f;
+        g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
+    }
+    __syncthreads();
+    float y_scale = 1.0f;
+    if (a.fp16) {                                                // see graph_kernel
+        __shared__ float s_scale[2];
+        if (!a.learn_graph) {
+            for (int r = warp; r < V; r += kHeadThreads / 32) {
+                const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
+                float t = 0.f;
+                for (int i = lane; i < C / 4; i += 32) {
+                    const float4 v = __ldg(row + i);
+                    t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+                }
+                t = warp_sum(t);
+                if (lane == 0) sq[r] = t;
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            float m = fmaxf(lane < V ? sq[lane] : 0.f, lane + 32 < V ? sq[lane + 32] : 0.f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) {
+                m = (m < 3.0e38f) ? sqrtf(m) : 0.f;
+                pow2_scales(m, &s_scale[0], &s_scale[1]);
+                a.y_unscale[b] = s_scale[1];
+            }
+        }
+        __syncthreads();
+        y_scale = s_scale[0];
+    }
+
+    // ---- Y = G . X ----
+    constexpr int kRows = 14;
+    const int rg = warp & 3, half = warp >> 2;
+    const float *xs = (half ? xs1 : xs0) + lane * 4;
+    const float *gr = g + rg * kRows * kGLd;
+    const size_t row0 = static_cast<size_t>(b) * V + rg * kRows;
+    const int n_pairs = C / (2 * kChunk);
+    stage_chunk_async(xs0, x, V, C, 0, tid);
+    stage_chunk_async(xs1, x, V, C, kChunk, tid);
+#pragma unroll 1
+    for (int it = 0; it < n_pairs; ++it) {
+        cp_async_wait<0>();
+        __syncthreads();
+        float acc[kRows][4];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+#pragma unroll 1
+        for (int j = 0; j < kV2Rows; j += 4) {
+            float4 xv[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) xv[jj] = *reinterpret_cast<const float4 *>(xs + (j + jj) * kXsLd);
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const float4 w = *reinterpret_cast<const float4 *>(gr + r * kGLd + j);
+                acc[r][0] = fmaf(w.x, xv[0].x, acc[r][0]); acc[r][1] = fmaf(w.x, xv[0].y, acc[r][1]);
+                acc[r][2] = fmaf(w.x, xv[0].z, acc[r][2]); acc[r][3] = fmaf(w.x, xv[0].w, acc[r][3]);
+                acc[r][0] = fmaf(w.y, xv[1].x, acc[r][0]); acc[r][1] = fmaf(w.y, xv[1].y, acc[r][1]);
+                acc[r][2] = fmaf(w.y, xv[1].z, acc[r][2]); acc[r][3] = fmaf(w.y, xv[1].w, acc[r][3]);
+                acc[r][0] = fmaf(w.z, xv[2].x, acc[r][0]); acc[r][1] = fmaf(w.z, xv[2].y, acc[r][1]);
+                acc[r][2] = fmaf(w.z, xv[2].z, acc[r][2]); acc[r][3] = fmaf(w.z, xv[2].w, acc[r][3]);
+                acc[r][0] = fmaf(w.w, xv[3].x, acc[r][0]); acc[r][1] = fmaf(w.w, xv[3].y, acc[r][1]);
+                acc[r][2] = fmaf(w.w, xv[3].z, acc[r][2]); acc[r][3] = fmaf(w.w, xv[3].w, acc[r][3]);
+            }
+        }
+        __syncthreads();                                         // every warp is done reading both buffers
+        if (it + 1 < n_pairs) {                                  // next pair flies while this one is stored
+            stage_chunk_async(xs0, x, V, C, (2 * it + 2) * kChunk, tid);
+            stage_chunk_async(xs1, x, V, C, (2 * it + 3) * kChunk, tid);
+        }
+        const int c0 = (2 * it + half) * kChunk + lane * 4;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            if (rg * kRows + r < V) {
+                float v0 = acc[r][0], v1 = acc[r][1], v2 = acc[r][2], v3 = acc[r][3];
+                __nv_bfloat16 *dst = a.y_planes + (row0 + r) * C + c0;
+                if (a.fp16) {
+                    const __half2 lo = __floats2half2_rn(v0 * y_scale, v1 * y_scale), hi = __floats2half2_rn(v2 * y_scale, v3 * y_scale);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                    *reinterpret_cast<uint2 *>(dst) = pk;
+                    continue;
+                }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    if (p < a.P) {
+                        const __nv_bfloat16 b0 = __float2bfloat16_rn(v0), b1 = __float2bfloat16_rn(v1);
+                        const __nv_bfloat16 b2 = __float2bfloat16_rn(v2), b3 = __float2bfloat16_rn(v3);
+                        __nv_bfloat162 lo = __halves2bfloat162(b0, b1), hi = __halves2bfloat162(b2, b3);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                        *reinterpret_cast<uint2 *>(dst + p * a.plane_stride) = pk;
+                        v0 = __fsub_rn(v0, __bfloat162float(b0)); v1 = __fsub_rn(v1, __bfloat162float(b1));
+                        v2 = __fsub_rn(v2, __bfloat162float(b2)); v3 = __fsub_rn(v3, __bfloat162float(b3));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // temporal attention + part mean + BN neck: one CTA per tracklet
 // ------------------------------------------------------------------------------------------------
 struct AttnArgs {
@@ -709,10 +921,24 @@ static int launch_graph_variant(const GraphArgs &ga, int64_t batch, cudaStream_t
 // option "graph_variant" (staging buffers, register cap -> CTAs per SM; 77 KiB smem double-buffered, 47 KiB single):
 //   0 = double, 128 (2/SM)   1 = single, 80 (3/SM)   2 = single, 128 (2/SM)   3 = double, 80
 //   4 = double, 112 and 5 = single, 112: two CTAs per SM NEXT TO a resident pooling CTA (48 regs x 160 threads)
+//   6 / 7 = graph_kernel_v2 (8x8 Gram tiles, 14x4 message-passing tiles) with 128 / 112 registers
 static int graph_variant() { return static_cast<int>(option(kOptGraphVariant)); }
+
+template <int kMaxRegs>
+static int launch_graph_v2(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
+    const size_t smem = (static_cast<size_t>(2 * kV2Rows) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
+    auto kern = graph_kernel_v2<kMaxRegs>;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
+    AGRL_LAUNCH_CHECK(st, "graph");
+    return AGRL_OK;
+}
 
 template <int NT>
 static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
+    const bool v2_ok = ga.V <= kV2Rows && ga.C % (2 * kChunk) == 0;
+    if (v2_ok && graph_variant() == 6) return launch_graph_v2<128>(ga, batch, st);
+    if (v2_ok && graph_variant() == 7) return launch_graph_v2<112>(ga, batch, st);
     switch (graph_variant()) {
         case 1: return launch_graph_variant<NT, 1, 80>(ga, batch, st);
         case 2: return launch_graph_variant<NT, 1, 128>(ga, batch, st);
@@ -903,7 +1129,9 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
         AGRL_LAUNCH_BEGIN(st);
         if (V == 56) rc = launch_graph<14>(ga, n, st); else rc = launch_graph<16>(ga, n, st);
         if (rc) return rc;
-        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, p->split == AGRL_SPLIT_BF16X3 ? 128 : 256, C))) return rc;
+        const bool pair = option(kOptGemmPair) != 0;
+        const int bn = p->split == AGRL_SPLIT_BF16X3 ? 128 : 256;
+        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, pair ? bn / 2 : bn, C))) return rc;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
         gemm::EpiGraphLayer epi{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope, nullptr, nullptr, V};
         if (gate && (rc = gate->join(l, st))) return rc;
@@ -911,9 +1139,15 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
         if (fp16) {
             gemm::EpiGraphLayerF16 epi16{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
                                          hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
-            rc = gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st);
-        } else if (p->split == AGRL_SPLIT_BF16X3) rc = gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
-        else rc = gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+            rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st)
+                      : gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st);
+        } else if (p->split == AGRL_SPLIT_BF16X3) {
+            rc = pair ? gemm::launch_pair_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st)
+                      : gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        } else {
+            rc = pair ? gemm::launch_pair_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st)
+                      : gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+        }
         if (rc) return rc;
         if (dst == nodes_out) x[cur ^ 1] = nodes_out;
         cur ^= 1;

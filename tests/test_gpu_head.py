@@ -156,7 +156,7 @@ def test_clip_pooling_strided_rows_and_cpu_input():
 def restore_options():
     from agrl.pytorch_b200 import _lib
     names = ('head_sub_batch', 'pool_tma', 'pool_stages', 'pool_ctas_per_sm', 'graph_variant', 'pool_l2_hint',
-             'overlap_mode')
+             'overlap_mode', 'gemm_pair')
     saved = {n: _lib.get_option(n) for n in names}
     yield _lib
     for n, v in saved.items():
@@ -197,7 +197,7 @@ def test_pipeline_modes_agree(restore_options):
     emax, _ = rel_err(outs[(1, 0, 2)], outs[(0, 0, 4)])
     assert emax < 2e-6
     lib.set_option('head_sub_batch', 4)
-    for variant in range(6):
+    for variant in range(8):
         lib.set_option('graph_variant', variant)
         with torch.no_grad():
             out = model.head(x1, x2, adj, S)

@@ -12,7 +12,7 @@ import bench
 from agrl.pytorch_b200 import _lib
 
 KEYS = {'sub': 'head_sub_batch', 'tma': 'pool_tma', 'stages': 'pool_stages', 'ctas': 'pool_ctas_per_sm', 'graph': 'graph_variant',
-        'mode': 'overlap_mode', 'hint': 'pool_l2_hint'}
+        'mode': 'overlap_mode', 'hint': 'pool_l2_hint', 'pair': 'gemm_pair'}
 
 
 def main():
