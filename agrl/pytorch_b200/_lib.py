@@ -72,6 +72,10 @@ _SIGNATURES = {
     'agrl_distance_prepare_operand_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_sz, c_vp]),
     'agrl_distance_prepared_dev': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
     'agrl_distance_host': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int]),
+    'agrl_pose_part_masks_dev': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, ctypes.c_double, c_vp, c_vp]),
+    'agrl_pose_adjacency_dev': (c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'agrl_head_forward_compact_dev': (c_int, [ctypes.POINTER(HeadParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
+                                              c_i64, c_i32, c_i32, c_i32, c_vp, c_sz, c_vp]),
     'agrl_clip_pool_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_vp]),
     'agrl_head_prepared_bytes': (c_sz, [ctypes.POINTER(HeadParams)]),
     'agrl_head_prepare_dev': (c_int, [ctypes.POINTER(HeadParams), c_vp, c_sz, c_vp]),

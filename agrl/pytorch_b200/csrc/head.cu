@@ -356,6 +356,7 @@ constexpr int kGLd = kMaxNodes + 4;         // graph row stride: float4-aligned 
 struct GraphArgs {
     const float *x;                    // (B, V, C) layer input
     const float *adj;                  // (B, V, V) or null
+    const uint64_t *masks;             // (B, 3) part-membership masks instead of adj (pose.cu), or null
     __nv_bfloat16 *y_planes;           // [P][B*V][C]
     int64_t plane_stride;              // B*V*C
     int V, C, P;
@@ -409,6 +410,24 @@ __device__ __forceinline__ void for_each_chunk(float *xs0, float *xs1, const flo
         }
     }
 }
+
+// element (r, c) of the pose graph: the dense matrix, or the three membership masks it is made of
+// (dataset_loader.py:373-387: every ordered pair of DISTINCT nodes that share a body-part class)
+struct PoseGraph {
+    const float *adj;
+    uint64_t m0, m1, m2;
+    int V;
+    __device__ __forceinline__ PoseGraph(const GraphArgs &a, int b) : adj(nullptr), m0(0), m1(0), m2(0), V(a.V) {
+        if (!a.use_pose) return;
+        if (a.adj) adj = a.adj + static_cast<size_t>(b) * a.V * a.V;
+        else { m0 = a.masks[3 * b]; m1 = a.masks[3 * b + 1]; m2 = a.masks[3 * b + 2]; }
+    }
+    __device__ __forceinline__ float at(int r, int c) const {
+        if (adj) return adj[r * V + c];
+        const uint64_t hit = ((m0 >> r) & (m0 >> c)) | ((m1 >> r) & (m1 >> c)) | ((m2 >> r) & (m2 >> c));
+        return (r != c && (hit & 1ull)) ? 1.0f : 0.0f;
+    }
+};
 
 template <int NT, int kBufs, int kMaxRegs>     // NT = ceil(V/4): 14 for the canonical V = 56
 __global__ void __maxnreg__(kMaxRegs)
@@ -495,12 +514,12 @@ graph_kernel(GraphArgs a) {
         __syncthreads();
     }
     // ---- L1 row normalisation + mixing: one warp per row ----
-    const float *adj = a.use_pose ? a.adj + static_cast<size_t>(b) * V * V : nullptr;
+    const PoseGraph pose(a, b);
     for (int r = warp; r < V; r += kHeadThreads / 32) {
         float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
         const int c1 = lane + 32;
         if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
-        if (a.use_pose) { a0 = (lane < V) ? adj[r * V + lane] : 0.f; a1 = (c1 < V) ? adj[r * V + c1] : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
+        if (a.use_pose) { a0 = (lane < V) ? pose.at(r, lane) : 0.f; a1 = (c1 < V) ? pose.at(r, c1) : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
         rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);              // F.normalize eps
         float m0, m1;
         if (a.learn_graph && a.use_pose) {
@@ -696,12 +715,12 @@ graph_kernel_v2(GraphArgs a) {
         __syncthreads();
     }
     // ---- L1 row normalisation + mixing: one warp per row ----
-    const float *adj = a.use_pose ? a.adj + static_cast<size_t>(b) * V * V : nullptr;
+    const PoseGraph pose(a, b);
     for (int r = warp; r < V; r += kHeadThreads / 32) {
         float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
         const int c1 = lane + 32;
         if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
-        if (a.use_pose) { a0 = (lane < V) ? adj[r * V + lane] : 0.f; a1 = (c1 < V) ? adj[r * V + c1] : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
+        if (a.use_pose) { a0 = (lane < V) ? pose.at(r, lane) : 0.f; a1 = (c1 < V) ? pose.at(r, c1) : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
         rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);
         float m0, m1;
         if (a.learn_graph && a.use_pose) {
@@ -1109,7 +1128,8 @@ struct Gate {
 };
 
 // graph layers + attention of `n` tracklets starting at tracklet `b0` (their nodes are in hwk.x[0])
-static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWorkspace hwk, const float *adj, float *out,
+static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWorkspace hwk, const float *adj,
+                         const uint64_t *masks, float *out,
                          int64_t ld_out, float *nodes_out, int64_t b0, int64_t n, int64_t batch, int S, cudaStream_t st,
                          const Gate *gate = nullptr) {
     const int C = p->channels, V = S * kParts, L = p->num_layers;
@@ -1118,13 +1138,14 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
     __nv_bfloat16 *y = hwk.y_planes + row0 * C;
     if (nodes_out) nodes_out += row0 * C;
     if (adj) adj += b0 * V * V;
+    if (masks) masks += b0 * 3;
     int rc;
     CUtensorMap map_y, map_w;
     if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, y, rows, C, p->split, gemm::BM, all_rows))) return rc;
     int cur = 0;
     for (int l = 0; l < L; ++l) {
         const int fp16 = p->split == AGRL_SPLIT_FP16X1;
-        GraphArgs ga{x[cur], adj, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph, fp16, hwk.y_unscale + b0};
+        GraphArgs ga{x[cur], adj, masks, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph, fp16, hwk.y_unscale + b0};
         if (gate && (rc = gate->partner(l, L, st))) return rc;
         AGRL_LAUNCH_BEGIN(st);
         if (V == 56) rc = launch_graph<14>(ga, n, st); else rc = launch_graph<16>(ga, n, st);
@@ -1171,15 +1192,15 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
 // graph layers + attention of sub-batch i wait for pooling i on the caller's stream -- so pooling i+1
 // streams from HBM underneath the compute of sub-batch i.  The caller's stream observes every kernel of
 // the call (it waits on each pooling event), so stream-ordered use of `out` stays valid.
-extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prepared,
-                                     const float *x4_1, const float *x4_2, const float *adj,
-                                     float *out, int64_t ld_out, float *nodes_out,
-                                     int64_t batch, int32_t S, int32_t h, int32_t w,
-                                     void *ws, size_t ws_bytes, void *stream) {
+static int head_forward_impl(const agrl_head_params *p, const void *prepared,
+                             const float *x4_1, const float *x4_2, const float *adj, const uint64_t *masks,
+                             float *out, int64_t ld_out, float *nodes_out,
+                             int64_t batch, int32_t S, int32_t h, int32_t w,
+                             void *ws, size_t ws_bytes, void *stream) {
     int rc = check_params(p);
     if (rc) return rc;
     if (!prepared || !x4_1 || !x4_2 || !out || batch < 0 || S < 1 || h < 1 || w < 1) return AGRL_E_INVALID;
-    if (p->use_pose && !adj) return AGRL_E_INVALID;
+    if (p->use_pose && !adj && !masks) return AGRL_E_INVALID;
     const int C = p->channels, V = S * kParts, hw = h * w;
     if (ld_out < 2 * C) return AGRL_E_INVALID;
     if (V > kMaxNodes || h % 4 != 0) return AGRL_E_UNSUPPORTED;
@@ -1189,7 +1210,8 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     if (!ws || ws_bytes < hwk.bytes) return AGRL_E_WORKSPACE;
     Prepared pr = carve_prepared(p, const_cast<void *>(prepared));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!p->use_pose) adj = nullptr;
+    if (!p->use_pose) { adj = nullptr; masks = nullptr; }
+    if (adj) masks = nullptr;
 
     const bool tma = option(kOptPoolTma) != 0 && hw == 128 && C % kTpCh == 0 &&
                      ((reinterpret_cast<uintptr_t>(x4_1) | reinterpret_cast<uintptr_t>(x4_2)) & 15u) == 0;
@@ -1203,7 +1225,7 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
         for (int64_t b0 = 0; b0 < batch; b0 += kMaxPerLaunch) {
             const int64_t n = batch - b0 < kMaxPerLaunch ? batch - b0 : kMaxPerLaunch;
             if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, tma ? 2 : 1, st))) return rc;
-            if ((rc = launch_layers(p, pr, hwk, adj, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
+            if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
         }
         return AGRL_OK;
     }
@@ -1222,7 +1244,7 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
             const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
             const int64_t nb0 = b0 + n, nn = j + 1 < nsub ? (batch - nb0 < sub ? batch - nb0 : sub) : 0;
             Gate gate{&ctx, j, nb0, nn, p, &pr, &hwk, x4_1, x4_2, out, ld_out, S, hw, ctas};
-            if ((rc = launch_layers(p, pr, hwk, adj, out, ld_out, nodes_out, b0, n, batch, S, st, &gate))) return rc;
+            if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st, &gate))) return rc;
         }
         return AGRL_OK;
     }
@@ -1234,9 +1256,26 @@ extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prep
     for (int j = 0; j < nsub; ++j) {
         const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
         AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx.pooled[j], 0));
-        if ((rc = launch_layers(p, pr, hwk, adj, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
+        if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
     }
     return AGRL_OK;
+}
+
+extern "C" int agrl_head_forward_dev(const agrl_head_params *p, const void *prepared,
+                                     const float *x4_1, const float *x4_2, const float *adj,
+                                     float *out, int64_t ld_out, float *nodes_out,
+                                     int64_t batch, int32_t S, int32_t h, int32_t w,
+                                     void *ws, size_t ws_bytes, void *stream) {
+    return head_forward_impl(p, prepared, x4_1, x4_2, adj, nullptr, out, ld_out, nodes_out, batch, S, h, w, ws, ws_bytes, stream);
+}
+
+// same head, pose graph given as three membership masks per tracklet (pose.cu) instead of the dense matrix
+extern "C" int agrl_head_forward_compact_dev(const agrl_head_params *p, const void *prepared,
+                                             const float *x4_1, const float *x4_2, const uint64_t *part_masks,
+                                             float *out, int64_t ld_out, float *nodes_out,
+                                             int64_t batch, int32_t S, int32_t h, int32_t w,
+                                             void *ws, size_t ws_bytes, void *stream) {
+    return head_forward_impl(p, prepared, x4_1, x4_2, nullptr, part_masks, out, ld_out, nodes_out, batch, S, h, w, ws, ws_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -203,9 +203,16 @@ class VMGN(nn.Module):
         B, V = BS // seq_len, seq_len * self.total_split
         x4_1 = x4_1.float().contiguous()
         x4_2 = x4_2.float().contiguous()
+        compact = False
         if self.use_pose:
-            assert adj is not None and tuple(adj.shape) == (B, V, V), 'adj must be (B, V, V) with V = S * P'
-            adj = adj.to(device=dev, dtype=torch.float32).contiguous()
+            # adj: the reference's dense (B, V, V) fp32 graph, or the three part-membership masks per tracklet it is
+            # made of (int64 (B, 3), agrl.pytorch_b200.pose.part_masks) -- the compact wire format
+            compact = adj is not None and adj.dtype == torch.int64 and tuple(adj.shape) == (B, 3)
+            if compact:
+                adj = adj.to(device=dev).contiguous()
+            else:
+                assert adj is not None and tuple(adj.shape) == (B, V, V), 'adj must be (B, V, V) with V = S * P'
+                adj = adj.to(device=dev, dtype=torch.float32).contiguous()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             P, tensors = self._head_params()
@@ -219,7 +226,8 @@ class VMGN(nn.Module):
                 assert out.dtype == torch.float32 and out.device == dev and tuple(out.shape) == (B, 2 * C) \
                     and out.stride(1) == 1, 'out must be a (B, 2C) fp32 tensor on the input device'
             nodes = torch.empty(B, V, C, dtype=torch.float32, device=dev) if return_nodes else None
-            _lib.check(lib.agrl_head_forward_dev(
+            entry = lib.agrl_head_forward_compact_dev if compact else lib.agrl_head_forward_dev
+            _lib.check(entry(
                 ctypes.byref(P), prepared.data_ptr(), x4_1.data_ptr(), x4_2.data_ptr(),
                 adj.data_ptr() if self.use_pose else None, out.data_ptr(), out.stride(0),
                 nodes.data_ptr() if return_nodes else None, B, seq_len, h, w,

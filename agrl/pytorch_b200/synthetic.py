@@ -75,6 +75,32 @@ def quantised_distmat(nq, ng, seed=0, levels=64):
     return (rng.randint(0, levels, size=(nq, ng)).astype(np.float32) / 8.0)
 
 
+def pose_keypoints(B, S=8, seed=0, missing=0.1, img_h=(96, 320)):
+    """Synthetic OpenPose-style detections for B tracklets of S frames: keypoints (B,S,18,3) float64 [x, y, conf] in
+    ORIGINAL image coordinates, heights (B,S) float64 (original image height, dataset_loader.py:313 ``size[1]``),
+    valid (B,S) uint8 (0: the pose lookup fails for that frame, :337-338).  An upright skeleton with jitter; some
+    keypoints below the 0.1 confidence threshold, some exactly on strip boundaries, some outside the image."""
+    rng = np.random.RandomState(seed)
+    heights = rng.randint(img_h[0], img_h[1], size=(B, S)).astype(np.float64)
+    heights[rng.rand(B, S) < 0.3] = 256.0                                   # MARS boxes are 256 x 128
+    # nominal vertical position (fraction of the height) of the 18 COCO keypoints
+    nominal = np.array([0.08, 0.18, 0.20, 0.32, 0.44, 0.20, 0.32, 0.44, 0.50, 0.70, 0.92, 0.50, 0.70, 0.92,
+                        0.06, 0.06, 0.07, 0.07])
+    kp = np.zeros((B, S, 18, 3), np.float64)
+    shift = rng.uniform(-0.25, 0.25, size=(B, S, 1))                        # person not centred in the box
+    scale = rng.uniform(0.6, 1.3, size=(B, S, 1))
+    y = (nominal[None, None] * scale + shift + rng.normal(0, 0.03, size=(B, S, 18))) * heights[..., None]
+    kp[..., 0] = rng.uniform(0, 128, size=(B, S, 18))
+    kp[..., 1] = y
+    kp[..., 2] = rng.uniform(0, 1, size=(B, S, 18))
+    kp[..., 2][rng.rand(B, S, 18) < 0.15] = 0.1                             # exactly the threshold: not counted
+    on_edge = rng.rand(B, S, 18) < 0.1                                       # exactly on a strip boundary
+    edge = rng.randint(0, 5, size=(B, S, 18)) * (heights[..., None] / 4)
+    kp[..., 1] = np.where(on_edge, edge, kp[..., 1])
+    valid = (rng.rand(B, S) >= missing).astype(np.uint8)
+    return kp, heights, valid
+
+
 def pose_adjacency(B, S=8, P=7, seed=0, mode='pose'):
     """(B, S*P, S*P) fp32 pose graph in the format of dataset_loader.py:345-388: binary, symmetric,
     zero diagonal; every node that contains a given body part (head/body/leg) is connected to every

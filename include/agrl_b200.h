@@ -294,6 +294,33 @@ AGRL_API int agrl_head_forward_dev(const agrl_head_params *p, const void *prepar
  * SURVEY.md section 8(f) rows ("next"): the callers / data formats either side of the path.
  * ============================================================================================= */
 
+/* ---- Pose-guided adjacency (torchreid/dataset_loader.py: generate_graph :218-343, adj_graph :345-388) ----------
+ * Canonical configuration only: num_parts = 3 (head / body / leg keypoint classes, :318-320), num_split = 4 with
+ * the pyramid strips [4,2,1] (7 nodes per frame), method 'same', num_scale = 1.  The reference builds the dense
+ * (V, V) matrix with python sets and itertools.permutations inside the loader workers; the graph is completely
+ * described by three V-bit membership masks per tracklet (bit s*7 + strip: that node holds the class), 24 bytes
+ * instead of 12.5 KB.
+ *
+ * agrl_pose_part_masks_dev: raw detections -> masks.
+ *   keypoints_dev (batch, seq_len, 18, 3) float64 [x, y, confidence] in ORIGINAL image coordinates (the pose dict
+ *                 entry poses[key], :316); heights_dev (batch, seq_len) float64 = im_sizes[..][1] (:313);
+ *   valid_dev     (batch, seq_len) uint8, 0 where the pose lookup fails (:337-338 leaves the frame empty); may be
+ *                 NULL (all valid);  threshold: 0.1 in the reference (:219);
+ *   masks_dev     out (batch, 3) uint64.
+ * agrl_pose_adjacency_dev: masks -> the reference's dense fp32 matrix (batch, nodes, nodes), binary, zero diagonal.
+ * agrl_head_forward_compact_dev: agrl_head_forward_dev with the masks in place of adj_dev (the dense matrix is
+ *   never materialised).  Bit-identical to running agrl_head_forward_dev on the expanded matrix. */
+AGRL_API int agrl_pose_part_masks_dev(const double *keypoints_dev, const double *heights_dev, const uint8_t *valid_dev,
+                             int64_t batch, int32_t seq_len, int32_t num_split, double threshold,
+                             uint64_t *masks_dev, void *stream);
+AGRL_API int agrl_pose_adjacency_dev(const uint64_t *masks_dev, int64_t batch, int32_t nodes, float *adj_dev,
+                            void *stream);
+AGRL_API int agrl_head_forward_compact_dev(const agrl_head_params *p, const void *prepared_dev,
+                                  const float *x4_1_dev, const float *x4_2_dev, const uint64_t *part_masks_dev,
+                                  float *out_dev, int64_t ld_out, float *nodes_out_dev,
+                                  int64_t batch, int32_t seq_len, int32_t h, int32_t w,
+                                  void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Clip pooling of the `dense` / `skipdense` test sampling (train_vidreid_xent_htri.py:461-476):
  * feats (tracklets * clips, dim) with the clips of a tracklet consecutive -> out (tracklets, dim),
  * torch.mean(features, 0) (AVG) or torch.max(features, 0) values (MAX) over the clip axis. */

@@ -216,3 +216,35 @@ def make_full_model():
 
 if __name__ == '__main__' and ('full' in sys.argv[1:] or not sys.argv[1:]):
     make_full_model()
+
+
+# ------------------------------------------------------------------------------------ pose graph
+def make_pose():
+    """The reference's own generate_graph (dataset_loader.py:218-343 -> adj_graph :345-388) on synthetic OpenPose
+    detections: MARS-style paths, a pose dict with some frames missing (KeyError -> empty sets), integer image sizes.
+    Stored: the detections and the (56, 56) adjacency per tracklet (bit-packed)."""
+    from torchreid.dataset_loader import generate_graph as ref_generate_graph
+    B, S = 24, 8
+    kp, heights, valid = synth.pose_keypoints(B, S, seed=21)
+    kp[1, :, :, 2] = 0.0                         # a tracklet without a single confident keypoint -> all-zero graph
+    valid[2] = 0                                 # a tracklet whose pose file has no entry at all
+    kp[3, 2] = np.nan                            # NaN coordinates / confidences in one frame
+    heights[4] = 7.0                             # tiny boxes: np.arange yields MORE than num_split + 1 boundaries below h = 4 only
+    heights[5, :3] = [1.0, 2.0, 3.0]             # ... exercised here
+    adjs = []
+    for b in range(B):
+        paths = ['data/mars/bbox_test/%04d/%04dC1T%04dF%03d.jpg' % (b, b, b, s) for s in range(S)]
+        poses = {p.split('/')[-1]: kp[b, s] for s, p in enumerate(paths) if valid[b, s]}
+        sizes = [(128, int(heights[b, s])) for s in range(S)]
+        adj = ref_generate_graph([None] * S, im_paths=paths, im_sizes=sizes, poses=poses, num_split=4, num_parts=3,
+                                 num_scale=1, pyramid_part=True)
+        adjs.append(adj.numpy())
+    adjs = np.stack(adjs)
+    assert adjs.shape == (B, 56, 56) and set(np.unique(adjs)) <= {0.0, 1.0}
+    np.savez_compressed(os.path.join(HERE, 'pose_graph.npz'), keypoints=kp, heights=heights, valid=valid,
+                        adj_bits=np.packbits(adjs.astype(np.uint8), axis=-1), density=np.float64(adjs.mean()))
+    print('pose_graph', adjs.shape, 'density %.3f' % adjs.mean(), 'empty graphs', int((adjs.sum((1, 2)) == 0).sum()))
+
+
+if __name__ == '__main__' and ('pose' in sys.argv[1:] or not sys.argv[1:]):
+    make_pose()
