@@ -76,6 +76,9 @@ _SIGNATURES = {
     'agrl_pose_adjacency_dev': (c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'agrl_head_forward_compact_dev': (c_int, [ctypes.POINTER(HeadParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
                                               c_i64, c_i32, c_i32, c_i32, c_vp, c_sz, c_vp]),
+    'agrl_rerank_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64, c_i64]),
+    'agrl_rerank_dev': (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.c_double,
+                                c_vp, c_i64, c_vp, c_sz, c_vp]),
     'agrl_clip_pool_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_vp]),
     'agrl_head_prepared_bytes': (c_sz, [ctypes.POINTER(HeadParams)]),
     'agrl_head_prepare_dev': (c_int, [ctypes.POINTER(HeadParams), c_vp, c_sz, c_vp]),

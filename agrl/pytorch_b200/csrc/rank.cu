@@ -19,18 +19,16 @@
 // The sequential floating-point recurrences of the reference (float accumulation with the term in
 // double for rank_cy; Python-double arithmetic and numpy's pairwise mean for evaluate_mars) are
 // reproduced with explicitly rounded intrinsics, so no FMA contraction can change a bit.
-#include "common.cuh"
+#include "topk.cuh"
 
 #include <limits.h>
 #include <string.h>
 
 namespace agrl {
 
-constexpr int kRankThreads = 256;
 constexpr int kFastBins    = 64;     // fast path: same-pid list of <= 62 items, padded to 64
 constexpr int kListCap     = 2048;   // shared-histogram path: list of <= 2048 items
 constexpr int kOverflowCtas = 8;     // brute-force path for longer lists
-constexpr uint64_t kKeyMax = 0xFFFFFFFFFFFFFFFFull;
 
 // ------------------------------------------------------------------------------------------------
 // labels: int64 (ABI) -> int32 (kernels), flagging values that do not fit
@@ -54,25 +52,6 @@ __global__ void narrow_labels_kernel(LabelArrays a, uint32_t *status) {
         dst[i] = static_cast<int32_t>(v);
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, AGRL_ST_LABEL_RANGE);
-}
-
-// ------------------------------------------------------------------------------------------------
-// shared-memory bitonic sort of n2 (power of two) uint64 keys by `nthreads` cooperating threads
-// ------------------------------------------------------------------------------------------------
-template <bool kWarpOnly>
-__device__ __forceinline__ void bitonic_sort_u64(uint64_t *keys, int n2, int tid, int nthreads) {
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (n2 >> 1); t += nthreads) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi = lo | j;
-                const uint64_t a = keys[lo], b = keys[hi];
-                const bool up = ((lo & k) == 0);
-                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-            }
-            if (kWarpOnly) __syncwarp(); else __syncthreads();
-        }
-    }
 }
 
 // visit every element of a row once, 16-byte vector loads over the aligned body
@@ -602,8 +581,6 @@ struct MarsArgs {
     uint32_t       index_offset;                    // global index of this shard's first gallery row
 };
 
-constexpr int kMarsTile = 1024;                     // elements examined between buffer checks
-
 // number of good images for the query: same pid, other camera (rank.py:166); result in *s_ngood
 __device__ __forceinline__ void mars_count_good(const MarsArgs &a, int pid, int cam, int tid, int *s_ngood) {
     const int ng = a.num_g;
@@ -621,62 +598,6 @@ __device__ __forceinline__ void mars_count_good(const MarsArgs &a, int pid, int 
     if (j < ng && a.g_pid[j] == pid) good += (a.g_cam[j] != cam);
     good = warp_sum(good);
     if ((tid & 31) == 0 && good) atomicAdd(s_ngood, good);
-}
-
-// Running top-K of one row: candidates below the threshold (K-th smallest key so far) go to a
-// shared buffer, which is sorted and cut back to K whenever the next tile could overflow it.
-// The first tile is short (one element per thread) so that a cheap sort establishes a threshold
-// early; with it only ~K*ln(n/256) later elements ever reach the buffer.  Sorts cover just the
-// occupied power-of-two prefix.  On return buf[0..valid) holds the min(K, n) smallest keys in order.
-__device__ __forceinline__ int mars_select_topk(const float *__restrict__ row, int ng, int K, int L,
-                                                uint64_t *buf, int *s_cnt, unsigned long long *s_thr, int tid) {
-    int base = 0;
-    bool first = true;
-    while (base < ng) {
-        const uint64_t thr = *s_thr;
-        const int tile = (first && K <= kRankThreads / 2) ? kRankThreads : kMarsTile;
-        if (tile == kRankThreads) {
-            const int j = base + tid;
-            if (j < ng) {
-                const uint64_t key = rank_key(row[j], static_cast<uint32_t>(j));
-                if (key < thr) buf[atomicAdd(s_cnt, 1)] = key;
-            }
-        } else {
-            const int j = base + tid * 4;               // thread t owns 4 consecutive elements of the tile
-            float d[4];
-            int n_here = 0;
-            if (j + 3 < ng && ((reinterpret_cast<uintptr_t>(row + j) & 15u) == 0)) {
-                const float4 x = __ldg(reinterpret_cast<const float4 *>(row + j));
-                d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w; n_here = 4;
-            } else {
-                for (int k = 0; k < 4; ++k) if (j + k < ng) { d[k] = row[j + k]; n_here = k + 1; }
-            }
-            for (int k = 0; k < n_here; ++k) {
-                const uint64_t key = rank_key(d[k], static_cast<uint32_t>(j + k));
-                if (key < thr) buf[atomicAdd(s_cnt, 1)] = key;    // *s_cnt <= L - kMarsTile before a tile
-            }
-        }
-        base += tile;
-        __syncthreads();
-        const int cnt = *s_cnt;
-        __syncthreads();                   // everyone holds the same cnt before anyone appends again
-        const bool last = (base >= ng);
-        if (cnt > L - kMarsTile || last || first) {
-            int n2 = 2;
-            while (n2 < cnt) n2 <<= 1;                 // cnt <= L and L is a power of two
-            for (int i = cnt + tid; i < n2; i += kRankThreads) buf[i] = kKeyMax;
-            __syncthreads();
-            bitonic_sort_u64<false>(buf, n2, tid, kRankThreads);
-            if (tid == 0) {
-                const int keep = cnt < K ? cnt : K;
-                *s_cnt = keep;
-                if (keep == K) *s_thr = buf[K - 1];    // later keys must beat the current K-th
-            }
-            __syncthreads();
-        }
-        first = false;
-    }
-    return *s_cnt;
 }
 
 // Compute_AP (rank.py:180-212) in Python-float (double) arithmetic, one rounding per operation.
@@ -733,7 +654,7 @@ rank_mars_kernel(MarsArgs a) {
     if (tid == 0) { s_cnt = 0; s_ngood = 0; s_thr = kKeyMax; }
     __syncthreads();
     mars_count_good(a, pid, cam, tid, &s_ngood);
-    const int valid = mars_select_topk(row, a.num_g, K, a.buf_len, buf, &s_cnt, &s_thr, tid);
+    const int valid = select_topk(row, a.num_g, K, a.buf_len, buf, &s_cnt, &s_thr, tid);
 
     // classify the ranked items: bit0 good, bit1 junk (rank.py:166-169)
     for (int n = tid; n < K; n += kRankThreads) {

@@ -321,6 +321,18 @@ AGRL_API int agrl_head_forward_compact_dev(const agrl_head_params *p, const void
                                   int64_t batch, int32_t seq_len, int32_t h, int32_t w,
                                   void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* ---- k-reciprocal re-ranking (torchreid/utils/re_ranking.py:30-94; test() :523-527 with --re-rank) ---------------
+ * q_g (num_q, num_g), q_q (num_q, num_q), g_g (num_g, num_g) fp32 distance matrices with row strides ld_*;
+ * out (num_q, num_g) fp32 = jaccard * (1 - lambda) + normalised original distance * lambda.
+ * Ties of the initial ranking are broken by index (numpy.argsort(kind='stable')).  Index work is exact; values
+ * follow the reference's float32 operation order except expf vs numpy's exp (<= 2 ulp) -> agreement ~1e-6.
+ * Limits: k1 <= 30, k2 <= 8, num_q + num_g <= 46000 (AGRL_E_UNSUPPORTED beyond; workspace_bytes returns 0). */
+AGRL_API size_t agrl_rerank_workspace_bytes(int64_t num_q, int64_t num_g, int64_t k1, int64_t k2);
+AGRL_API int    agrl_rerank_dev(const float *q_g_dev, int64_t ld_qg, const float *q_q_dev, int64_t ld_qq,
+                       const float *g_g_dev, int64_t ld_gg, int64_t num_q, int64_t num_g,
+                       int64_t k1, int64_t k2, double lambda_value,
+                       float *out_dev, int64_t ld_out, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Clip pooling of the `dense` / `skipdense` test sampling (train_vidreid_xent_htri.py:461-476):
  * feats (tracklets * clips, dim) with the clips of a tracklet consecutive -> out (tracklets, dim),
  * torch.mean(features, 0) (AVG) or torch.max(features, 0) values (MAX) over the clip axis. */

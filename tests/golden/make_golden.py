@@ -248,3 +248,35 @@ def make_pose():
 
 if __name__ == '__main__' and ('pose' in sys.argv[1:] or not sys.argv[1:]):
     make_pose()
+
+
+# ------------------------------------------------------------------------------------ re-ranking
+def make_rerank():
+    """The reference's own re_ranking() (utils/re_ranking.py:30-94) as test() calls it (train_vidreid_xent_htri.py:
+    523-527: the three distance matrices come from compute_distance_matrix), numpy.argsort forced stable."""
+    from torchreid.utils.re_ranking import re_ranking as ref_re_ranking
+    cases = {
+        'clustered': dict(nq=40, ng=260, nid=12, d=64, metric='euclidean', k1=20, k2=6, lam=0.3),
+        'cosine': dict(nq=25, ng=150, nid=8, d=48, metric='cosine', k1=20, k2=6, lam=0.3),
+        'tiny': dict(nq=3, ng=9, nid=2, d=16, metric='euclidean', k1=20, k2=6, lam=0.3),     # N < k1 + 1
+        'k2_one': dict(nq=20, ng=120, nid=6, d=32, metric='euclidean', k1=10, k2=1, lam=0.5),
+        'ties': dict(nq=16, ng=100, nid=5, d=8, metric='euclidean', k1=7, k2=3, lam=0.3, quantise=True),
+    }
+    for name, c in cases.items():
+        qp, qc, gp, gc = synth.eval_labels((c['nq'], c['ng'], c['nid'], 3), seed=31)
+        qf, gf = synth.eval_features(qp, gp, c['d'], seed=32, clustered=True)
+        if c.get('quantise'):
+            qf, gf = torch.round(qf), torch.round(gf)                  # integer features -> many exact distance ties
+        qg = ref_metrics.compute_distance_matrix(qf, gf, c['metric']).numpy()
+        qq = ref_metrics.compute_distance_matrix(qf, qf, c['metric']).numpy()
+        gg = ref_metrics.compute_distance_matrix(gf, gf, c['metric']).numpy()
+        with orank.stable_argsort():
+            out = ref_re_ranking(qg, qq, gg, k1=c['k1'], k2=c['k2'], lambda_value=c['lam'])
+        assert out.shape == (c['nq'], c['ng']) and out.dtype == np.float32
+        np.savez_compressed(os.path.join(HERE, 'rerank_%s.npz' % name), q_g=qg, q_q=qq, g_g=gg, out=out,
+                            k1=np.int64(c['k1']), k2=np.int64(c['k2']), lam=np.float64(c['lam']))
+        print('rerank_%s' % name, out.shape, float(out.min()), float(out.max()))
+
+
+if __name__ == '__main__' and ('rerank' in sys.argv[1:] or not sys.argv[1:]):
+    make_rerank()
