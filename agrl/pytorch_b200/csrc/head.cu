@@ -607,15 +607,14 @@ graph_kernel(GraphArgs a) {
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     if (p < a.P) {
-                        const __nv_bfloat16 b0 = __float2bfloat16_rn(v0), b1 = __float2bfloat16_rn(v1);
-                        const __nv_bfloat16 b2 = __float2bfloat16_rn(v2), b3 = __float2bfloat16_rn(v3);
-                        __nv_bfloat162 lo = __halves2bfloat162(b0, b1), hi = __halves2bfloat162(b2, b3);
+                        // packed conversions (F2FP, full rate) -- the scalar F2F path runs at a quarter of it
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
                         uint2 pk;
-                        pk.x = *reinterpret_cast<uint32_t *>(&lo);
-                        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
                         *reinterpret_cast<uint2 *>(dst + p * a.plane_stride) = pk;
-                        v0 = __fsub_rn(v0, __bfloat162float(b0)); v1 = __fsub_rn(v1, __bfloat162float(b1));
-                        v2 = __fsub_rn(v2, __bfloat162float(b2)); v3 = __fsub_rn(v3, __bfloat162float(b3));
+                        v0 = __fsub_rn(v0, __uint_as_float(pk.x << 16)); v1 = __fsub_rn(v1, __uint_as_float(pk.x & 0xffff0000u));
+                        v2 = __fsub_rn(v2, __uint_as_float(pk.y << 16)); v3 = __fsub_rn(v3, __uint_as_float(pk.y & 0xffff0000u));
                     }
                 }
             }
@@ -819,15 +818,14 @@ graph_kernel_v2(GraphArgs a) {
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     if (p < a.P) {
-                        const __nv_bfloat16 b0 = __float2bfloat16_rn(v0), b1 = __float2bfloat16_rn(v1);
-                        const __nv_bfloat16 b2 = __float2bfloat16_rn(v2), b3 = __float2bfloat16_rn(v3);
-                        __nv_bfloat162 lo = __halves2bfloat162(b0, b1), hi = __halves2bfloat162(b2, b3);
+                        // packed conversions (F2FP, full rate) -- the scalar F2F path runs at a quarter of it
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
                         uint2 pk;
-                        pk.x = *reinterpret_cast<uint32_t *>(&lo);
-                        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
                         *reinterpret_cast<uint2 *>(dst + p * a.plane_stride) = pk;
-                        v0 = __fsub_rn(v0, __bfloat162float(b0)); v1 = __fsub_rn(v1, __bfloat162float(b1));
-                        v2 = __fsub_rn(v2, __bfloat162float(b2)); v3 = __fsub_rn(v3, __bfloat162float(b3));
+                        v0 = __fsub_rn(v0, __uint_as_float(pk.x << 16)); v1 = __fsub_rn(v1, __uint_as_float(pk.x & 0xffff0000u));
+                        v2 = __fsub_rn(v2, __uint_as_float(pk.y << 16)); v3 = __fsub_rn(v3, __uint_as_float(pk.y & 0xffff0000u));
                     }
                 }
             }
