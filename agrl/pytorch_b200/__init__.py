@@ -7,13 +7,16 @@ Host-side mirror of the reference's interface for that path, over the C ABI of l
     agrl.pytorch_b200.metrics.compute_distance_matrix       <- torchreid/metrics/distance.py:11
     agrl.pytorch_b200.metrics.evaluate_rank                 <- torchreid/metrics/rank.py:215
     agrl.pytorch_b200.metrics.rank_cylib.rank_cy.evaluate_cy <- rank_cylib/rank_cy.pyx:24
+    agrl.pytorch_b200.utils.re_ranking.re_ranking           <- torchreid/utils/re_ranking.py:30   (section 8f)
+    agrl.pytorch_b200.pose.generate_graph                   <- torchreid/dataset_loader.py:218    (section 8f)
+    agrl.pytorch_b200.models.pool_clips                     <- train_vidreid_xent_htri.py:471-476 (section 8f)
 
 ``install_as_torchreid()`` registers these under the reference's own dotted names so an unmodified
 caller (``from torchreid import metrics, models``) picks them up.  There is no CPU fallback.
 """
 import sys
 
-from . import metrics, models
+from . import metrics, models, pose, utils
 
 __all__ = ['install_as_torchreid']
 
@@ -38,4 +41,12 @@ def install_as_torchreid(force=False):
     root.models = models
     sys.modules['torchreid.models'] = models
     sys.modules['torchreid.models.vmgn'] = models.vmgn_module
+    # section 8(f): re-ranking (train_vidreid_xent_htri.py:26) and the pose-graph builder of the loader
+    root.utils = utils
+    sys.modules['torchreid.utils'] = utils
+    sys.modules['torchreid.utils.re_ranking'] = utils.re_ranking_module
+    loader = types.ModuleType('torchreid.dataset_loader')
+    loader.generate_graph = pose.generate_graph
+    root.dataset_loader = loader
+    sys.modules['torchreid.dataset_loader'] = loader
     return root

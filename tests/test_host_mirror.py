@@ -65,7 +65,31 @@ def test_install_as_torchreid_aliases():
         from torchreid.metrics.rank import IS_CYTHON_AVAI
         assert metrics.evaluate_rank is pkg.metrics.evaluate_rank and callable(evaluate_cy) and IS_CYTHON_AVAI
         assert models.init_model is pkg.models.init_model
+        from torchreid.utils.re_ranking import re_ranking                     # train_vidreid_xent_htri.py:26
+        from torchreid.dataset_loader import generate_graph
+        assert re_ranking is pkg.utils.re_ranking and generate_graph is pkg.pose.generate_graph
     finally:
         for k in [k for k in sys.modules if k == 'torchreid' or k.startswith('torchreid.')]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_pose_key_and_keypoint_packing_need_no_device():
+    from agrl.pytorch_b200 import pose
+    paths = ['data/mars/bbox_test/0001/0001C1T0001F%03d.jpg' % s for s in range(3)]
+    poses = {paths[0].split('/')[-1]: np.ones((18, 3)), paths[2].split('/')[-1]: np.full((18, 3), 2.0)}
+    kp, heights, valid = pose.pack_keypoints(paths, [(128, 256), (64, 100), (128, 256)], poses)
+    assert kp.shape == (3, 18, 3) and list(valid) == [1, 0, 1] and list(heights) == [256.0, 100.0, 256.0]
+    assert kp[2, 5, 1] == 2.0 and kp[1].sum() == 0
+    with pytest.raises(ValueError, match='is not acceptable'):
+        pose.pose_key('elsewhere/img.jpg')
+    assert pose.pose_key('data/dukemtmc-vidreid/DukeMTMC-VideoReID/train/0148/0212/0148_C5_F0006_X89499.jpg') == \
+        '0148-0212-0148_C5_F0006_X89499.jpg'
+
+
+def test_rerank_workspace_query_and_limits():
+    from agrl.pytorch_b200 import _lib
+    lib = _lib.load()
+    assert lib.agrl_rerank_workspace_bytes(1980, 9330, 20, 6) > 4 * 11310 * 11310
+    assert lib.agrl_rerank_workspace_bytes(1980, 9330, 64, 6) == 0            # k1 beyond one warp of neighbours
+    assert lib.agrl_rerank_workspace_bytes(0, 10, 20, 6) == 0
