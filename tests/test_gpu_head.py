@@ -257,3 +257,39 @@ def test_fp16_single_plane_mode_is_range_safe(map_scale, w_std, use_pose, learn_
     emax, enrm = rel_err(out.cpu()[:, 2048:], ref[:, 2048:])       # the attention half is the one the GEMM feeds
     tol = 1e-3 if w_std > 1.0 else TOL
     assert emax < tol and enrm < tol, (emax, enrm)
+
+
+@pytest.mark.parametrize('S', [1, 4, 5, 9])
+@pytest.mark.parametrize('split', [1, 2])
+def test_head_other_sequence_lengths(S, split, restore_options):
+    """V = 7 S nodes: 7 / 28 / 35 (graph_kernel_v2 with zero-padded rows), 63 (graph_kernel, 64-node tiling);
+    the bulk-copy pooling ring with fewer / more frames than stages; sub-batched as well."""
+    lib = restore_options
+    B = 5
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=90 + S, scale=2.0)
+    adj = synth.pose_adjacency(B, S, 7, seed=91 + S)
+    wts = synth.head_weights(2048, 2, seed=92, randomise_bn=True)
+    model = make_model(wts, split=split)
+    ref = ohead.head_forward(x1, x2, adj, wts, S=S, dtype=torch.float64)
+    for sub in (0, 2):
+        lib.set_option('head_sub_batch', sub)
+        with torch.no_grad():
+            out = model.head(x1.cuda(), x2.cuda(), adj.cuda(), S)
+        emax, enrm = rel_err(out.cpu(), ref)
+        assert emax < TOL and enrm < TOL, (S, split, sub, emax, enrm)
+
+
+def test_head_empty_batch_and_single_tracklet():
+    wts = synth.head_weights(2048, 2, seed=93)
+    model = make_model(wts)
+    with torch.no_grad():
+        out = model.head(torch.zeros(0, 2048, 16, 8, device='cuda'), torch.zeros(0, 2048, 16, 8, device='cuda'),
+                         torch.zeros(0, 56, 56, device='cuda'), 8)
+    assert tuple(out.shape) == (0, 4096)
+    x1, x2 = synth.feature_maps(1, 8, 2048, 16, 8, seed=94)
+    adj = synth.pose_adjacency(1, 8, 7, seed=95)
+    ref = ohead.head_forward(x1, x2, adj, wts, dtype=torch.float64)
+    with torch.no_grad():
+        out = model.head(x1.cuda(), x2.cuda(), adj.cuda(), 8)
+    emax, enrm = rel_err(out.cpu(), ref)
+    assert emax < TOL and enrm < TOL
