@@ -201,6 +201,9 @@ class VMGN(nn.Module):
         dev = x4_1.device
         BS, C, h, w = x4_1.shape
         B, V = BS // seq_len, seq_len * self.total_split
+        if B == 0:                                                   # empty loader batch: nothing to launch
+            empty = torch.empty(0, 2 * C, dtype=torch.float32, device=dev) if out is None else out
+            return (empty, torch.empty(0, V, C, dtype=torch.float32, device=dev)) if return_nodes else empty
         x4_1 = x4_1.float().contiguous()
         x4_2 = x4_2.float().contiguous()
         compact = False
