@@ -32,6 +32,7 @@ class HeadParams(ctypes.Structure):
         ('bn_weight', c_vp * HEAD_MAX_LAYERS), ('bn_bias', c_vp * HEAD_MAX_LAYERS),
         ('bn_mean', c_vp * HEAD_MAX_LAYERS), ('bn_var', c_vp * HEAD_MAX_LAYERS),
         ('global_bn', c_vp * 4), ('att_bn', c_vp * 4),
+        ('maps_nhwc', c_i32),
     ]
 
 

@@ -172,6 +172,61 @@ pool_kernel(PoolArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// pooling, channels-last maps (the part that stays on our side of the cuDNN boundary):
+// a backbone run in torch.channels_last hands over (B*S, h, w, C)-ordered memory; converting it back to NCHW would
+// cost a second pass over the 16 MiB per tracklet.  Here a thread owns 4 consecutive channels (one 16-byte load per
+// pixel, fully coalesced across the CTA), keeps the four quarter-strip sums in registers and writes node rows
+// straight from them.  grid (C / 1024, B), 256 threads.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add4(float4 &a, const float4 &b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ float4 scale4(const float4 &a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+__global__ void __launch_bounds__(kHeadThreads)
+pool_nhwc_kernel(PoolArgs a) {
+    const int b = blockIdx.y;
+    const int c = (blockIdx.x * kHeadThreads + threadIdx.x) * 4;
+    if (c >= a.C) return;
+    const int hw = a.hw, qlen = hw >> 2, V = a.S * kParts;
+    const float inv_q = 1.0f / static_cast<float>(qlen), inv_h = 1.0f / static_cast<float>(2 * qlen);
+    const float inv_w = 1.0f / static_cast<float>(hw);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float *nodes = a.nodes + static_cast<size_t>(b) * V * a.C + c;
+    for (int s = 0; s < a.S; ++s) {
+        const size_t frame = (static_cast<size_t>(b) * a.S + s) * hw * a.C + c;
+        float4 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+            const size_t base = frame + static_cast<size_t>(k) * qlen * a.C;
+#pragma unroll 8
+            for (int p = 0; p < qlen; ++p) {
+                add4(s1, __ldcs(reinterpret_cast<const float4 *>(a.x41 + base + static_cast<size_t>(p) * a.C)));
+                add4(s2, __ldcs(reinterpret_cast<const float4 *>(a.x42 + base + static_cast<size_t>(p) * a.C)));
+            }
+            add4(g, s1);
+            q[k] = s2;
+        }
+        float4 h0 = q[0], h1 = q[2];
+        add4(h0, q[1]); add4(h1, q[3]);
+        float4 w = h0;
+        add4(w, h1);
+        float *row = nodes + static_cast<size_t>(s) * kParts * a.C;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<float4 *>(row + static_cast<size_t>(k) * a.C) = scale4(q[k], inv_q);
+        *reinterpret_cast<float4 *>(row + 4 * static_cast<size_t>(a.C)) = scale4(h0, inv_h);
+        *reinterpret_cast<float4 *>(row + 5 * static_cast<size_t>(a.C)) = scale4(h1, inv_h);
+        *reinterpret_cast<float4 *>(row + 6 * static_cast<size_t>(a.C)) = scale4(w, inv_w);
+    }
+    const float inv_all = 1.0f / (static_cast<float>(a.S) * static_cast<float>(hw));
+    const float4 sc = *reinterpret_cast<const float4 *>(a.g_scale + c), sh = *reinterpret_cast<const float4 *>(a.g_shift + c);
+    float4 o;
+    o.x = fmaf(g.x * inv_all, sc.x, sh.x); o.y = fmaf(g.y * inv_all, sc.y, sh.y);
+    o.z = fmaf(g.z * inv_all, sc.z, sh.z); o.w = fmaf(g.w * inv_all, sc.w, sh.w);
+    float *dst = a.out + static_cast<size_t>(b) * a.ld_out + c;
+    dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w;      // ld_out need not be a multiple of 4
+}
+
+// ------------------------------------------------------------------------------------------------
 // pooling, bulk-copy (TMA) flavour: a persistent, deliberately small CTA (1 producer + 4 consumer
 // warps, < 64 registers) that keeps its loads in flight in a shared-memory ring instead of in
 // registers, so that it can sit NEXT TO the graph / GEMM CTAs of the previous sub-batch on the same SM
@@ -1069,6 +1124,13 @@ static int launch_pool(const agrl_head_params *p, const Prepared &pr, const Head
     float *nodes = hwk.x[0] + static_cast<size_t>(b0) * V * C;
     float *o = out + static_cast<size_t>(b0) * ld_out;
     AGRL_LAUNCH_BEGIN(st);
+    if (p->maps_nhwc) {
+        PoolArgs pa{x4_1 + in_off, x4_2 + in_off, nodes, o, ld_out, pr.scale[L], pr.shift[L], S, C, hw};
+        const dim3 grid((C / 4 + kHeadThreads - 1) / kHeadThreads, static_cast<unsigned>(n));
+        pool_nhwc_kernel<<<grid, kHeadThreads, 0, st>>>(pa);
+        AGRL_LAUNCH_CHECK(st, "pool");
+        return AGRL_OK;
+    }
     if (tma) {
         const int64_t all_units = n * (C / kTpCh);
         if (unit_hi < 0) unit_hi = all_units;
@@ -1211,7 +1273,8 @@ static int head_forward_impl(const agrl_head_params *p, const void *prepared,
     if (!p->use_pose) { adj = nullptr; masks = nullptr; }
     if (adj) masks = nullptr;
 
-    const bool tma = option(kOptPoolTma) != 0 && hw == 128 && C % kTpCh == 0 &&
+    if (p->maps_nhwc && (((reinterpret_cast<uintptr_t>(x4_1) | reinterpret_cast<uintptr_t>(x4_2)) & 15u) != 0)) return AGRL_E_UNSUPPORTED;
+    const bool tma = !p->maps_nhwc && option(kOptPoolTma) != 0 && hw == 128 && C % kTpCh == 0 &&
                      ((reinterpret_cast<uintptr_t>(x4_1) | reinterpret_cast<uintptr_t>(x4_2)) & 15u) == 0;
     int64_t sub = option(kOptHeadSubBatch);
     if (sub > 0 && (batch + sub - 1) / sub > kMaxSubBatches) sub = (batch + kMaxSubBatches - 1) / kMaxSubBatches;

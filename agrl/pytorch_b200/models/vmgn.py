@@ -204,8 +204,15 @@ class VMGN(nn.Module):
         if B == 0:                                                   # empty loader batch: nothing to launch
             empty = torch.empty(0, 2 * C, dtype=torch.float32, device=dev) if out is None else out
             return (empty, torch.empty(0, V, C, dtype=torch.float32, device=dev)) if return_nodes else empty
-        x4_1 = x4_1.float().contiguous()
-        x4_2 = x4_2.float().contiguous()
+        # a torch.channels_last backbone hands over (B*S, h, w, C)-ordered memory: pooled as is (no NCHW copy)
+        nhwc = (x4_1.dim() == 4 and C % 4 == 0 and not x4_1.is_contiguous()
+                and x4_1.is_contiguous(memory_format=torch.channels_last)
+                and x4_2.is_contiguous(memory_format=torch.channels_last))
+        if nhwc:
+            x4_1, x4_2 = x4_1.float(), x4_2.float()                  # .float() keeps the memory format
+        else:
+            x4_1 = x4_1.float().contiguous()
+            x4_2 = x4_2.float().contiguous()
         compact = False
         if self.use_pose:
             # adj: the reference's dense (B, V, V) fp32 graph, or the three part-membership masks per tracklet it is
@@ -219,6 +226,7 @@ class VMGN(nn.Module):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             P, tensors = self._head_params()
+            P.maps_nhwc = int(nhwc)
             prepared = self._prepared(lib, P, tensors, dev, stream)
             wsb = lib.agrl_head_workspace_bytes(ctypes.byref(P), B, seq_len)
             if self._ws is None or self._ws.device != dev or self._ws.numel() < wsb:

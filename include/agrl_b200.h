@@ -267,6 +267,9 @@ typedef struct agrl_head_params {
     const float *bn_var[AGRL_HEAD_MAX_LAYERS];
     const float *global_bn[4];    /* global_bottleneck.{weight,bias,running_mean,running_var}      */
     const float *att_bn[4];       /* att_bottleneck.{weight,bias,running_mean,running_var}         */
+    int32_t maps_nhwc;            /* 0: x4_1 / x4_2 are (B*S, C, h, w) NCHW-contiguous (the reference);
+                                     1: channels-last memory, (B*S, h, w, C) (torch.channels_last
+                                     backbone): pooled directly, no layout conversion pass            */
 } agrl_head_params;
 
 /* bytes of the persistent, weight-derived buffer (bf16 planes of W, folded BN scale/shift) */
@@ -277,7 +280,8 @@ AGRL_API int    agrl_head_prepare_dev(const agrl_head_params *p, void *prepared_
 AGRL_API size_t agrl_head_workspace_bytes(const agrl_head_params *p, int64_t batch, int32_t seq_len);
 
 /*
- *   x4_1_dev, x4_2_dev  (batch*seq_len, C, h, w) fp32 NCHW contiguous (layer4_1 / layer4_2 outputs)
+ *   x4_1_dev, x4_2_dev  (batch*seq_len, C, h, w) fp32 NCHW contiguous (layer4_1 / layer4_2 outputs), or the same
+ *                       tensors in channels-last memory when p->maps_nhwc (16-byte aligned)
  *   adj_dev             (batch, V, V) fp32, V = seq_len * 7 (dataset_loader.py:345-388); may be NULL
  *                       when use_pose == 0
  *   out_dev             (batch, 2*C) fp32, row stride ld_out: [BN(global mean) | BN(attention feature)]

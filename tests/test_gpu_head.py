@@ -293,3 +293,27 @@ def test_head_empty_batch_and_single_tracklet():
         out = model.head(x1.cuda(), x2.cuda(), adj.cuda(), 8)
     emax, enrm = rel_err(out.cpu(), ref)
     assert emax < TOL and enrm < TOL
+
+
+@pytest.mark.parametrize('w', [8, 2])
+def test_channels_last_maps_are_pooled_without_a_layout_copy(w, restore_options):
+    """a torch.channels_last backbone hands over (B*S, h, w, C)-ordered memory: same result as NCHW"""
+    lib = restore_options
+    S, B = 8, 6
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, w, seed=97, scale=2.0)
+    adj = synth.pose_adjacency(B, S, 7, seed=98)
+    wts = synth.head_weights(2048, 2, seed=99, randomise_bn=True)
+    model = make_model(wts)
+    ref = ohead.head_forward(x1, x2, adj, wts, dtype=torch.float64)
+    c1 = x1.cuda().contiguous(memory_format=torch.channels_last)
+    c2 = x2.cuda().contiguous(memory_format=torch.channels_last)
+    assert not c1.is_contiguous()
+    for sub in (0, 4):
+        lib.set_option('head_sub_batch', sub)
+        with torch.no_grad():
+            nchw = model.head(x1.cuda(), x2.cuda(), adj.cuda(), S)
+            nhwc = model.head(c1, c2, adj.cuda(), S)
+        emax, enrm = rel_err(nhwc.cpu(), ref)
+        assert emax < TOL and enrm < TOL, (w, sub, emax, enrm)
+        emax, _ = rel_err(nhwc.cpu(), nchw.cpu())
+        assert emax < 5e-6

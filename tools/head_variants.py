@@ -1,5 +1,5 @@
 """Head-pipeline variants on one resident input pool (one process, options switched at run time).
-usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split call)
+usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split pair nhwc call)
 `call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
 import json
 import os
@@ -39,9 +39,13 @@ def main():
         call = min(cfg['call'], pool_n)
         chunks = [(o, min(call, J - o)) for o in range(0, J, call)]
 
+        if cfg.get('nhwc') and 'cl' not in globals():
+            globals()['cl'] = (x1.contiguous(memory_format=torch.channels_last), x2.contiguous(memory_format=torch.channels_last))
+        m1, m2 = globals()['cl'] if cfg.get('nhwc') else (x1, x2)
+
         def head_pass():
             for off, n in chunks:
-                model.head(x1[:n * S], x2[:n * S], adj[:n], S, out=feats[off:off + n])
+                model.head(m1[:n * S], m2[:n * S], adj[:n], S, out=feats[off:off + n])
         try:
             with torch.no_grad():
                 for _ in range(2):
