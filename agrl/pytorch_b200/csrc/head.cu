@@ -889,6 +889,318 @@ graph_kernel_v2(GraphArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// graph kernel on the tensor cores (graph_variant 8): the two 56 x 56 x 2048 products of a graph layer -- the Gram
+// matrix X.X^T and the message passing Y = G.X -- as tcgen05 MMAs whose operands the CTA converts itself in shared
+// memory (no extra HBM traffic: X is read twice, Y planes written once, exactly as in the CUDA-core kernels).
+//   Gram   per 64-channel block the [node][channel] tile is split into THREE bf16 planes (fp32-exact, the distances
+//          d2 = |xi|^2 + |xj|^2 - 2 xi.xj cancel) in the 128-byte-swizzled K-major layout and multiplied with itself:
+//          6 plane products, M = 128 (rows 64.. are don't-care), N = 64, accumulated over all blocks in TMEM with the
+//          dominant product in its own accumulator (as the distance GEMM does).
+//   G      affinity, L1 rows, pose mixing on CUDA cores exactly as in graph_kernel; then G as two bf16 planes.
+//   Y      per 64-channel block the TRANSPOSED tile [channel][node] (K = nodes) as two bf16 planes; D = G.X^T block,
+//          3 plane products (same 16-bit operand class as the planes Y is rounded to anyway), double-buffered
+//          accumulator so the epilogue of block i-1 (TMEM -> planes -> global) runs under the MMAs of block i.
+// One CTA per tracklet, 256 threads, 2-3 CTAs per SM (74 KiB smem, 128 TMEM columns each).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcPlane = 64 * 128;                     // one operand plane: 64 rows x 128 B
+constexpr int kTcRing = 6 * kTcPlane;                  // Gram: 2 buffers x 3 planes; Y: 2 buffers x 2 planes
+constexpr int kTcSlack = kTcPlane;                     // rows 64..127 of the last plane's 128-row descriptor land here
+constexpr int kTcGPlanes = kTcRing + kTcSlack;         // two G planes, followed by g[] (their 128-row tail)
+constexpr int kTcG = kTcGPlanes + 2 * kTcPlane;
+constexpr int kTcSmem = kTcG + (kMaxNodes * kGLd + kMaxNodes) * 4 + 64 + 1024;
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 8 fp32 -> `P` bf16 planes of 8 values (16 bytes each): p0 = bf16(x), p1 = bf16(x - p0), ...
+template <int P>
+__device__ __forceinline__ void split8(const float (&v)[8], uint4 (&out)[P]) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = v[i];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 b = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t *>(&b);
+            r[2 * i] = __fsub_rn(r[2 * i], __uint_as_float(w[i] << 16));
+            r[2 * i + 1] = __fsub_rn(r[2 * i + 1], __uint_as_float(w[i] & 0xffff0000u));
+        }
+        out[p] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 2)
+graph_kernel_tc(GraphArgs a) {
+    extern __shared__ __align__(16) unsigned char tc_smem_dyn[];
+    unsigned char *smem = tc_smem_dyn + ((1024u - (gemm::smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
+    float *g = reinterpret_cast<float *>(smem + kTcG);                 // [64][68]
+    float *sq = g + kMaxNodes * kGLd;                                  // [64]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sq + kMaxNodes);     // mma_done[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+    const uint32_t ring = gemm::smem_u32(smem), gplanes = ring + kTcGPlanes, bar0 = gemm::smem_u32(bars);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.V, C = a.C, b = blockIdx.x;
+    const float *x = a.x + static_cast<size_t>(b) * V * C;
+
+    if (tid == 0) { gemm::mbar_init(bar0, 1); gemm::mbar_init(bar0 + 8, 1); gemm::fence_barrier_init(); }
+    if (warp == 0) { gemm::tmem_alloc(gemm::smem_u32(tmem_slot), 128); gemm::tmem_relinquish(); }
+    for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
+    gemm::tc_fence_before();
+    __syncthreads();
+    gemm::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // epilogue threads: the warps that may read TMEM lanes 0..63 (warp % 4 in {0, 1}); row = node
+    const bool epi_warp = (warp & 3) < 2;
+    const int erow = (warp & 3) * 32 + lane, ehalf = warp >> 2;
+    const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    int uses0 = 0, uses1 = 0;                                          // completed-or-pending MMA batches per barrier
+    auto wait_use = [&](int buf, int use) { gemm::mbar_wait(bar0 + 8 * buf, static_cast<uint32_t>(use & 1)); };
+    constexpr uint32_t idesc = gemm::make_idesc(128, 64);
+    const int n_blocks = C / 64;
+
+    if (a.learn_graph) {
+        // ================= Gram =================
+        // item = (row, 8-channel slot): 64 rows x 8 slots, two items per thread; next block's loads in flight
+        float nxt[2][8];
+        auto load_block = [&](int kb) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
+                if (row < V) {
+                    const float4 *src = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * C + kb * 64 + slot * 8);
+                    const float4 lo = __ldg(src), hi = __ldg(src + 1);
+                    nxt[t][0] = lo.x; nxt[t][1] = lo.y; nxt[t][2] = lo.z; nxt[t][3] = lo.w;
+                    nxt[t][4] = hi.x; nxt[t][5] = hi.y; nxt[t][6] = hi.z; nxt[t][7] = hi.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) nxt[t][i] = 0.f;
+                }
+            }
+        };
+        load_block(0);
+        for (int kb = 0; kb < n_blocks; ++kb) {
+            const int buf = kb & 1;
+            if (kb >= 2) wait_use(buf, (kb >> 1) - 1);                 // the MMAs that read this buffer have retired
+            unsigned char *dst = smem + buf * 3 * kTcPlane;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
+                uint4 pl[3];
+                split8<3>(nxt[t], pl);
+                const int off = row * 128 + ((slot ^ (row & 7)) << 4);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) *reinterpret_cast<uint4 *>(dst + p * kTcPlane + off) = pl[p];
+            }
+            if (kb + 1 < n_blocks) load_block(kb + 1);
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                gemm::tc_fence_after();
+                const uint32_t base = ring + buf * 3 * kTcPlane;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    int pa, pb;
+                    gemm::pair_of(3, i, pa, pb);
+                    const uint64_t da = gemm::make_smem_desc(base + pa * kTcPlane), db = gemm::make_smem_desc(base + pb * kTcPlane);
+                    const bool main_acc = (i == 5);                    // a0.b0 alone in columns 0..63, corrections in 64..127
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        gemm::tc_mma_bf16(tmem + (main_acc ? 0 : 64), da + 2 * k, db + 2 * k, idesc,
+                                          main_acc ? ((kb | k) != 0) : ((kb | i | k) != 0));
+                }
+                gemm::tc_commit(bar0 + 8 * buf);
+            }
+            if (buf == 0) ++uses0; else ++uses1;
+        }
+        // every MMA has retired once the last commit of each barrier has fired
+        if (uses0 > 0) wait_use(0, uses0 - 1);
+        if (uses1 > 0) wait_use(1, uses1 - 1);
+        gemm::tc_fence_after();
+        if (epi_warp) {
+            uint32_t m[32], c[32];
+            gemm::tmem_ld_32x32(tlane + ehalf * 32, m);
+            gemm::tmem_ld_32x32(tlane + 64 + ehalf * 32, c);
+            gemm::tmem_ld_wait();
+            if (erow < V) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    g[erow * kGLd + ehalf * 32 + j] = __fadd_rn(__uint_as_float(m[j]), __uint_as_float(c[j]));
+            }
+        }
+        gemm::tc_fence_before();
+        __syncthreads();
+        if (tid < V) sq[tid] = g[tid * kGLd + tid];
+        __syncthreads();
+        for (int i = tid; i < V * V; i += kHeadThreads) {               // affinity (vmgn.py:116-120)
+            const int r = i / V, c = i % V;
+            float d2 = __fadd_rn(sq[c], sq[r]);
+            d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
+            const float d = sqrtf(fmaxf(d2, 1e-12f));
+            g[r * kGLd + c] = __fdiv_rn(2.0f, expf(d) + 1.0f);
+        }
+        __syncthreads();
+    }
+    // ---- L1 row normalisation + mixing: one warp per row (as graph_kernel) ----
+    const PoseGraph pose(a, b);
+    for (int r = warp; r < V; r += kHeadThreads / 32) {
+        float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
+        const int c1 = lane + 32;
+        if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
+        if (a.use_pose) { a0 = (lane < V) ? pose.at(r, lane) : 0.f; a1 = (c1 < V) ? pose.at(r, c1) : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
+        rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);
+        float m0, m1;
+        if (a.learn_graph && a.use_pose) {
+            m0 = __fdiv_rn(__fdiv_rn(a0, ra) + __fdiv_rn(s0, rs), 2.0f);
+            m1 = __fdiv_rn(__fdiv_rn(a1, ra) + __fdiv_rn(s1, rs), 2.0f);
+        } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
+        else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
+        __syncwarp();
+        g[r * kGLd + lane] = (lane < V) ? m0 : 0.f;
+        g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
+    }
+    __syncthreads();
+    float y_scale = 1.0f;
+    if (a.fp16) {                                                      // see graph_kernel
+        __shared__ float s_scale[2];
+        if (!a.learn_graph) {
+            for (int r = warp; r < V; r += kHeadThreads / 32) {
+                const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
+                float t = 0.f;
+                for (int i = lane; i < C / 4; i += 32) {
+                    const float4 v = __ldg(row + i);
+                    t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+                }
+                t = warp_sum(t);
+                if (lane == 0) sq[r] = t;
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            float m = fmaxf(lane < V ? sq[lane] : 0.f, lane + 32 < V ? sq[lane + 32] : 0.f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) {
+                m = (m < 3.0e38f) ? sqrtf(m) : 0.f;
+                pow2_scales(m, &s_scale[0], &s_scale[1]);
+                a.y_unscale[b] = s_scale[1];
+            }
+        }
+        __syncthreads();
+        y_scale = s_scale[0];
+    }
+    // ---- G as two bf16 planes, K-major [row = output node][k = input node] ----
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (row < V) ? g[row * kGLd + slot * 8 + i] : 0.f;    // columns >= V hold zeros
+        uint4 pl[2];
+        split8<2>(v, pl);
+        const int off = row * 128 + ((slot ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4 *>(smem + kTcGPlanes + off) = pl[0];
+        *reinterpret_cast<uint4 *>(smem + kTcGPlanes + kTcPlane + off) = pl[1];
+    }
+    // ================= Y = G . X, 64 channels per block =================
+    // item = (channel, 8-node group): lane = channel -> every load instruction is one coalesced 128-byte row piece
+    float nx[2][8];
+    auto load_yblock = [&](int cb) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int item = tid + kHeadThreads * t, ch = item & 63, grp = item >> 6;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int v = grp * 8 + i;
+                nx[t][i] = (v < V) ? __ldg(x + static_cast<size_t>(v) * C + cb * 64 + ch) : 0.f;
+            }
+        }
+    };
+    auto y_epilogue = [&](int cb) {                                   // block cb: accumulator cb & 1 -> planes -> global
+        const int acc = cb & 1;
+        wait_use(acc, (acc == 0 ? uses0 : uses1) - 1);
+        gemm::tc_fence_after();
+        uint32_t r[32];
+        gemm::tmem_ld_32x32(tlane + acc * 64 + ehalf * 32, r);
+        gemm::tmem_ld_wait();
+        if (erow < V) {
+            __nv_bfloat16 *dst = a.y_planes + (static_cast<size_t>(b) * V + erow) * C + cb * 64 + ehalf * 32;
+            if (a.fp16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __half2 h = __floats2half2_rn(__uint_as_float(r[8 * q + 2 * i]) * y_scale,
+                                                            __uint_as_float(r[8 * q + 2 * i + 1]) * y_scale);
+                        w[i] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    reinterpret_cast<uint4 *>(dst)[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * q + i]);
+                    if (a.P == 3) {
+                        uint4 pl[3];
+                        split8<3>(v, pl);
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) reinterpret_cast<uint4 *>(dst + p * a.plane_stride)[q] = pl[p];
+                    } else {
+                        uint4 pl[2];
+                        split8<2>(v, pl);
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) reinterpret_cast<uint4 *>(dst + p * a.plane_stride)[q] = pl[p];
+                    }
+                }
+            }
+        }
+        gemm::tc_fence_before();
+    };
+    load_yblock(0);
+    for (int cb = 0; cb < n_blocks; ++cb) {
+        const int buf = cb & 1;
+        const int used = (buf == 0 ? uses0 : uses1);
+        if (used > 0) wait_use(buf, used - 1);                         // operand buffer `buf` (and, for cb >= 2, its accumulator) is free
+        unsigned char *dst = smem + buf * 2 * kTcPlane;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int item = tid + kHeadThreads * t, ch = item & 63, grp = item >> 6;
+            uint4 pl[2];
+            split8<2>(nx[t], pl);
+            const int off = ch * 128 + ((grp ^ (ch & 7)) << 4);
+            *reinterpret_cast<uint4 *>(dst + off) = pl[0];
+            *reinterpret_cast<uint4 *>(dst + kTcPlane + off) = pl[1];
+        }
+        if (cb + 1 < n_blocks) load_yblock(cb + 1);
+        fence_proxy_async_smem();
+        __syncthreads();                                               // also: the epilogue of block cb - 2 has left accumulator `buf`
+        if (tid == 0) {
+            gemm::tc_fence_after();
+            const uint32_t bbase = ring + buf * 2 * kTcPlane;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                int pa, pb;
+                gemm::pair_of(2, i, pa, pb);
+                const uint64_t da = gemm::make_smem_desc(gplanes + pa * kTcPlane), db = gemm::make_smem_desc(bbase + pb * kTcPlane);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) gemm::tc_mma_bf16(tmem + buf * 64, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
+            }
+            gemm::tc_commit(bar0 + 8 * buf);
+        }
+        if (buf == 0) ++uses0; else ++uses1;
+        if (cb >= 1 && epi_warp) y_epilogue(cb - 1);
+    }
+    if (epi_warp) y_epilogue(n_blocks - 1);
+    gemm::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) gemm::tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
 // temporal attention + part mean + BN neck: one CTA per tracklet
 // ------------------------------------------------------------------------------------------------
 struct AttnArgs {
@@ -994,6 +1306,7 @@ static int launch_graph_variant(const GraphArgs &ga, int64_t batch, cudaStream_t
 //   0 = double, 128 (2/SM)   1 = single, 80 (3/SM)   2 = single, 128 (2/SM)   3 = double, 80
 //   4 = double, 112 and 5 = single, 112: two CTAs per SM NEXT TO a resident pooling CTA (48 regs x 160 threads)
 //   6 / 7 = graph_kernel_v2 (8x8 Gram tiles, 14x4 message-passing tiles) with 128 / 112 registers
+//   8 = graph_kernel_tc (both products on tcgen05, operands converted in shared memory)
 static int graph_variant() { return static_cast<int>(option(kOptGraphVariant)); }
 
 template <int kMaxRegs>
@@ -1009,6 +1322,12 @@ static int launch_graph_v2(const GraphArgs &ga, int64_t batch, cudaStream_t st) 
 template <int NT>
 static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
     const bool v2_ok = ga.V <= kV2Rows && ga.C % (2 * kChunk) == 0;
+    if (graph_variant() == 8 && ga.V <= kMaxNodes && ga.C % 64 == 0) {
+        AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+        graph_kernel_tc<<<static_cast<unsigned>(batch), kHeadThreads, kTcSmem, st>>>(ga);
+        AGRL_LAUNCH_CHECK(st, "graph");
+        return AGRL_OK;
+    }
     if (v2_ok && graph_variant() == 6) return launch_graph_v2<128>(ga, batch, st);
     if (v2_ok && graph_variant() == 7) return launch_graph_v2<112>(ga, batch, st);
     switch (graph_variant()) {

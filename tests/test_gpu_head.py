@@ -197,7 +197,7 @@ def test_pipeline_modes_agree(restore_options):
     emax, _ = rel_err(outs[(1, 0, 2)], outs[(0, 0, 4)])
     assert emax < 2e-6
     lib.set_option('head_sub_batch', 4)
-    for variant in range(8):
+    for variant in range(9):
         lib.set_option('graph_variant', variant)
         with torch.no_grad():
             out = model.head(x1, x2, adj, S)
