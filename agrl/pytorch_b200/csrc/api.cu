@@ -69,7 +69,7 @@ static const OptionDef kOptionDefs[kOptCount] = {
     {"pool_tma", "AGRL_POOL_TMA", 1, 0, 1},
     {"pool_stages", "AGRL_POOL_STAGES", 4, 2, 12},            // 16 KiB ring stages per pooling CTA
     {"pool_ctas_per_sm", "AGRL_POOL_CTAS", 1, 1, 4},
-    {"graph_variant", "AGRL_GRAPH_VARIANT", 6, 0, 8},
+    {"graph_variant", "AGRL_GRAPH_VARIANT", 8, 0, 8},
     {"pool_l2_hint", "AGRL_POOL_HINT", 1, 0, 1},              // evict-first hint on the pooling bulk copies
     // sub-batched pipeline: 0 = poolings free-run on the side stream; 1 = pooling of sub-batch i+1 is cut into
     // pieces that run only under the graph / attention kernels of sub-batch i (the GEMMs wait for their piece)

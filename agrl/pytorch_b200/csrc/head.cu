@@ -897,17 +897,24 @@ graph_kernel_v2(GraphArgs a) {
 //          6 plane products, M = 128 (rows 64.. are don't-care), N = 64, accumulated over all blocks in TMEM with the
 //          dominant product in its own accumulator (as the distance GEMM does).
 //   G      affinity, L1 rows, pose mixing on CUDA cores exactly as in graph_kernel; then G as two bf16 planes.
-//   Y      per 64-channel block the TRANSPOSED tile [channel][node] (K = nodes) as two bf16 planes; D = G.X^T block,
-//          3 plane products (same 16-bit operand class as the planes Y is rounded to anyway), double-buffered
-//          accumulator so the epilogue of block i-1 (TMEM -> planes -> global) runs under the MMAs of block i.
-// One CTA per tracklet, 256 threads, 2-3 CTAs per SM (74 KiB smem, 128 TMEM columns each).
+//   Y      per 128-channel block the TRANSPOSED tile [channel][node] (K = nodes) as two bf16 planes; D = G.X^T block,
+//          3 plane products (same 16-bit operand class as the planes Y is rounded to anyway), 128 x 128 x 16 MMAs,
+//          double-buffered accumulator.
+//   roles  13 warps: 0..11 workers, 12 issues the MMAs.  Gram: workers 0..7 convert.  Y: workers 2,3,6..11 convert,
+//          workers 0,1,4,5 (the ones that may read TMEM lanes 0..63) drain accumulators into operand planes.  Inside a
+//          phase the roles are coupled by mbarriers only (operands ready / MMAs retired / accumulator drained).
+// Measured: an MMA costs ~128 cycles of A-operand fetch whatever N is, so the small Gram MMAs are no bargain per flop --
+// but they run beside the conversions instead of on the FMA pipe, and the kernel is 25 % faster than graph_kernel_v2.
+// One CTA per tracklet, 416 threads, 2 CTAs per SM (81 KiB smem, 256 TMEM columns each).
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcPlane = 64 * 128;                     // one operand plane: 64 rows x 128 B
-constexpr int kTcRing = 6 * kTcPlane;                  // Gram: 2 buffers x 3 planes; Y: 2 buffers x 2 planes
-constexpr int kTcSlack = kTcPlane;                     // rows 64..127 of the last plane's 128-row descriptor land here
-constexpr int kTcGPlanes = kTcRing + kTcSlack;         // two G planes, followed by g[] (their 128-row tail)
-constexpr int kTcG = kTcGPlanes + 2 * kTcPlane;
-constexpr int kTcSmem = kTcG + (kMaxNodes * kGLd + kMaxNodes) * 4 + 64 + 1024;
+constexpr int kTcPlane = 64 * 128;                     // 8 KiB: 64 rows x 128 B
+constexpr int kTcGPlanes = 0;                          // two G planes; the 128-row A descriptor of plane 1 runs into the ring
+constexpr int kTcRingOff = 2 * kTcPlane;               // Gram: 2 buffers x 3 planes x 8 KiB (+ the last plane's 128-row tail);
+constexpr int kTcRingBytes = 8 * kTcPlane;             // Y: 2 buffers x 2 planes x 16 KiB; in between: g[64][68], sq[64]
+constexpr int kTcBars = kTcRingOff + kTcRingBytes;
+constexpr int kTcSmem = kTcBars + 128 + 1024;
+constexpr int kTcThreads = 416;
+static_assert((kMaxNodes * kGLd + kMaxNodes) * 4 <= kTcRingBytes, "g[] fits the ring");
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -931,72 +938,116 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 (&out)[P]) {
     }
 }
 
-__global__ void __launch_bounds__(kHeadThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, 2)
 graph_kernel_tc(GraphArgs a) {
     extern __shared__ __align__(16) unsigned char tc_smem_dyn[];
     unsigned char *smem = tc_smem_dyn + ((1024u - (gemm::smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
-    float *g = reinterpret_cast<float *>(smem + kTcG);                 // [64][68]
+    unsigned char *ring_p = smem + kTcRingOff;
+    float *g = reinterpret_cast<float *>(ring_p);                      // [64][68], between the two MMA phases
     float *sq = g + kMaxNodes * kGLd;                                  // [64]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sq + kMaxNodes);     // mma_done[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
-    const uint32_t ring = gemm::smem_u32(smem), gplanes = ring + kTcGPlanes, bar0 = gemm::smem_u32(bars);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcBars);     // done[2], gfull[2], yfull[2], accfree[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    const uint32_t gplanes = gemm::smem_u32(smem) + kTcGPlanes, ring = gemm::smem_u32(ring_p), bar0 = gemm::smem_u32(bars);
+    const uint32_t b_done = bar0, b_gfull = bar0 + 16, b_yfull = bar0 + 32, b_accfree = bar0 + 48;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool worker = warp < 12, issuer = warp == 12, gram_worker = warp < 8;
     const int V = a.V, C = a.C, b = blockIdx.x;
     const float *x = a.x + static_cast<size_t>(b) * V * C;
 
-    if (tid == 0) { gemm::mbar_init(bar0, 1); gemm::mbar_init(bar0 + 8, 1); gemm::fence_barrier_init(); }
-    if (warp == 0) { gemm::tmem_alloc(gemm::smem_u32(tmem_slot), 128); gemm::tmem_relinquish(); }
-    for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            gemm::mbar_init(b_done + 8 * i, 1); gemm::mbar_init(b_gfull + 8 * i, 8);
+            gemm::mbar_init(b_yfull + 8 * i, 8); gemm::mbar_init(b_accfree + 8 * i, 4);
+        }
+        gemm::fence_barrier_init();
+    }
+    if (warp == 0) { gemm::tmem_alloc(gemm::smem_u32(tmem_slot), 256); gemm::tmem_relinquish(); }
+    if (!a.learn_graph && gram_worker) for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
     gemm::tc_fence_before();
     __syncthreads();
     gemm::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // epilogue threads: the warps that may read TMEM lanes 0..63 (warp % 4 in {0, 1}); row = node
-    const bool epi_warp = (warp & 3) < 2;
+    const bool epi_warp = gram_worker && (warp & 3) < 2;               // warps 0,1,4,5 may read TMEM lanes 0..63; row = node
     const int erow = (warp & 3) * 32 + lane, ehalf = warp >> 2;
     const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    int uses0 = 0, uses1 = 0;                                          // completed-or-pending MMA batches per barrier
-    auto wait_use = [&](int buf, int use) { gemm::mbar_wait(bar0 + 8 * buf, static_cast<uint32_t>(use & 1)); };
-    constexpr uint32_t idesc = gemm::make_idesc(128, 64);
-    const int n_blocks = C / 64;
+    auto wait_bar = [&](uint32_t bar, int use) { gemm::mbar_wait(bar, static_cast<uint32_t>(use & 1)); };
+    const int n_gblocks = C / 64;                                      // even (C % 128 == 0)
+    const int g_uses = a.learn_graph ? n_gblocks / 2 : 0;              // commits on each done[] barrier by the Gram phase
 
     if (a.learn_graph) {
         // ================= Gram =================
-        // item = (row, 8-channel slot): 64 rows x 8 slots, two items per thread; next block's loads in flight
-        float nxt[2][8];
-        auto load_block = [&](int kb) {
+        if (gram_worker) {
+            // item = (row, 8-channel slot): 64 rows x 8 slots, two items per thread; blocks kb and kb + 1 in flight
+            float nxt[2][8], nx2[2][8];
+            auto load_block = [&](int kb, float (&dstv)[2][8]) {
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
-                if (row < V) {
-                    const float4 *src = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * C + kb * 64 + slot * 8);
-                    const float4 lo = __ldg(src), hi = __ldg(src + 1);
-                    nxt[t][0] = lo.x; nxt[t][1] = lo.y; nxt[t][2] = lo.z; nxt[t][3] = lo.w;
-                    nxt[t][4] = hi.x; nxt[t][5] = hi.y; nxt[t][6] = hi.z; nxt[t][7] = hi.w;
-                } else {
+                for (int t = 0; t < 2; ++t) {
+                    const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
+                    if (row < V) {
+                        const float4 *src = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * C + kb * 64 + slot * 8);
+                        const float4 lo = __ldg(src), hi = __ldg(src + 1);
+                        dstv[t][0] = lo.x; dstv[t][1] = lo.y; dstv[t][2] = lo.z; dstv[t][3] = lo.w;
+                        dstv[t][4] = hi.x; dstv[t][5] = hi.y; dstv[t][6] = hi.z; dstv[t][7] = hi.w;
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) nxt[t][i] = 0.f;
+                        for (int i = 0; i < 8; ++i) dstv[t][i] = 0.f;
+                    }
                 }
-            }
-        };
-        load_block(0);
-        for (int kb = 0; kb < n_blocks; ++kb) {
-            const int buf = kb & 1;
-            if (kb >= 2) wait_use(buf, (kb >> 1) - 1);                 // the MMAs that read this buffer have retired
-            unsigned char *dst = smem + buf * 3 * kTcPlane;
+            };
+            auto prefetch_block = [&](int kb) {                         // DRAM -> L2 a few blocks ahead
+                if (kb < n_gblocks && (tid & 3) == 0) {
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
-                uint4 pl[3];
-                split8<3>(nxt[t], pl);
-                const int off = row * 128 + ((slot ^ (row & 7)) << 4);
+                    for (int t = 0; t < 2; ++t) {
+                        const int row = (tid >> 3) + 32 * t;
+                        if (row < V) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + static_cast<size_t>(row) * C + kb * 64 + (tid & 4) * 8));
+                    }
+                }
+            };
+            prefetch_block(2); prefetch_block(3); prefetch_block(4); prefetch_block(5);
+            load_block(0, nxt);
+            load_block(1, nx2);
+            auto gram_step = [&](int kb, float (&cur)[2][8]) {          // convert block kb (in `cur`), refill `cur` with kb + 2
+                const int buf = kb & 1;
+                prefetch_block(kb + 6);
+                if (kb >= 2) wait_bar(b_done + 8 * buf, (kb >> 1) - 1);  // the MMAs that read this buffer have retired
+                unsigned char *dst = ring_p + buf * 3 * kTcPlane;
 #pragma unroll
-                for (int p = 0; p < 3; ++p) *reinterpret_cast<uint4 *>(dst + p * kTcPlane + off) = pl[p];
+                for (int t = 0; t < 2; ++t) {
+                    const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
+                    uint4 pl[3];
+                    split8<3>(cur[t], pl);
+                    const int off = row * 128 + ((slot ^ (row & 7)) << 4);
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) *reinterpret_cast<uint4 *>(dst + p * kTcPlane + off) = pl[p];
+                }
+                if (kb + 2 < n_gblocks) load_block(kb + 2, cur);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) gemm::mbar_arrive(b_gfull + 8 * buf);
+            };
+            for (int kb = 0; kb < n_gblocks; kb += 2) {
+                gram_step(kb, nxt);
+                gram_step(kb + 1, nx2);
             }
-            if (kb + 1 < n_blocks) load_block(kb + 1);
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) {
+            wait_bar(b_done, g_uses - 1);                              // every Gram MMA has retired
+            wait_bar(b_done + 8, g_uses - 1);
+            gemm::tc_fence_after();
+            if (epi_warp) {
+                uint32_t m[32], c[32];
+                gemm::tmem_ld_32x32(tlane + ehalf * 32, m);
+                gemm::tmem_ld_32x32(tlane + 64 + ehalf * 32, c);
+                gemm::tmem_ld_wait();
+                // (all 64 x 64 entries: rows / columns >= V are products of zero rows, i.e. zeros)
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    g[erow * kGLd + ehalf * 32 + j] = __fadd_rn(__uint_as_float(m[j]), __uint_as_float(c[j]));
+            }
+            gemm::tc_fence_before();
+        } else if (issuer && lane == 0) {
+            constexpr uint32_t idesc = gemm::make_idesc(128, 64);
+            for (int kb = 0; kb < n_gblocks; ++kb) {
+                const int buf = kb & 1;
+                wait_bar(b_gfull + 8 * buf, kb >> 1);
                 gemm::tc_fence_after();
                 const uint32_t base = ring + buf * 3 * kTcPlane;
 #pragma unroll
@@ -1010,70 +1061,59 @@ graph_kernel_tc(GraphArgs a) {
                         gemm::tc_mma_bf16(tmem + (main_acc ? 0 : 64), da + 2 * k, db + 2 * k, idesc,
                                           main_acc ? ((kb | k) != 0) : ((kb | i | k) != 0));
                 }
-                gemm::tc_commit(bar0 + 8 * buf);
-            }
-            if (buf == 0) ++uses0; else ++uses1;
-        }
-        // every MMA has retired once the last commit of each barrier has fired
-        if (uses0 > 0) wait_use(0, uses0 - 1);
-        if (uses1 > 0) wait_use(1, uses1 - 1);
-        gemm::tc_fence_after();
-        if (epi_warp) {
-            uint32_t m[32], c[32];
-            gemm::tmem_ld_32x32(tlane + ehalf * 32, m);
-            gemm::tmem_ld_32x32(tlane + 64 + ehalf * 32, c);
-            gemm::tmem_ld_wait();
-            if (erow < V) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    g[erow * kGLd + ehalf * 32 + j] = __fadd_rn(__uint_as_float(m[j]), __uint_as_float(c[j]));
+                gemm::tc_commit(b_done + 8 * buf);
             }
         }
-        gemm::tc_fence_before();
         __syncthreads();
-        if (tid < V) sq[tid] = g[tid * kGLd + tid];
+        if (gram_worker && tid < V) sq[tid] = g[tid * kGLd + tid];
         __syncthreads();
-        for (int i = tid; i < V * V; i += kHeadThreads) {               // affinity (vmgn.py:116-120)
-            const int r = i / V, c = i % V;
-            float d2 = __fadd_rn(sq[c], sq[r]);
-            d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
-            const float d = sqrtf(fmaxf(d2, 1e-12f));
-            g[r * kGLd + c] = __fdiv_rn(2.0f, expf(d) + 1.0f);
+        if (gram_worker) {
+            for (int i = tid; i < V * V; i += kHeadThreads) {           // affinity (vmgn.py:116-120)
+                const int r = i / V, c = i % V;
+                float d2 = __fadd_rn(sq[c], sq[r]);
+                d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
+                const float d = sqrtf(fmaxf(d2, 1e-12f));
+                g[r * kGLd + c] = __fdiv_rn(2.0f, expf(d) + 1.0f);
+            }
         }
         __syncthreads();
     }
-    // ---- L1 row normalisation + mixing: one warp per row (as graph_kernel) ----
-    const PoseGraph pose(a, b);
-    for (int r = warp; r < V; r += kHeadThreads / 32) {
-        float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
-        const int c1 = lane + 32;
-        if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
-        if (a.use_pose) { a0 = (lane < V) ? pose.at(r, lane) : 0.f; a1 = (c1 < V) ? pose.at(r, c1) : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
-        rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);
-        float m0, m1;
-        if (a.learn_graph && a.use_pose) {
-            m0 = __fdiv_rn(__fdiv_rn(a0, ra) + __fdiv_rn(s0, rs), 2.0f);
-            m1 = __fdiv_rn(__fdiv_rn(a1, ra) + __fdiv_rn(s1, rs), 2.0f);
-        } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
-        else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
-        __syncwarp();
-        g[r * kGLd + lane] = (lane < V) ? m0 : 0.f;
-        g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
+    // ---- L1 row normalisation + mixing: one worker warp per row (as graph_kernel) ----
+    if (worker) {
+        const PoseGraph pose(a, b);
+        for (int r = warp; r < V; r += 12) {
+            float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
+            const int c1 = lane + 32;
+            if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
+            if (a.use_pose) { a0 = (lane < V) ? pose.at(r, lane) : 0.f; a1 = (c1 < V) ? pose.at(r, c1) : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
+            rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);
+            float m0, m1;
+            if (a.learn_graph && a.use_pose) {
+                m0 = __fdiv_rn(__fdiv_rn(a0, ra) + __fdiv_rn(s0, rs), 2.0f);
+                m1 = __fdiv_rn(__fdiv_rn(a1, ra) + __fdiv_rn(s1, rs), 2.0f);
+            } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
+            else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
+            __syncwarp();
+            g[r * kGLd + lane] = (lane < V) ? m0 : 0.f;
+            g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
+        }
     }
     __syncthreads();
+    __shared__ float s_scale[2];
     float y_scale = 1.0f;
     if (a.fp16) {                                                      // see graph_kernel
-        __shared__ float s_scale[2];
         if (!a.learn_graph) {
-            for (int r = warp; r < V; r += kHeadThreads / 32) {
-                const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
-                float t = 0.f;
-                for (int i = lane; i < C / 4; i += 32) {
-                    const float4 v = __ldg(row + i);
-                    t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+            if (worker) {
+                for (int r = warp; r < V; r += 12) {
+                    const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
+                    float t = 0.f;
+                    for (int i = lane; i < C / 4; i += 32) {
+                        const float4 v = __ldg(row + i);
+                        t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+                    }
+                    t = warp_sum(t);
+                    if (lane == 0) sq[r] = t;
                 }
-                t = warp_sum(t);
-                if (lane == 0) sq[r] = t;
             }
             __syncthreads();
         }
@@ -1091,113 +1131,145 @@ graph_kernel_tc(GraphArgs a) {
         y_scale = s_scale[0];
     }
     // ---- G as two bf16 planes, K-major [row = output node][k = input node] ----
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (row < V) ? g[row * kGLd + slot * 8 + i] : 0.f;    // columns >= V hold zeros
-        uint4 pl[2];
-        split8<2>(v, pl);
-        const int off = row * 128 + ((slot ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4 *>(smem + kTcGPlanes + off) = pl[0];
-        *reinterpret_cast<uint4 *>(smem + kTcGPlanes + kTcPlane + off) = pl[1];
-    }
-    // ================= Y = G . X, 64 channels per block =================
-    // item = (channel, 8-node group): lane = channel -> every load instruction is one coalesced 128-byte row piece
-    float nx[2][8];
-    auto load_yblock = [&](int cb) {
+    if (gram_worker) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-            const int item = tid + kHeadThreads * t, ch = item & 63, grp = item >> 6;
+            const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
+            float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int v = grp * 8 + i;
-                nx[t][i] = (v < V) ? __ldg(x + static_cast<size_t>(v) * C + cb * 64 + ch) : 0.f;
-            }
-        }
-    };
-    auto y_epilogue = [&](int cb) {                                   // block cb: accumulator cb & 1 -> planes -> global
-        const int acc = cb & 1;
-        wait_use(acc, (acc == 0 ? uses0 : uses1) - 1);
-        gemm::tc_fence_after();
-        uint32_t r[32];
-        gemm::tmem_ld_32x32(tlane + acc * 64 + ehalf * 32, r);
-        gemm::tmem_ld_wait();
-        if (erow < V) {
-            __nv_bfloat16 *dst = a.y_planes + (static_cast<size_t>(b) * V + erow) * C + cb * 64 + ehalf * 32;
-            if (a.fp16) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const __half2 h = __floats2half2_rn(__uint_as_float(r[8 * q + 2 * i]) * y_scale,
-                                                            __uint_as_float(r[8 * q + 2 * i + 1]) * y_scale);
-                        w[i] = *reinterpret_cast<const uint32_t *>(&h);
-                    }
-                    reinterpret_cast<uint4 *>(dst)[q] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * q + i]);
-                    if (a.P == 3) {
-                        uint4 pl[3];
-                        split8<3>(v, pl);
-#pragma unroll
-                        for (int p = 0; p < 3; ++p) reinterpret_cast<uint4 *>(dst + p * a.plane_stride)[q] = pl[p];
-                    } else {
-                        uint4 pl[2];
-                        split8<2>(v, pl);
-#pragma unroll
-                        for (int p = 0; p < 2; ++p) reinterpret_cast<uint4 *>(dst + p * a.plane_stride)[q] = pl[p];
-                    }
-                }
-            }
-        }
-        gemm::tc_fence_before();
-    };
-    load_yblock(0);
-    for (int cb = 0; cb < n_blocks; ++cb) {
-        const int buf = cb & 1;
-        const int used = (buf == 0 ? uses0 : uses1);
-        if (used > 0) wait_use(buf, used - 1);                         // operand buffer `buf` (and, for cb >= 2, its accumulator) is free
-        unsigned char *dst = smem + buf * 2 * kTcPlane;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int item = tid + kHeadThreads * t, ch = item & 63, grp = item >> 6;
+            for (int i = 0; i < 8; ++i) v[i] = (row < V) ? g[row * kGLd + slot * 8 + i] : 0.f;    // columns >= V hold zeros
             uint4 pl[2];
-            split8<2>(nx[t], pl);
-            const int off = ch * 128 + ((grp ^ (ch & 7)) << 4);
-            *reinterpret_cast<uint4 *>(dst + off) = pl[0];
-            *reinterpret_cast<uint4 *>(dst + kTcPlane + off) = pl[1];
+            split8<2>(v, pl);
+            const int off = row * 128 + ((slot ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4 *>(smem + kTcGPlanes + off) = pl[0];
+            *reinterpret_cast<uint4 *>(smem + kTcGPlanes + kTcPlane + off) = pl[1];
         }
-        if (cb + 1 < n_blocks) load_yblock(cb + 1);
         fence_proxy_async_smem();
-        __syncthreads();                                               // also: the epilogue of block cb - 2 has left accumulator `buf`
-        if (tid == 0) {
-            gemm::tc_fence_after();
-            const uint32_t bbase = ring + buf * 2 * kTcPlane;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                int pa, pb;
-                gemm::pair_of(2, i, pa, pb);
-                const uint64_t da = gemm::make_smem_desc(gplanes + pa * kTcPlane), db = gemm::make_smem_desc(bbase + pb * kTcPlane);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) gemm::tc_mma_bf16(tmem + buf * 64, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
-            }
-            gemm::tc_commit(bar0 + 8 * buf);
-        }
-        if (buf == 0) ++uses0; else ++uses1;
-        if (cb >= 1 && epi_warp) y_epilogue(cb - 1);
     }
-    if (epi_warp) y_epilogue(n_blocks - 1);
+    __syncthreads();                                                   // g[] (in the ring) is dead from here on
+
+    // ================= Y = G . X, 128 channels per block =================
+    const int n_blocks = C / 128;
+    if (issuer) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = gemm::make_idesc(128, 128);
+            for (int cb = 0; cb < n_blocks; ++cb) {
+                const int buf = cb & 1;
+                wait_bar(b_yfull + 8 * buf, cb >> 1);
+                if (cb >= 2) wait_bar(b_accfree + 8 * buf, (cb >> 1) - 1);   // the epilogue has drained this accumulator
+                gemm::tc_fence_after();
+                const uint32_t bbase = ring + buf * 4 * kTcPlane;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    int pa, pb;
+                    gemm::pair_of(2, i, pa, pb);
+                    const uint64_t da = gemm::make_smem_desc(gplanes + pa * kTcPlane), db = gemm::make_smem_desc(bbase + pb * 2 * kTcPlane);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) gemm::tc_mma_bf16(tmem + buf * 128, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
+                }
+                gemm::tc_commit(b_done + 8 * buf);
+            }
+        }
+    } else if (!epi_warp) {
+        // converters (workers 2,3,6..11 -> 256 threads), 64 channels at a time: item = (channel, 8-node group), lane =
+        // channel, so every load instruction is one coalesced 128-byte piece of a node row; two items per thread, the
+        // next 64 channels in flight; two such halves fill one operand buffer
+        const int cw = warp < 8 ? ((warp >> 2) * 2 + (warp & 1)) : warp - 4;   // 0..7
+        const int ctid = cw * 32 + lane, ch = ctid & 63, g0 = ctid >> 6, n_halves = 2 * n_blocks;
+        float nx[2][8];
+        auto load_half = [&](int hh) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int v = (g0 + 4 * t) * 8 + i;
+                    nx[t][i] = (v < V) ? __ldg(x + static_cast<size_t>(v) * C + hh * 64 + ch) : 0.f;
+                }
+            }
+        };
+        auto prefetch_half = [&](int hh) {                              // DRAM -> L2 ahead: one 128-byte line per thread
+            const int row = ctid & 63;
+            if (ctid < 128 && hh < n_halves && row < V)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(x + static_cast<size_t>(row) * C + hh * 64 + (ctid >> 6) * 32));
+        };
+        for (int hh = 1; hh < 6; ++hh) prefetch_half(hh);
+        load_half(0);
+        for (int hh = 0; hh < n_halves; ++hh) {
+            prefetch_half(hh + 6);
+            const int cb = hh >> 1, buf = cb & 1, prev = g_uses + (cb >> 1) - 1;
+            if ((hh & 1) == 0 && prev >= 0) wait_bar(b_done + 8 * buf, prev);   // the MMAs that read this buffer have retired
+            unsigned char *dst = ring_p + buf * 4 * kTcPlane;
+            const int row = (hh & 1) * 64 + ch;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                uint4 pl[2];
+                split8<2>(nx[t], pl);
+                const int off = row * 128 + (((g0 + 4 * t) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4 *>(dst + off) = pl[0];
+                *reinterpret_cast<uint4 *>(dst + 2 * kTcPlane + off) = pl[1];
+            }
+            if (hh + 1 < n_halves) load_half(hh + 1);
+            if (hh & 1) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) gemm::mbar_arrive(b_yfull + 8 * buf);
+            }
+        }
+    } else {
+        // epilogue (workers 0,1,4,5): accumulator -> registers (frees it for block cb + 2) -> planes -> global
+        for (int cb = 0; cb < n_blocks; ++cb) {
+            const int acc = cb & 1;
+            wait_bar(b_done + 8 * acc, g_uses + (cb >> 1));
+            gemm::tc_fence_after();
+            uint32_t r[2][32];
+            gemm::tmem_ld_32x32(tlane + acc * 128 + ehalf * 64, r[0]);
+            gemm::tmem_ld_32x32(tlane + acc * 128 + ehalf * 64 + 32, r[1]);
+            gemm::tmem_ld_wait();
+            gemm::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) gemm::mbar_arrive(b_accfree + 8 * acc);
+            if (erow < V) {
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    __nv_bfloat16 *dst = a.y_planes + (static_cast<size_t>(b) * V + erow) * C + cb * 128 + ehalf * 64 + hq * 32;
+                    if (a.fp16) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const __half2 h = __floats2half2_rn(__uint_as_float(r[hq][8 * q + 2 * i]) * y_scale,
+                                                                    __uint_as_float(r[hq][8 * q + 2 * i + 1]) * y_scale);
+                                w[i] = *reinterpret_cast<const uint32_t *>(&h);
+                            }
+                            reinterpret_cast<uint4 *>(dst)[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[hq][8 * q + i]);
+                            if (a.P == 3) {
+                                uint4 pl[3];
+                                split8<3>(v, pl);
+#pragma unroll
+                                for (int p = 0; p < 3; ++p) reinterpret_cast<uint4 *>(dst + p * a.plane_stride)[q] = pl[p];
+                            } else {
+                                uint4 pl[2];
+                                split8<2>(v, pl);
+#pragma unroll
+                                for (int p = 0; p < 2; ++p) reinterpret_cast<uint4 *>(dst + p * a.plane_stride)[q] = pl[p];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
     gemm::tc_fence_before();
     __syncthreads();
-    if (warp == 0) gemm::tmem_dealloc(tmem, 128);
+    if (warp == 0) gemm::tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1306,7 +1378,7 @@ static int launch_graph_variant(const GraphArgs &ga, int64_t batch, cudaStream_t
 //   0 = double, 128 (2/SM)   1 = single, 80 (3/SM)   2 = single, 128 (2/SM)   3 = double, 80
 //   4 = double, 112 and 5 = single, 112: two CTAs per SM NEXT TO a resident pooling CTA (48 regs x 160 threads)
 //   6 / 7 = graph_kernel_v2 (8x8 Gram tiles, 14x4 message-passing tiles) with 128 / 112 registers
-//   8 = graph_kernel_tc (both products on tcgen05, operands converted in shared memory)
+//   8 = graph_kernel_tc (default: both products on tcgen05, operands converted in shared memory)
 static int graph_variant() { return static_cast<int>(option(kOptGraphVariant)); }
 
 template <int kMaxRegs>
@@ -1322,9 +1394,9 @@ static int launch_graph_v2(const GraphArgs &ga, int64_t batch, cudaStream_t st) 
 template <int NT>
 static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
     const bool v2_ok = ga.V <= kV2Rows && ga.C % (2 * kChunk) == 0;
-    if (graph_variant() == 8 && ga.V <= kMaxNodes && ga.C % 64 == 0) {
+    if (graph_variant() >= 8 && ga.V <= kMaxNodes && ga.C % 128 == 0) {
         AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-        graph_kernel_tc<<<static_cast<unsigned>(batch), kHeadThreads, kTcSmem, st>>>(ga);
+        graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, kTcSmem, st>>>(ga);
         AGRL_LAUNCH_CHECK(st, "graph");
         return AGRL_OK;
     }
