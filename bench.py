@@ -317,7 +317,7 @@ def run_b200(args):
         'config': {'workload': 'MARS-shaped test pass: graph head over 11310 tracklets (8 frames, 2048x16x8 maps), '
                                '1980x9330 %s distance on the 4096-d features, MARS-metric CMC/mAP' % args.dist_metric,
                    'tracklets_per_step_per_gpu': J, 'pool_tracklets': pool_n,
-                   'head': 'bulk-copy pooling (TMA ring), graph_kernel_v2, bf16x2 split GEMM (3 products); options %s' % (
+                   'head': 'bulk-copy pooling (TMA ring), graph layers on tcgen05 (graph_kernel_tc + bf16x2 split GEMM, 3 products); options %s' % (
                        {k: _lib.get_option(k) for k in ('head_sub_batch', 'pool_tma', 'pool_stages', 'graph_variant', 'gemm_pair')},),
                    'cache': 'input pool %.1f GB per GPU, larger than L2; cycled' % (pool_n * BYTES_PER_TRACKLET / 1e9),
                    'parallelism': 'independent head shards + gallery-sharded eval (NCCL merge)' if world > 1 else 'single GPU'},
