@@ -905,6 +905,8 @@ graph_kernel_v2(GraphArgs a) {
 //          phase the roles are coupled by mbarriers only (operands ready / MMAs retired / accumulator drained).
 // Measured: an MMA costs ~128 cycles of A-operand fetch whatever N is, so the small Gram MMAs are no bargain per flop --
 // but they run beside the conversions instead of on the FMA pipe, and the kernel is 25 % faster than graph_kernel_v2.
+// The 960 MMAs per tracklet-layer are now the bound (85 % of the time at 128 cycles each); UMMA M = 64 was tried:
+// its accumulator rows do not sit in TMEM lanes 0..63, and it is only 8 % faster per MMA.
 // One CTA per tracklet, 416 threads, 2 CTAs per SM (81 KiB smem, 256 TMEM columns each).
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcPlane = 64 * 128;                     // 8 KiB: 64 rows x 128 B
