@@ -892,10 +892,12 @@ graph_kernel_v2(GraphArgs a) {
 // graph kernel on the tensor cores (graph_variant 8): the two 56 x 56 x 2048 products of a graph layer -- the Gram
 // matrix X.X^T and the message passing Y = G.X -- as tcgen05 MMAs whose operands the CTA converts itself in shared
 // memory (no extra HBM traffic: X is read twice, Y planes written once, exactly as in the CUDA-core kernels).
-//   Gram   per 64-channel block the [node][channel] tile is split into THREE bf16 planes (fp32-exact, the distances
-//          d2 = |xi|^2 + |xj|^2 - 2 xi.xj cancel) in the 128-byte-swizzled K-major layout and multiplied with itself:
-//          6 plane products, M = 128 (rows 64.. are don't-care), N = 64, accumulated over all blocks in TMEM with the
-//          dominant product in its own accumulator (as the distance GEMM does).
+//   Gram   of the CENTRED nodes x_v - x_ref (x_ref = the whole-frame strip of frame 0): distances are translation
+//          invariant, and with the common part removed d2 = |xi'|^2 + |xj'|^2 - 2 xi'.xj' no longer cancels 99 % of its
+//          terms, so TWO bf16 planes (3 plane products instead of the 6 an fp32-exact Gram of the raw rows needs)
+//          keep the affinity within 1e-6.  Per 64-channel block the [node][channel] tile in the 128-byte-swizzled
+//          K-major layout is multiplied with itself: M = 128 (rows 64.. are don't-care), N = 64, accumulated over all
+//          blocks in TMEM with the dominant product in its own accumulator (as the distance GEMM does).
 //   G      affinity, L1 rows, pose mixing on CUDA cores exactly as in graph_kernel; then G as two bf16 planes.
 //   Y      per 128-channel block the TRANSPOSED tile [channel][node] (K = nodes) as two bf16 planes; D = G.X^T block,
 //          3 plane products (same 16-bit operand class as the planes Y is rounded to anyway), 128 x 128 x 16 MMAs,
@@ -903,15 +905,18 @@ graph_kernel_v2(GraphArgs a) {
 //   roles  13 warps: 0..11 workers, 12 issues the MMAs.  Gram: workers 0..7 convert.  Y: workers 2,3,6..11 convert,
 //          workers 0,1,4,5 (the ones that may read TMEM lanes 0..63) drain accumulators into operand planes.  Inside a
 //          phase the roles are coupled by mbarriers only (operands ready / MMAs retired / accumulator drained).
-// Measured: an MMA costs ~128 cycles of A-operand fetch whatever N is, so the small Gram MMAs are no bargain per flop --
-// but they run beside the conversions instead of on the FMA pipe, and the kernel is 25 % faster than graph_kernel_v2.
-// The 960 MMAs per tracklet-layer are now the bound (85 % of the time at 128 cycles each); UMMA M = 64 was tried:
-// its accumulator rows do not sit in TMEM lanes 0..63, and it is only 8 % faster per MMA.
+//          clock64 per phase (one tracklet, 2 CTAs per SM): Gram 63 k cycles, graph build 28 k, Y 125-143 k, in which the
+//          four drain warps are busy 92 % of the time.  Tried without gain: staging the planes through padded shared
+//          memory for 64-byte-contiguous stores (11.3 vs 11.5 ms per pass), eight drain + six convert warps at 64
+//          registers (12.8 ms), UMMA M = 64 (other TMEM row layout, 8 % faster per MMA), 64-channel Y blocks, two or
+//          four accumulators per product class, three CTAs per SM.
+// Measured: the kernel is 30 % faster than graph_kernel_v2 (11.5 vs 16.3 ms per pass); a Gram on the CUDA cores with
+// only Y on tcgen05 was slower than either (17.1 ms).
 // One CTA per tracklet, 416 threads, 2 CTAs per SM (81 KiB smem, 256 TMEM columns each).
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcPlane = 64 * 128;                     // 8 KiB: 64 rows x 128 B
 constexpr int kTcGPlanes = 0;                          // two G planes; the 128-row A descriptor of plane 1 runs into the ring
-constexpr int kTcRingOff = 2 * kTcPlane;               // Gram: 2 buffers x 3 planes x 8 KiB (+ the last plane's 128-row tail);
+constexpr int kTcRingOff = 2 * kTcPlane;               // Gram: 2 buffers x 2 planes x 8 KiB (+ the last plane's 128-row tail);
 constexpr int kTcRingBytes = 8 * kTcPlane;             // Y: 2 buffers x 2 planes x 16 KiB; in between: g[64][68], sq[64]
 constexpr int kTcBars = kTcRingOff + kTcRingBytes;
 constexpr int kTcSmem = kTcBars + 128 + 1024;
@@ -973,6 +978,7 @@ graph_kernel_tc(GraphArgs a) {
     const int erow = (warp & 3) * 32 + lane, ehalf = warp >> 2;
     const uint32_t tlane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     auto wait_bar = [&](uint32_t bar, int use) { gemm::mbar_wait(bar, static_cast<uint32_t>(use & 1)); };
+    const int ref_row = (V > 6) ? 6 : V - 1;                           // centre of the Gram: the whole-frame strip of frame 0
     const int n_gblocks = C / 64;                                      // even (C % 128 == 0)
     const int g_uses = a.learn_graph ? n_gblocks / 2 : 0;              // commits on each done[] barrier by the Gram phase
 
@@ -981,15 +987,20 @@ graph_kernel_tc(GraphArgs a) {
         if (gram_worker) {
             // item = (row, 8-channel slot): 64 rows x 8 slots, two items per thread; blocks kb and kb + 1 in flight
             float nxt[2][8], nx2[2][8];
+            const float *xref = x + static_cast<size_t>(ref_row) * C;
             auto load_block = [&](int kb, float (&dstv)[2][8]) {
+                const float4 *rsrc = reinterpret_cast<const float4 *>(xref + kb * 64 + (tid & 7) * 8);      // slot is the same for both items
+                const float4 rlo = __ldg(rsrc), rhi = __ldg(rsrc + 1);
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
                     if (row < V) {
                         const float4 *src = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * C + kb * 64 + slot * 8);
                         const float4 lo = __ldg(src), hi = __ldg(src + 1);
-                        dstv[t][0] = lo.x; dstv[t][1] = lo.y; dstv[t][2] = lo.z; dstv[t][3] = lo.w;
-                        dstv[t][4] = hi.x; dstv[t][5] = hi.y; dstv[t][6] = hi.z; dstv[t][7] = hi.w;
+                        dstv[t][0] = __fsub_rn(lo.x, rlo.x); dstv[t][1] = __fsub_rn(lo.y, rlo.y);
+                        dstv[t][2] = __fsub_rn(lo.z, rlo.z); dstv[t][3] = __fsub_rn(lo.w, rlo.w);
+                        dstv[t][4] = __fsub_rn(hi.x, rhi.x); dstv[t][5] = __fsub_rn(hi.y, rhi.y);
+                        dstv[t][6] = __fsub_rn(hi.z, rhi.z); dstv[t][7] = __fsub_rn(hi.w, rhi.w);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) dstv[t][i] = 0.f;
@@ -1012,20 +1023,20 @@ graph_kernel_tc(GraphArgs a) {
                 const int buf = kb & 1;
                 prefetch_block(kb + 6);
                 if (kb >= 2) wait_bar(b_done + 8 * buf, (kb >> 1) - 1);  // the MMAs that read this buffer have retired
-                unsigned char *dst = ring_p + buf * 3 * kTcPlane;
+                unsigned char *dst = ring_p + buf * 2 * kTcPlane;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
-                    uint4 pl[3];
-                    split8<3>(cur[t], pl);
+                    uint4 pl[2];
+                    split8<2>(cur[t], pl);
                     const int off = row * 128 + ((slot ^ (row & 7)) << 4);
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) *reinterpret_cast<uint4 *>(dst + p * kTcPlane + off) = pl[p];
+                    for (int p = 0; p < 2; ++p) *reinterpret_cast<uint4 *>(dst + p * kTcPlane + off) = pl[p];
                 }
-                if (kb + 2 < n_gblocks) load_block(kb + 2, cur);
-                fence_proxy_async_smem();
+                fence_proxy_async_smem();                               // (a MEMBAR: issue it BEFORE the next loads, or it waits for them)
                 __syncwarp();
                 if (lane == 0) gemm::mbar_arrive(b_gfull + 8 * buf);
+                if (kb + 2 < n_gblocks) load_block(kb + 2, cur);
             };
             for (int kb = 0; kb < n_gblocks; kb += 2) {
                 gram_step(kb, nxt);
@@ -1051,13 +1062,13 @@ graph_kernel_tc(GraphArgs a) {
                 const int buf = kb & 1;
                 wait_bar(b_gfull + 8 * buf, kb >> 1);
                 gemm::tc_fence_after();
-                const uint32_t base = ring + buf * 3 * kTcPlane;
+                const uint32_t base = ring + buf * 2 * kTcPlane;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
+                for (int i = 0; i < 3; ++i) {
                     int pa, pb;
-                    gemm::pair_of(3, i, pa, pb);
+                    gemm::pair_of(2, i, pa, pb);
                     const uint64_t da = gemm::make_smem_desc(base + pa * kTcPlane), db = gemm::make_smem_desc(base + pb * kTcPlane);
-                    const bool main_acc = (i == 5);                    // a0.b0 alone in columns 0..63, corrections in 64..127
+                    const bool main_acc = (i == 2);                    // a0.b0 alone in columns 0..63, corrections in 64..127
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         gemm::tc_mma_bf16(tmem + (main_acc ? 0 : 64), da + 2 * k, db + 2 * k, idesc,
@@ -1123,8 +1134,17 @@ graph_kernel_tc(GraphArgs a) {
             float m = fmaxf(lane < V ? sq[lane] : 0.f, lane + 32 < V ? sq[lane + 32] : 0.f);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float refn = 0.f;                                          // the Gram was centred: |x_v| <= |x_ref| + |x_v - x_ref|
+            if (a.learn_graph) {
+                const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(ref_row) * C);
+                for (int i = lane; i < C / 4; i += 32) {
+                    const float4 v = __ldg(row + i);
+                    refn = fmaf(v.x, v.x, refn); refn = fmaf(v.y, v.y, refn); refn = fmaf(v.z, v.z, refn); refn = fmaf(v.w, v.w, refn);
+                }
+                refn = warp_sum(refn);
+            }
             if (lane == 0) {
-                m = (m < 3.0e38f) ? sqrtf(m) : 0.f;
+                m = (m < 3.0e38f && refn < 3.0e38f) ? sqrtf(m) + sqrtf(refn) : 0.f;
                 pow2_scales(m, &s_scale[0], &s_scale[1]);
                 a.y_unscale[b] = s_scale[1];
             }
@@ -1210,12 +1230,12 @@ graph_kernel_tc(GraphArgs a) {
                 *reinterpret_cast<uint4 *>(dst + off) = pl[0];
                 *reinterpret_cast<uint4 *>(dst + 2 * kTcPlane + off) = pl[1];
             }
-            if (hh + 1 < n_halves) load_half(hh + 1);
             if (hh & 1) {
-                fence_proxy_async_smem();
+                fence_proxy_async_smem();                               // (a MEMBAR: before the next loads are issued)
                 __syncwarp();
                 if (lane == 0) gemm::mbar_arrive(b_yfull + 8 * buf);
             }
+            if (hh + 1 < n_halves) load_half(hh + 1);
         }
     } else {
         // epilogue (workers 0,1,4,5): accumulator -> registers (frees it for block cb + 2) -> planes -> global
