@@ -1080,8 +1080,8 @@ graph_kernel_tc(GraphArgs a) {
         __syncthreads();
         if (gram_worker && tid < V) sq[tid] = g[tid * kGLd + tid];
         __syncthreads();
-        if (gram_worker) {
-            for (int i = tid; i < V * V; i += kHeadThreads) {           // affinity (vmgn.py:116-120)
+        if (worker) {
+            for (int i = tid; i < V * V; i += 32 * 12) {                // affinity (vmgn.py:116-120), all 12 worker warps
                 const int r = i / V, c = i % V;
                 float d2 = __fadd_rn(sq[c], sq[r]);
                 d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
