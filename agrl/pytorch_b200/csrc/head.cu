@@ -2,18 +2,21 @@
 //
 // Per batch of B tracklets (S frames, P = 7 pyramid strips, V = S*P region nodes, C channels):
 //
-//   pool_kernel        one pass over both layer4 maps (the only HBM-heavy step, 2 x S*C*h*w*4 B per
-//                      tracklet): strip means -> node tensor X0 (B,V,C) written directly in node order
-//                      (vmgn.py:304-308, no cat / transpose copies, x4_2 read once instead of three
-//                      times) and the global mean -> BN neck -> out[:, :C] (vmgn.py:299-301).
-//   graph_kernel       one CTA per tracklet: Gram matrix on CUDA cores in fp32 (the cancellation in
-//                      |xi|^2+|xj|^2-2xi.xj needs it), affinity 2/(exp(d)+1) (vmgn.py:114-120), L1 row
-//                      normalisation of affinity and pose graph with warp shuffles (:157,:162), average
-//                      (:164), then Y = G.X (the message passing, :168, re-associated as (G.X).W^T)
-//                      emitted straight as bf16 operand planes for the tensor-core GEMM.
+//   pool_tma_kernel    one pass over both layer4 maps (the only HBM-heavy step, 2 x S*C*h*w*4 B per tracklet): strip
+//                      means -> node tensor X0 (B,V,C) written directly in node order (vmgn.py:304-308, no cat / transpose
+//                      copies, x4_2 read once instead of three times) and the global mean -> BN neck -> out[:, :C]
+//                      (vmgn.py:299-301).  Persistent CTAs, loads kept in flight in a shared-memory ring by cp.async.bulk;
+//                      runs at the measured HBM copy peak.  pool_kernel (register loads) covers maps that are not 16x8 or
+//                      unaligned, pool_nhwc_kernel channels-last maps.
+//   graph_kernel_tc    one CTA per tracklet: Gram matrix of the centred nodes and the message passing Y = G.X (vmgn.py:168,
+//                      re-associated as (G.X).W^T) as tcgen05 MMAs on operands the CTA converts itself in shared memory;
+//                      affinity 2/(exp(d)+1) (vmgn.py:114-120), L1 row normalisation of affinity and pose graph (:157,:162),
+//                      average (:164) on CUDA cores in between.  Y leaves as operand planes for the GEMM.
+//                      graph_kernel_v2 / graph_kernel are the CUDA-core versions (fallback: V > 64 or C % 128 != 0).
 //   split_gemm_kernel  (gemm_sm100.cuh) Y.W^T on tcgen05 with the layer's epilogue fused:
 //                      0.9*X + 0.1*LeakyReLU(BN(.)) (vmgn.py:169-172).
 //   attn_kernel        temporal attention (vmgn.py:276-277), part mean, BN neck -> out[:, C:] (:317-321).
+//   clip_pool_kernel   mean / max over the clips of a tracklet (train_vidreid_xent_htri.py:471-476).
 #include "gemm_sm100.cuh"
 
 #include <cuda_fp16.h>

@@ -87,11 +87,13 @@ AGRL_API uint64_t    agrl_launch_count(void);
  * time from the previous event to this one, i.e. the kernel's duration on a busy stream). */
 AGRL_API int         agrl_profile_begin(void *stream);
 AGRL_API int         agrl_profile_end(char *text, size_t capacity);
-/* Process-wide tuning knobs (no effect on results).  Names: "head_sub_batch" (tracklets per internal
- * sub-batch of agrl_head_forward_dev; 0 = one pass), "pool_tma" (1 = bulk-copy pooling kernel),
- * "pool_stages" (16 KiB ring stages per pooling CTA), "pool_ctas_per_sm", "graph_variant".  Defaults can
- * also come from the AGRL_HEAD_SUB / AGRL_POOL_TMA / AGRL_POOL_STAGES / AGRL_POOL_CTAS /
- * AGRL_GRAPH_VARIANT environment variables.  set returns AGRL_E_INVALID for an unknown name or a value
+/* Process-wide tuning knobs (results change at most by summation order, i.e. far below the parity bars).
+ * Names: "head_sub_batch" (tracklets per internal sub-batch of agrl_head_forward_dev; 0 = one pass, default),
+ * "overlap_mode", "pool_tma" (1 = bulk-copy pooling kernel, default), "pool_stages" (16 KiB ring stages per
+ * pooling CTA), "pool_ctas_per_sm", "pool_l2_hint", "graph_variant" (8 = tensor-core graph kernel, default;
+ * 6 = CUDA-core graph_kernel_v2; 0-5 = graph_kernel flavours), "gemm_pair" (1 = cta_group::2 GEMMs; default 0).
+ * Defaults can also come from the AGRL_HEAD_SUB / AGRL_OVERLAP_MODE / AGRL_POOL_TMA / AGRL_POOL_STAGES /
+ * AGRL_POOL_CTAS / AGRL_POOL_HINT / AGRL_GRAPH_VARIANT / AGRL_GEMM_PAIR environment variables.  set returns AGRL_E_INVALID for an unknown name or a value
  * out of range; get returns -1 for an unknown name. */
 AGRL_API int         agrl_set_option(const char *name, int64_t value);
 AGRL_API int64_t     agrl_get_option(const char *name);
