@@ -259,7 +259,8 @@ struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
         for (int q = 0; q < 8; ++q) xin[q] = __ldg(xr + q);
     }
     // 32 consecutive columns of one row: the math, then the stores
-    __device__ __forceinline__ void store_row32(int row, int col0, int n_cols, const uint32_t (&acc)[32], const float4 (&xin)[8]) const {
+    __device__ __forceinline__ void store_row32(int row, int col0, int n_cols, const uint32_t (&acc)[32], const float4 (&xin)[8],
+                                                float &sumsq) const {
         float4 *orow = reinterpret_cast<float4 *>(out + static_cast<size_t>(row) * ldo + col0);
         const float4 *sc = reinterpret_cast<const float4 *>(scale + col0);
         const float4 *sh = reinterpret_cast<const float4 *>(shift + col0);
@@ -276,6 +277,7 @@ struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
             h = fmaf(kScaled ? __uint_as_float(acc[4 * q + 2]) * unscale : __uint_as_float(acc[4 * q + 2]), s4.z, t4.z); h = h >= 0.f ? h : h * slope; o.z = fmaf(gamma, h, keep * xin[q].z);
             h = fmaf(kScaled ? __uint_as_float(acc[4 * q + 3]) * unscale : __uint_as_float(acc[4 * q + 3]), s4.w, t4.w); h = h >= 0.f ? h : h * slope; o.w = fmaf(gamma, h, keep * xin[q].w);
             orow[q] = o;
+            sumsq = fmaf(o.x, o.x, sumsq); sumsq = fmaf(o.y, o.y, sumsq); sumsq = fmaf(o.z, o.z, sumsq); sumsq = fmaf(o.w, o.w, sumsq);
         }
     }
     const float *x;             // layer input (M, ldx)
@@ -286,6 +288,13 @@ struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
     const float *row_unscale;   // kScaled: 2^-k of each tracklet's Y rows (one float per tracklet)
     const float *w_unscale;     // kScaled: 2^-k of this layer's W (one float)
     int nodes;                  // rows per tracklet
+    // optional (last layer): per row and per (column tile, half) the sum of squares of the stored outputs, so that the
+    // attention kernel gets its row norms (vmgn.py:276) without a pass of its own: (M, sumsq_slots) floats
+    float *row_sumsq = nullptr;
+    int sumsq_slots = 0;
+    __device__ __forceinline__ void store_sumsq(int row, int slot, float v) const {
+        if (row_sumsq) row_sumsq[static_cast<size_t>(row) * sumsq_slots + slot] = v;
+    }
     struct Col { float scale, shift; };
     __device__ __forceinline__ Col col_state(int col) const {
         Col c; c.scale = __ldg(scale + col); c.shift = __ldg(shift + col); return c;
@@ -489,6 +498,7 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 // the residual of round c + 1 is in flight while round c is computed and stored; round 0's loads
                 // are issued before the wait for the accumulator
                 float4 xa[8], xb[8];
+                float sumsq = 0.f;
                 if (live) epi.load_row32(row, n0 + col_half, xa);
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
@@ -498,14 +508,15 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                     tmem_ld_32x32(tq + col_half + c, r);
                     if (live && c + 32 < BN / 2) epi.load_row32(row, n0 + col_half + c + 32, xb);
                     tmem_ld_wait();
-                    if (live) epi.store_row32(row, n0 + col_half + c, N, r, xa);
+                    if (live) epi.store_row32(row, n0 + col_half + c, N, r, xa, sumsq);
                     if (c + 32 < BN / 2) {
                         tmem_ld_32x32(tq + col_half + c + 32, r);
                         if (live && c + 64 < BN / 2) epi.load_row32(row, n0 + col_half + c + 64, xa);
                         tmem_ld_wait();
-                        if (live) epi.store_row32(row, n0 + col_half + c + 32, N, r, xb);
+                        if (live) epi.store_row32(row, n0 + col_half + c + 32, N, r, xb, sumsq);
                     }
                 }
+                if (live) epi.store_sumsq(row, (n0 / BN) * 2 + (ew >> 2), sumsq);
                 tc_fence_before();
                 if (lane == 0) release_acc(acc);
                 ++cit;

@@ -1305,6 +1305,8 @@ struct AttnArgs {
     float *out; int64_t ld_out;        // (B, 2C): attention branch -> [:, C:]
     const float *a_scale, *a_shift;    // folded att_bottleneck
     int S, C;
+    const float *row_sumsq;            // optional (B*V, slots): partial sums of squares from the last GEMM's epilogue
+    int slots;
 };
 
 __global__ void __launch_bounds__(kHeadThreads)
@@ -1315,15 +1317,24 @@ attn_kernel(AttnArgs a) {
     const int V = a.S * kParts, C = a.C, b = blockIdx.x;
     const float *x = a.x + static_cast<size_t>(b) * V * C;
     // a[s,p] = ||f[s,p,:]||_2
-    for (int r = warp; r < V; r += kHeadThreads / 32) {
-        const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
-        float s = 0.f;
-        for (int i = lane; i < C / 4; i += 32) {
-            const float4 v = __ldg(row + i);
-            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+    if (a.row_sumsq) {                                     // the last GEMM epilogue already summed the squares per column tile
+        if (tid < V) {
+            const float *ps = a.row_sumsq + (static_cast<size_t>(b) * V + tid) * a.slots;
+            float s = 0.f;
+            for (int i = 0; i < a.slots; ++i) s += ps[i];
+            s_norm[tid] = sqrtf(s);
         }
-        s = warp_sum(s);
-        if (lane == 0) s_norm[r] = sqrtf(s);
+    } else {
+        for (int r = warp; r < V; r += kHeadThreads / 32) {
+            const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
+            float s = 0.f;
+            for (int i = lane; i < C / 4; i += 32) {
+                const float4 v = __ldg(row + i);
+                s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) s_norm[r] = sqrtf(s);
+        }
     }
     __syncthreads();
     // att = a / max(sum_s |a|, 1e-12)   (F.normalize p=1 over the frame axis)
@@ -1365,6 +1376,7 @@ struct HeadWorkspace {
     float *x[2];
     __nv_bfloat16 *y_planes;
     float *y_unscale;                  // (batch) fp16 mode
+    float *row_sumsq;                  // (batch*V, 32) partial row norms of the last layer's output
     size_t bytes;
 };
 
@@ -1376,6 +1388,7 @@ static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t bat
     w.x[1] = c.take<float>(n);
     w.y_planes = c.take<__nv_bfloat16>(static_cast<size_t>(p->split) * n);
     w.y_unscale = c.take<float>(static_cast<size_t>(batch));
+    w.row_sumsq = c.take<float>(static_cast<size_t>(batch) * S * kParts * 32);
     w.bytes = c.total();
     return w;
 }
@@ -1616,6 +1629,8 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
     if (adj) adj += b0 * V * V;
     if (masks) masks += b0 * 3;
     int rc;
+    const float *attn_sumsq = nullptr;
+    int attn_slots = 0;
     CUtensorMap map_y, map_w;
     if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, y, rows, C, p->split, gemm::BM, all_rows))) return rc;
     int cur = 0;
@@ -1631,11 +1646,15 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
         if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, pair ? bn / 2 : bn, C))) return rc;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
         gemm::EpiGraphLayer epi{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope, nullptr, nullptr, V};
+        const int sumsq_slots = 2 * ((C + bn - 1) / bn);                 // (column tile, half) pairs of the direct epilogue
+        float *sumsq = (l == L - 1 && C % bn == 0) ? hwk.row_sumsq + row0 * 32 : nullptr;
+        if (sumsq) { epi.row_sumsq = sumsq; epi.sumsq_slots = sumsq_slots; attn_sumsq = sumsq; attn_slots = sumsq_slots; }
         if (gate && (rc = gate->join(l, st))) return rc;
         AGRL_LAUNCH_BEGIN(st);
         if (fp16) {
             gemm::EpiGraphLayerF16 epi16{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
                                          hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
+            epi16.row_sumsq = epi.row_sumsq; epi16.sumsq_slots = epi.sumsq_slots;
             rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st)
                       : gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st);
         } else if (p->split == AGRL_SPLIT_BF16X3) {
@@ -1651,7 +1670,7 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
     }
     if (L == 0 && nodes_out)
         AGRL_CUDA_TRY(cudaMemcpyAsync(nodes_out, x[0], sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
-    AttnArgs aa{x[cur], out + static_cast<size_t>(b0) * ld_out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C};
+    AttnArgs aa{x[cur], out + static_cast<size_t>(b0) * ld_out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C, attn_sumsq, attn_slots};
     if (gate && (rc = gate->partner(L, L, st))) return rc;
     AGRL_LAUNCH_BEGIN(st);
     attn_kernel<<<static_cast<unsigned>(n), kHeadThreads, 0, st>>>(aa);
