@@ -20,7 +20,7 @@ def to_bytes(v, unit):
     return float(v) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
 
 
-res = {'_source': 'ncu --set full captures of round-1 v6 (profiles/r1/ncu_head_v6.txt, ncu_eval_v6.txt); bench.py --pool 882 / tools/run_eval_once.py'}
+res = {'_source': 'ncu --set full captures of round-1 v7 (profiles/r1/ncu_head_v7.txt, ncu_eval_v7.txt); bench.py --pool 882 / tools/run_eval_once.py'}
 for rep in sys.argv[1:]:
     for row in rows(rep):
         name = row['Kernel Name'][0]
