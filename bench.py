@@ -262,6 +262,16 @@ def run_b200(args):
         timeline = prof.totals()
         barrier()
 
+        # ---- same-box comparator: the reference's module code in stock PyTorch on this GPU (rank 0) ----
+        eager = None
+        if not args.no_eager and rank == 0:
+            try:
+                eager = torch_eager_gpu(args, dev, weights, x1, x2, adj, feats)
+            except Exception as exc:                     # a comparator must never cost the bench line
+                eager = {'unavailable': '%s: %s' % (type(exc).__name__, exc)}
+            torch.cuda.empty_cache()
+        barrier()
+
         # ---- end to end through host buffers -------------------------------------------------
         e2e = None
         if not args.no_e2e:
@@ -338,6 +348,11 @@ def run_b200(args):
                     'tests/test_gpu_head.py); NOT the configuration `value` is measured in',
             'head_ms': fast['head_ms'], 'head_tracklets_per_s_per_gpu': J / (fast['head_ms'] * 1e-3),
             'head_hbm_frac': fgbs / pk['hbm_gbs'], 'kernels_ms': fast['kernels']}
+    if eager is not None:
+        if 'head_ms_per_pass' in eager:
+            eager['b200_head_speedup'] = eager['head_ms_per_pass'] / head_ms
+            eager['b200_distance_speedup'] = eager['distance_ms'] / gemm_d
+        line['torch_eager_gpu'] = eager
     if e2e is not None:
         line['e2e'] = e2e
     if not args.no_cpu_baseline and world >= 1:
@@ -510,6 +525,95 @@ def run_e2e(args, model, dev, rank, world, labels):
 
 
 # ------------------------------------------------------------------------------------------------
+# same-box GPU comparator: the reference's head / distance lines as stock PyTorch modules
+# on the same B200 (library kernels: cuDNN/ATen pooling, cuBLAS fp32 GEMMs, elementwise ATen ops)
+# ------------------------------------------------------------------------------------------------
+def build_eager(dev, weights):
+    """(head, distance) callables: the reference's module code for this path, written with the stock torch.nn modules
+    it is built from (vmgn.py:104-123,142-172,237-268,270-278,296-321; distance.py:59-73), on device `dev`."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    pool3d = nn.AdaptiveAvgPool3d(1)
+    part_pools = [nn.AdaptiveAvgPool2d((k, 1)) for k in (4, 2, 1)]
+
+    def bn(prefix):
+        m = nn.BatchNorm1d(C).to(dev).eval()
+        for k in ('weight', 'bias', 'running_mean', 'running_var'):
+            getattr(m, k).data.copy_(weights[prefix + '.' + k])
+        return m
+    g_neck, a_neck = bn('global_bottleneck'), bn('att_bottleneck')
+    layers = []
+    for i in range(2):
+        lin = nn.Linear(C, C, bias=False).to(dev)
+        lin.weight.data.copy_(weights['graph_layers.%d.linear.weight' % i])
+        layers.append((lin, bn('graph_layers.%d.bn' % i)))
+    act = nn.LeakyReLU(0.1)
+
+    def layer(lin, norm, f, a):
+        h = lin(f)
+        a = F.normalize(a, p=1, dim=2)
+        sq = torch.pow(f, 2).sum(dim=2)
+        d = sq.unsqueeze(1) + sq.unsqueeze(2)
+        d -= 2 * torch.bmm(f, f.transpose(1, 2))
+        g = F.normalize(2 / (d.clamp(1e-12).sqrt().exp() + 1), p=1, dim=2)
+        hp = torch.bmm((a + g) / 2, h)
+        hp = act(norm(hp.view(-1, C)).view(h.shape))
+        return 0.9 * f + 0.1 * hp
+
+    def head(m1, m2, a):
+        b = a.shape[0]
+        g_bn = g_neck(pool3d(m1.view(b, S, C, H, W).transpose(1, 2).contiguous()).view(b, -1))
+        f = torch.cat([p(m2).view(b, S, C, k) for p, k in zip(part_pools, (4, 2, 1))], dim=3)
+        f = f.transpose(2, 3).contiguous().view(b, S * 7, C)
+        for lin, norm in layers:
+            f = layer(lin, norm, f, a)
+        f = f.view(b, S, 7, C)
+        att = F.normalize(f.norm(p=2, dim=3, keepdim=True), p=1, dim=1)
+        return torch.cat([g_bn, a_neck(f.mul(att).sum(dim=1).mean(dim=1))], dim=1)
+
+    def distance(q, g):
+        d = torch.pow(q, 2).sum(dim=1, keepdim=True).expand(q.shape[0], g.shape[0]) + \
+            torch.pow(g, 2).sum(dim=1, keepdim=True).expand(g.shape[0], q.shape[0]).t()
+        return d.addmm(q, g.t(), beta=1, alpha=-2)
+
+    return head, distance
+
+
+def torch_eager_gpu(args, dev, weights, x1, x2, adj, feats):
+    """What the reference's own module code costs on this GPU, left in PyTorch's default fp32 mode (TF32 matmuls
+    off).  Not a product path and not the oracle: a reported comparator, timed on a bounded sample of the resident
+    pool.  The ranking has no GPU form in the reference (numpy / Cython), so it is not part of it."""
+    head, distance = build_eager(dev, weights)
+    n = min(args.eager_sample, x1.shape[0] // S)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    chunk = min(n, 64)                                     # the transposed copy of 64 tracklets is 0.5 GB
+    with torch.no_grad():
+        def head_sample():
+            for off in range(0, n - chunk + 1, chunk):
+                head(x1[off * S:(off + chunk) * S], x2[off * S:(off + chunk) * S], adj[off:off + chunk])
+        done = (n // chunk) * chunk
+        head_ms = timed(head_sample, 3) / done
+        dist_ms = timed(lambda: distance(feats[:NQ], feats[NQ:]), 5)
+    J = NQ + NG
+    return {'what': 'the reference head / distance lines as stock torch.nn modules on this GPU, default fp32 (TF32 off), '
+                    'maps resident; ranking excluded (numpy / Cython only in the reference)',
+            'sample': 'head: %d of %d tracklets in batches of %d, extrapolated; distance %dx%dx%d in full' % (done, J, chunk, NQ, NG, 2 * C),
+            'head_ms_per_tracklet': head_ms, 'head_tracklets_per_s': 1e3 / head_ms, 'head_ms_per_pass': head_ms * J,
+            'distance_ms': dist_ms}
+
+
+# ------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the same path, bounded sample
 # ------------------------------------------------------------------------------------------------
 def cpu_reference(args, steps, warmup):
@@ -594,6 +698,8 @@ def main():
     ap.add_argument('--sweep-gallery', type=int, default=1000000)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch-on-this-GPU comparator (SURVEY 8d)')
+    ap.add_argument('--eager-sample', type=int, default=256, help='tracklets of the pool the comparator head is timed on')
     ap.add_argument('--no-fast-mode', action='store_true', help='skip the extra head pass with the fp16 single-plane GEMM')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
