@@ -10,13 +10,14 @@ Host-side mirror of the reference's interface for that path, over the C ABI of l
     agrl.pytorch_b200.utils.re_ranking.re_ranking           <- torchreid/utils/re_ranking.py:30   (section 8f)
     agrl.pytorch_b200.pose.generate_graph                   <- torchreid/dataset_loader.py:218    (section 8f)
     agrl.pytorch_b200.models.pool_clips                     <- train_vidreid_xent_htri.py:471-476 (section 8f)
+    agrl.pytorch_b200.engine.test                           <- train_vidreid_xent_htri.py:450-542 (the path's caller)
 
 ``install_as_torchreid()`` registers these under the reference's own dotted names so an unmodified
 caller (``from torchreid import metrics, models``) picks them up.  There is no CPU fallback.
 """
 import sys
 
-from . import metrics, models, pose, utils
+from . import engine, metrics, models, pose, utils
 
 __all__ = ['install_as_torchreid']
 
