@@ -78,6 +78,12 @@ static const OptionDef kOptionDefs[kOptCount] = {
     // Parity-tested; measured SLOWER than one CTA per tile on B200 (24.6 vs 23.3 ms, fp16 plane 19.8 vs 11.9 ms per
     // pass; tensor pipe 68 % vs 79 % active, a third less L2->SM traffic) -- default off, see DESIGN.md
     {"gemm_pair", "AGRL_GEMM_PAIR", 0, 0, 1},
+    // Spatial partition of the sub-batched pipeline (free-running mode, overlap_mode = 0): with pool_sms > 0 the
+    // poolings of sub-batches 1.. run as ONE wide CTA per SM on pool_sms SMs (two producer/consumer lanes per CTA and
+    // a ring that fills the SM's shared memory, so no graph / GEMM CTA can share the SM), while the persistent GEMM
+    // of every sub-batch but the last is launched on gemm_sms CTAs (0 = all SMs minus pool_sms).  Experimental: off.
+    {"pool_sms", "AGRL_POOL_SMS", 0, 0, 148},
+    {"gemm_sms", "AGRL_GEMM_SMS", 0, 0, 148},
 };
 static std::atomic<int64_t> g_options[kOptCount];
 static std::atomic<int> g_options_init{0};

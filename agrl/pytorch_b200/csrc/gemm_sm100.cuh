@@ -667,13 +667,15 @@ int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, 
 
 template <int P, int BN, bool kSplit, class Epi>
 int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,
-                      const Epi &epi, cudaStream_t st) {
+                      const Epi &epi, cudaStream_t st, int max_ctas = 0) {
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>;
     static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
     auto kern = split_gemm_kernel<P, BN, kSplit, Epi>;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    // persistent grid: one CTA per SM, or per SM of the partition the caller leaves to this kernel (max_ctas > 0)
+    const int width = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
+    const int grid = tiles < width ? tiles : width;
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
     AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;

@@ -257,9 +257,14 @@ struct PoolTmaArgs {
     int l2_hint;                       // 1: evict-first cache hint on the bulk copies
 };
 
-static size_t pool_tma_smem(int S, int stages) {
-    return static_cast<size_t>(stages) * kTpStageBytes + 2 * static_cast<size_t>(S) * kParts * kTpCh * sizeof(float) +
-           2 * static_cast<size_t>(stages) * 8 + 128;
+// bytes of one producer/consumer lane: ring | two node tiles | barriers, rounded up to 128
+static __host__ __device__ inline size_t pool_tma_lane_bytes(int S, int stages) {
+    const size_t b = static_cast<size_t>(stages) * kTpStageBytes + 2 * static_cast<size_t>(S) * kParts * kTpCh * sizeof(float) +
+                     2 * static_cast<size_t>(stages) * 8;
+    return (b + 127) & ~static_cast<size_t>(127);
+}
+static size_t pool_tma_smem(int S, int stages, int lanes = 1) {
+    return lanes * pool_tma_lane_bytes(S, stages) + 128;
 }
 
 __device__ __forceinline__ void bulk_load_evict_first(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
@@ -293,23 +298,32 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__global__ void __maxnreg__(48)
-pool_tma_kernel(PoolTmaArgs a) {
+// kLanes independent producer/consumer groups ("lanes") per CTA, each with its own ring, node tiles, barriers and
+// work units.  kLanes = 1 is the default kernel (two such CTAs per SM).  kLanes = 2 is the spatially partitioned
+// flavour: ONE CTA that fills an SM's shared memory, launched on a subset of the SMs while the graph / GEMM kernels of
+// the previous sub-batch own the others (option pool_sms) -- the block scheduler would spread two narrow CTAs over
+// two SMs, so the pair is fused into one CTA.
+template <int kLanes>
+__device__ __forceinline__ void pool_tma_body(const PoolTmaArgs &a) {
     extern __shared__ __align__(16) unsigned char tp_smem_dyn[];
-    // align to 128 B by OFFSET (not by casting through an integer) so that the compiler keeps emitting LDS / STS
-    unsigned char *smem = tp_smem_dyn + ((128u - (gemm::smem_u32(tp_smem_dyn) & 127u)) & 127u);
     const int stages = a.stages, S = a.S, C = a.C, V = S * kParts;
+    const int group = kLanes > 1 ? static_cast<int>(threadIdx.x) / kTpThreads : 0;     // which lane this thread serves
+    // align to 128 B by OFFSET (not by casting through an integer) so that the compiler keeps emitting LDS / STS
+    unsigned char *smem = tp_smem_dyn + ((128u - (gemm::smem_u32(tp_smem_dyn) & 127u)) & 127u) +
+                          (kLanes > 1 ? group * pool_tma_lane_bytes(S, stages) : 0);
     const float4 *ring_f4 = reinterpret_cast<const float4 *>(smem);
     float *s_nodes = reinterpret_cast<float *>(smem + stages * kTpStageBytes);   // [2][V][32]
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_nodes + 2 * V * kTpCh);
     const uint32_t ring = gemm::smem_u32(smem);
     const uint32_t bar_full = gemm::smem_u32(bars), bar_empty = bar_full + 8 * stages;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = static_cast<int>(threadIdx.x) - group * kTpThreads;                 // thread index within the lane
+    const int warp = tid >> 5, lane = tid & 31;
     const int chunks = C / kTpCh;
     const int units = a.unit1;
-    const int first = a.unit0 + blockIdx.x;
+    const int first = a.unit0 + static_cast<int>(blockIdx.x) * kLanes + group;
+    const int stride = static_cast<int>(gridDim.x) * kLanes;
 
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         for (int i = 0; i < stages; ++i) { gemm::mbar_init(bar_full + 8 * i, 1); gemm::mbar_init(bar_empty + 8 * i, kTpConsumerWarps); }
         gemm::fence_barrier_init();
     }
@@ -321,7 +335,7 @@ pool_tma_kernel(PoolTmaArgs a) {
             uint64_t policy;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
             int stage = 0; uint32_t phase = 0;
-            for (int u = first; u < units; u += gridDim.x) {
+            for (int u = first; u < units; u += stride) {
                 const int b = u / chunks, cc = u % chunks;
                 for (int s = 0; s < S; ++s) {
                     const size_t off = ((static_cast<size_t>(b) * S + s) * C + static_cast<size_t>(cc) * kTpCh) * 128;
@@ -339,11 +353,11 @@ pool_tma_kernel(PoolTmaArgs a) {
         }
     } else {
         // ================= consumers =================
-        const int cw = warp - 1, ct = threadIdx.x - 32;           // consumer warp / thread index
+        const int cw = warp - 1, ct = tid - 32;                   // consumer warp / thread index
         const int grp = lane >> 3, sub = lane & 7;                // 8-lane group <-> quarter strip (4 rows of 8)
         const float inv_all = 1.0f / (static_cast<float>(S) * 128.0f);
         int stage = 0; uint32_t phase = 0; int it = 0;
-        for (int u = first; u < units; u += gridDim.x, ++it) {
+        for (int u = first; u < units; u += stride, ++it) {
             const int b = u / chunks, c0 = (u % chunks) * kTpCh;
             float *sn = s_nodes + (it & 1) * V * kTpCh;
             float gsum[8];
@@ -396,13 +410,21 @@ pool_tma_kernel(PoolTmaArgs a) {
                     a.out[static_cast<size_t>(b) * a.ld_out + c] = fmaf(t * inv_all, a.g_scale[c], a.g_shift[c]);
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kTpConsumerWarps) : "memory");   // node tile complete
+            // node tile complete (one named barrier per lane)
+            if (kLanes > 1 && group == 1) asm volatile("bar.sync 2, %0;" ::"n"(32 * kTpConsumerWarps) : "memory");
+            else asm volatile("bar.sync 1, %0;" ::"n"(32 * kTpConsumerWarps) : "memory");
             float *nodes = a.nodes + static_cast<size_t>(b) * V * C + c0;
             for (int v = ct >> 5; v < V; v += kTpConsumerWarps) nodes[static_cast<size_t>(v) * C + lane] = sn[v * kTpCh + lane];
             // (the other s_nodes buffer is used next; this one is rewritten only after the next unit's barrier)
         }
     }
 }
+
+__global__ void __maxnreg__(48)
+pool_tma_kernel(PoolTmaArgs a) { pool_tma_body<1>(a); }
+
+__global__ void __maxnreg__(48)
+pool_tma_wide_kernel(PoolTmaArgs a) { pool_tma_body<2>(a); }
 
 // ------------------------------------------------------------------------------------------------
 // graph kernel: one CTA per tracklet
@@ -1547,7 +1569,7 @@ static thread_local HeadCtx tl_head_ctx;
 // (TMA flavour only: `part` / `parts` selects a contiguous slice of the work units, see the gated pipeline)
 static int launch_pool(const agrl_head_params *p, const Prepared &pr, const HeadWorkspace &hwk, const float *x4_1,
                        const float *x4_2, float *out, int64_t ld_out, int64_t b0, int64_t n, int S, int hw, bool tma,
-                       int ctas_per_sm, cudaStream_t st, int64_t unit_lo = 0, int64_t unit_hi = -1) {
+                       int ctas_per_sm, cudaStream_t st, int64_t unit_lo = 0, int64_t unit_hi = -1, int wide_sms = 0) {
     const int C = p->channels, V = S * kParts, L = p->num_layers;
     const size_t in_off = static_cast<size_t>(b0) * S * C * hw;
     float *nodes = hwk.x[0] + static_cast<size_t>(b0) * V * C;
@@ -1567,9 +1589,24 @@ static int launch_pool(const agrl_head_params *p, const Prepared &pr, const Head
         PoolTmaArgs ta{x4_1 + in_off, x4_2 + in_off, nodes, o, ld_out, pr.scale[L], pr.shift[L], S, C,
                        static_cast<int>(option(kOptPoolStages)), static_cast<int>(unit_lo), static_cast<int>(unit_hi),
                        static_cast<int>(option(kOptPoolHint))};
+        const int64_t units = unit_hi - unit_lo;
+        if (wide_sms > 0) {
+            // spatial partition: one two-lane CTA per SM on `wide_sms` SMs; the ring is made as deep as the SM's shared
+            // memory allows (>= 5 stages per lane), which also keeps every graph / GEMM CTA off these SMs
+            int stages = ta.stages < 5 ? 5 : ta.stages;
+            while (stages > 2 && pool_tma_smem(S, stages, 2) > 227u * 1024u) --stages;
+            ta.stages = stages;
+            const size_t wsmem = pool_tma_smem(S, stages, 2);
+            if (wsmem > 227u * 1024u) return AGRL_E_UNSUPPORTED;
+            AGRL_CUDA_TRY(cudaFuncSetAttribute(pool_tma_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem)));
+            int64_t wgrid = wide_sms < kNumSMs ? wide_sms : kNumSMs;
+            if (wgrid * 2 > units) wgrid = (units + 1) / 2;
+            pool_tma_wide_kernel<<<static_cast<unsigned>(wgrid), 2 * kTpThreads, wsmem, st>>>(ta);
+            AGRL_LAUNCH_CHECK(st, "pool");
+            return AGRL_OK;
+        }
         const size_t smem = pool_tma_smem(S, ta.stages);
         AGRL_CUDA_TRY(cudaFuncSetAttribute(pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        const int64_t units = unit_hi - unit_lo;
         int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
         if (grid > units) grid = units;
         pool_tma_kernel<<<static_cast<unsigned>(grid), kTpThreads, smem, st>>>(ta);
@@ -1620,7 +1657,7 @@ struct Gate {
 static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWorkspace hwk, const float *adj,
                          const uint64_t *masks, float *out,
                          int64_t ld_out, float *nodes_out, int64_t b0, int64_t n, int64_t batch, int S, cudaStream_t st,
-                         const Gate *gate = nullptr) {
+                         const Gate *gate = nullptr, int gemm_ctas = 0) {
     const int C = p->channels, V = S * kParts, L = p->num_layers;
     const int64_t rows = n * V, row0 = b0 * V, all_rows = batch * V;
     float *x[2] = {hwk.x[0] + row0 * C, hwk.x[1] + row0 * C};
@@ -1656,13 +1693,13 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
                                          hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
             epi16.row_sumsq = epi.row_sumsq; epi16.sumsq_slots = epi.sumsq_slots;
             rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st)
-                      : gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st);
+                      : gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas);
         } else if (p->split == AGRL_SPLIT_BF16X3) {
             rc = pair ? gemm::launch_pair_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st)
-                      : gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+                      : gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
         } else {
             rc = pair ? gemm::launch_pair_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st)
-                      : gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st);
+                      : gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
         }
         if (rc) return rc;
         if (dst == nodes_out) x[cur ^ 1] = nodes_out;
@@ -1744,15 +1781,24 @@ static int head_forward_impl(const agrl_head_params *p, const void *prepared,
         }
         return AGRL_OK;
     }
+    // Spatial partition (option pool_sms, experimental): pooling 0 has the chip to itself (two CTAs per SM); poolings
+    // 1.. are wide CTAs on pool_sms SMs, and while one of them can be running the persistent GEMMs keep to the other
+    // SMs (gemm_sms, default all minus pool_sms).  The last sub-batch's GEMMs have no pooling beside them: full width.
+    const int psms = tma ? static_cast<int>(option(kOptPoolSms)) : 0;
+    int gsms = static_cast<int>(option(kOptGemmSms));
+    if (psms > 0 && gsms == 0) gsms = kNumSMs - psms > 0 ? kNumSMs - psms : 1;
     for (int j = 0; j < nsub; ++j) {
         const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
-        if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, ctas, ctx.side))) return rc;
+        const bool wide = psms > 0 && j > 0;
+        if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, (psms > 0 && j == 0) ? 2 : ctas, ctx.side,
+                              0, -1, wide ? psms : 0))) return rc;
         AGRL_CUDA_TRY(cudaEventRecord(ctx.pooled[j], ctx.side));
     }
     for (int j = 0; j < nsub; ++j) {
         const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
         AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx.pooled[j], 0));
-        if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
+        const int gemm_ctas = (psms > 0 && j + 1 < nsub) ? gsms : 0;
+        if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st, nullptr, gemm_ctas))) return rc;
     }
     return AGRL_OK;
 }

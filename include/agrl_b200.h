@@ -91,9 +91,11 @@ AGRL_API int         agrl_profile_end(char *text, size_t capacity);
  * Names: "head_sub_batch" (tracklets per internal sub-batch of agrl_head_forward_dev; 0 = one pass, default),
  * "overlap_mode", "pool_tma" (1 = bulk-copy pooling kernel, default), "pool_stages" (16 KiB ring stages per
  * pooling CTA), "pool_ctas_per_sm", "pool_l2_hint", "graph_variant" (8 = tensor-core graph kernel, default;
- * 6 = CUDA-core graph_kernel_v2; 0-5 = graph_kernel flavours), "gemm_pair" (1 = cta_group::2 GEMMs; default 0).
+ * 6 = CUDA-core graph_kernel_v2; 0-5 = graph_kernel flavours), "gemm_pair" (1 = cta_group::2 GEMMs; default 0),
+ * "pool_sms" / "gemm_sms" (experimental spatial partition of the sub-batched pipeline with overlap_mode = 0: poolings
+ * 1.. as one shared-memory-filling CTA per SM on pool_sms SMs, persistent GEMMs on gemm_sms CTAs, 0 = the rest; default 0 = off).
  * Defaults can also come from the AGRL_HEAD_SUB / AGRL_OVERLAP_MODE / AGRL_POOL_TMA / AGRL_POOL_STAGES /
- * AGRL_POOL_CTAS / AGRL_POOL_HINT / AGRL_GRAPH_VARIANT / AGRL_GEMM_PAIR environment variables.  set returns AGRL_E_INVALID for an unknown name or a value
+ * AGRL_POOL_CTAS / AGRL_POOL_HINT / AGRL_GRAPH_VARIANT / AGRL_GEMM_PAIR / AGRL_POOL_SMS / AGRL_GEMM_SMS environment variables.  set returns AGRL_E_INVALID for an unknown name or a value
  * out of range; get returns -1 for an unknown name. */
 AGRL_API int         agrl_set_option(const char *name, int64_t value);
 AGRL_API int64_t     agrl_get_option(const char *name);

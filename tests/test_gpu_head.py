@@ -156,7 +156,7 @@ def test_clip_pooling_strided_rows_and_cpu_input():
 def restore_options():
     from agrl.pytorch_b200 import _lib
     names = ('head_sub_batch', 'pool_tma', 'pool_stages', 'pool_ctas_per_sm', 'graph_variant', 'pool_l2_hint',
-             'overlap_mode', 'gemm_pair')
+             'overlap_mode', 'gemm_pair', 'pool_sms', 'gemm_sms')
     saved = {n: _lib.get_option(n) for n in names}
     yield _lib
     for n, v in saved.items():
@@ -203,6 +203,35 @@ def test_pipeline_modes_agree(restore_options):
             out = model.head(x1, x2, adj, S)
         emax, enrm = rel_err(out.cpu(), ref)
         assert emax < TOL and enrm < TOL, (variant, emax, enrm)
+
+
+@pytest.mark.parametrize('split', [1, 2, 3])
+def test_spatially_partitioned_pipeline_agrees(split, restore_options):
+    """options pool_sms / gemm_sms (free-running sub-batches): poolings 1.. run as one two-lane CTA per SM on a subset
+    of the SMs while the persistent GEMMs keep to the others.  Same arithmetic as the one-pass bulk-copy run, so the
+    result is bit-identical to it; several partition widths, ragged last sub-batch, odd unit counts."""
+    lib = restore_options
+    S, B = 8, 13
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=64, scale=2.0)
+    adj = synth.pose_adjacency(B, S, 7, seed=65)
+    wts = synth.head_weights(2048, 2, seed=66, randomise_bn=True)
+    model = make_model(wts, split=split)
+    ref = ohead.head_forward(x1, x2, adj, wts, dtype=torch.float64)
+    x1, x2, adj = x1.cuda(), x2.cuda(), adj.cuda()
+    lib.set_option('pool_tma', 1); lib.set_option('head_sub_batch', 0)
+    with torch.no_grad():
+        base = model.head(x1, x2, adj, S).cpu()
+    emax, enrm = rel_err(base, ref)
+    assert emax < TOL and enrm < TOL
+    lib.set_option('overlap_mode', 0)
+    for sub, psms, gsms, stages in ((4, 40, 0, 4), (3, 148, 20, 6), (5, 1, 147, 12), (6, 7, 3, 2)):
+        lib.set_option('head_sub_batch', sub); lib.set_option('pool_sms', psms); lib.set_option('gemm_sms', gsms)
+        lib.set_option('pool_stages', stages)
+        for _ in range(2):
+            with torch.no_grad():
+                out = model.head(x1, x2, adj, S)
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), base), (sub, psms, gsms, stages, rel_err(out.cpu(), ref))
 
 
 def test_sub_batched_head_into_preallocated_rows_and_nodes(restore_options):
