@@ -1,5 +1,6 @@
 """Head-pipeline variants on one resident input pool (one process, options switched at run time).
-usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split pair psms gsms nhwc call)
+usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split pair psms gsms wldg nhwc call gb)
+`gb` = number of graph layers of the model (0: pooling + attention only -> the pooling kernels run practically alone).
 `call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
 import json
 import os
@@ -12,7 +13,7 @@ import bench
 from agrl.pytorch_b200 import _lib
 
 KEYS = {'sub': 'head_sub_batch', 'tma': 'pool_tma', 'stages': 'pool_stages', 'ctas': 'pool_ctas_per_sm', 'graph': 'graph_variant',
-        'mode': 'overlap_mode', 'hint': 'pool_l2_hint', 'pair': 'gemm_pair', 'psms': 'pool_sms', 'gsms': 'gemm_sms'}
+        'mode': 'overlap_mode', 'hint': 'pool_l2_hint', 'pair': 'gemm_pair', 'psms': 'pool_sms', 'gsms': 'gemm_sms', 'wldg': 'pool_wide_ldg'}
 
 
 def main():
@@ -21,6 +22,21 @@ def main():
     torch.cuda.set_device(dev)
     _lib.require_device()
     model = bench.make_model(dev, bench.make_head_weights())
+    models_by_gb = {2: model}
+
+    def model_for(gb):
+        if gb not in models_by_gb:
+            from agrl.pytorch_b200 import models
+            m = models.init_model('vmgn', num_classes=625, loss={'xent', 'htri'}, last_stride=1, num_split=4, num_gb=gb,
+                                  num_scale=1, pyramid_part=True, use_pose=True, learn_graph=True, pretrained=False)
+            sd = m.state_dict()
+            for k, v in bench.make_head_weights().items():
+                if k in sd:
+                    sd[k].copy_(v)
+            for name in ('graph_layers', 'global_bottleneck', 'att_bottleneck'):
+                getattr(m, name).to(dev)
+            models_by_gb[gb] = m.eval()
+        return models_by_gb[gb]
     x1, x2, adj = bench.make_pool(pool_n, dev, seed=1)
     J, S = int(os.environ.get('HV_TRACKLETS', bench.NQ + bench.NG)), bench.S
     feats = torch.empty(J, 2 * bench.C, device=dev)
@@ -35,6 +51,7 @@ def main():
                 cfg[k] = int(v)
         for k, name in KEYS.items():
             _lib.set_option(name, cfg[k])
+        model = model_for(cfg.get('gb', 2))
         model.head_split = cfg.get('split', 2)
         call = min(cfg['call'], pool_n)
         chunks = [(o, min(call, J - o)) for o in range(0, J, call)]
