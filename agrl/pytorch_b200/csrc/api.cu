@@ -84,8 +84,6 @@ static const OptionDef kOptionDefs[kOptCount] = {
     // of every sub-batch but the last is launched on gemm_sms CTAs (0 = all SMs minus pool_sms).  Experimental: off.
     {"pool_sms", "AGRL_POOL_SMS", 0, 0, 148},
     {"gemm_sms", "AGRL_GEMM_SMS", 0, 0, 148},
-    // partitioned poolings: 0 = two-lane bulk-copy CTA (shared-memory ring), 1 = 1024-thread register-load CTA
-    {"pool_wide_ldg", "AGRL_POOL_WIDE_LDG", 0, 0, 1},
 };
 static std::atomic<int64_t> g_options[kOptCount];
 static std::atomic<int> g_options_init{0};

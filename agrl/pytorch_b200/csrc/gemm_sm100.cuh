@@ -640,7 +640,7 @@ int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, in
 // CTA-pair flavour; map_b must have been built with box_rows = BN / 2.
 template <int P, int BN, bool kSplit, class Epi>
 int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,
-                     const Epi &epi, cudaStream_t st) {
+                     const Epi &epi, cudaStream_t st, int max_ctas = 0) {
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, true>;
     static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
     auto kern = pair_gemm_kernel<P, BN, kSplit, Epi>;
@@ -659,7 +659,8 @@ int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, 
         return n < kNumSMs / 2 ? n : kNumSMs / 2;
     }();
     const int tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + BN - 1) / BN);
-    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    int pairs = tiles < max_pairs ? tiles : max_pairs;
+    if (max_ctas > 0 && pairs > max_ctas / 2) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;   // the caller's SM partition
     kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
     AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;

@@ -174,74 +174,6 @@ pool_kernel(PoolArgs a) {
     }
 }
 
-// Register-load pooling for the spatially partitioned pipeline (options pool_sms + pool_wide_ldg): ONE persistent
-// 1024-thread CTA per SM = four independent 256-thread groups, each looping over (tracklet, 64-channel chunk) work
-// units exactly as a pool_kernel<true> CTA does (same loads, same summation order -> same bits).  The loads stay in
-// registers (no shared-memory ring), so the SM's shared-memory port carries only the node rows; the dynamic shared
-// memory request is padded so that no graph / GEMM CTA shares the SM.  Needs h*w == 128 and 16-byte aligned maps.
-constexpr int kWideGroups = 4;
-__global__ void __launch_bounds__(kWideGroups * kHeadThreads, 1)
-pool_ldg_wide_kernel(PoolArgs a, int units) {
-    extern __shared__ float s_wide[];                  // [kWideGroups][S][7][kPoolCh]
-    const int group = threadIdx.x / kHeadThreads, tid = threadIdx.x % kHeadThreads;
-    const int V = a.S * kParts, chunks = a.C / kPoolCh;
-    float *s_nodes = s_wide + group * V * kPoolCh;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int grp = lane >> 3, sub = lane & 7;
-    constexpr int hw = 128;
-    constexpr float inv_q = 1.0f / 32.0f, inv_h = 1.0f / 64.0f, inv_w = 1.0f / 128.0f;
-    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kHeadThreads) : "memory"); };
-    for (int u = blockIdx.x * kWideGroups + group; u < units; u += gridDim.x * kWideGroups) {
-        const int b = u / chunks, c0 = (u % chunks) * kPoolCh;
-        float gsum[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gsum[i] = 0.f;
-        for (int s = 0; s < a.S; ++s) {
-            const size_t frame = (static_cast<size_t>(b) * a.S + s) * a.C;
-            float q1[8], q2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const size_t off = (frame + c0 + warp * 8 + i) * hw + lane * 4;
-                const float4 v1 = __ldcs(reinterpret_cast<const float4 *>(a.x41 + off));
-                const float4 v2 = __ldcs(reinterpret_cast<const float4 *>(a.x42 + off));
-                q1[i] = (v1.x + v1.y) + (v1.z + v1.w);
-                q2[i] = (v2.x + v2.y) + (v2.z + v2.w);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float v1 = q1[i], v2 = q2[i];
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 4); v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 2); v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 1); v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
-                const float h2 = v2 + __shfl_xor_sync(0xffffffffu, v2, 8);
-                const float w2 = h2 + __shfl_xor_sync(0xffffffffu, h2, 16);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
-                gsum[i] += v1;
-                float *dst = s_nodes + (s * kParts) * kPoolCh + warp * 8 + i;
-                if (sub == 0) dst[grp * kPoolCh] = v2 * inv_q;
-                if (lane == 0) { dst[4 * kPoolCh] = h2 * inv_h; dst[6 * kPoolCh] = w2 * inv_w; }
-                if (lane == 16) dst[5 * kPoolCh] = h2 * inv_h;
-            }
-        }
-        if (lane == 0) {
-            const float inv_all = 1.0f / (static_cast<float>(a.S) * static_cast<float>(hw));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = c0 + warp * 8 + i;
-                a.out[static_cast<size_t>(b) * a.ld_out + c] = fmaf(gsum[i] * inv_all, a.g_scale[c], a.g_shift[c]);
-            }
-        }
-        group_sync();
-        float *nodes = a.nodes + static_cast<size_t>(b) * V * a.C + c0;
-        for (int i = tid; i < V * kPoolCh; i += kHeadThreads) {
-            const int v = i / kPoolCh, c = i % kPoolCh;
-            nodes[static_cast<size_t>(v) * a.C + c] = s_nodes[i];
-        }
-        group_sync();                                   // the node tile is rewritten by the next unit
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // pooling, channels-last maps (the part that stays on our side of the cuDNN boundary):
 // a backbone run in torch.channels_last hands over (B*S, h, w, C)-ordered memory; converting it back to NCHW would
@@ -1658,20 +1590,6 @@ static int launch_pool(const agrl_head_params *p, const Prepared &pr, const Head
                        static_cast<int>(option(kOptPoolStages)), static_cast<int>(unit_lo), static_cast<int>(unit_hi),
                        static_cast<int>(option(kOptPoolHint))};
         const int64_t units = unit_hi - unit_lo;
-        if (wide_sms > 0 && option(kOptPoolWideLdg) != 0) {
-            // spatial partition, register-load flavour: one 1024-thread CTA per SM on `wide_sms` SMs
-            PoolArgs pa{x4_1 + in_off, x4_2 + in_off, nodes, o, ld_out, pr.scale[L], pr.shift[L], S, C, hw};
-            const int64_t wunits = n * (C / kPoolCh);
-            size_t wsmem = static_cast<size_t>(kWideGroups) * S * kParts * kPoolCh * sizeof(float);
-            if (wsmem > 227u * 1024u || C % kPoolCh != 0) return AGRL_E_UNSUPPORTED;
-            if (wsmem < 160u * 1024u) wsmem = 160u * 1024u;             // keeps graph / GEMM CTAs off these SMs
-            AGRL_CUDA_TRY(cudaFuncSetAttribute(pool_ldg_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem)));
-            int64_t wgrid = wide_sms < kNumSMs ? wide_sms : kNumSMs;
-            if (wgrid * kWideGroups > wunits) wgrid = (wunits + kWideGroups - 1) / kWideGroups;
-            pool_ldg_wide_kernel<<<static_cast<unsigned>(wgrid), kWideGroups * kHeadThreads, wsmem, st>>>(pa, static_cast<int>(wunits));
-            AGRL_LAUNCH_CHECK(st, "pool");
-            return AGRL_OK;
-        }
         if (wide_sms > 0) {
             // spatial partition: one two-lane CTA per SM on `wide_sms` SMs; the ring is made as deep as the SM's shared
             // memory allows (>= 5 stages per lane), which also keeps every graph / GEMM CTA off these SMs
@@ -1683,7 +1601,20 @@ static int launch_pool(const agrl_head_params *p, const Prepared &pr, const Head
             AGRL_CUDA_TRY(cudaFuncSetAttribute(pool_tma_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem)));
             int64_t wgrid = wide_sms < kNumSMs ? wide_sms : kNumSMs;
             if (wgrid * 2 > units) wgrid = (units + 1) / 2;
-            pool_tma_wide_kernel<<<static_cast<unsigned>(wgrid), 2 * kTpThreads, wsmem, st>>>(ta);
+            if (option(kOptGemmPair) != 0 && wgrid % 2 == 0) {
+                // the GEMMs run as CTA pairs (two SMs of one TPC): launch the pooling CTAs as clusters of two as well, so
+                // that they fill whole TPCs instead of taking one SM out of twice as many
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(static_cast<unsigned>(wgrid)); cfg.blockDim = dim3(2 * kTpThreads);
+                cfg.dynamicSmemBytes = wsmem; cfg.stream = st;
+                cudaLaunchAttribute at;
+                at.id = cudaLaunchAttributeClusterDimension;
+                at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+                cfg.attrs = &at; cfg.numAttrs = 1;
+                AGRL_CUDA_TRY(cudaLaunchKernelEx(&cfg, pool_tma_wide_kernel, ta));
+            } else {
+                pool_tma_wide_kernel<<<static_cast<unsigned>(wgrid), 2 * kTpThreads, wsmem, st>>>(ta);
+            }
             AGRL_LAUNCH_CHECK(st, "pool");
             return AGRL_OK;
         }
@@ -1774,13 +1705,13 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
             gemm::EpiGraphLayerF16 epi16{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
                                          hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
             epi16.row_sumsq = epi.row_sumsq; epi16.sumsq_slots = epi.sumsq_slots;
-            rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st)
+            rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas)
                       : gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas);
         } else if (p->split == AGRL_SPLIT_BF16X3) {
-            rc = pair ? gemm::launch_pair_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st)
+            rc = pair ? gemm::launch_pair_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas)
                       : gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
         } else {
-            rc = pair ? gemm::launch_pair_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st)
+            rc = pair ? gemm::launch_pair_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas)
                       : gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
         }
         if (rc) return rc;
