@@ -77,7 +77,7 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in open(self.path):
             f = [x.strip() for x in line.split(',')]
@@ -87,13 +87,17 @@ class ClockSampler(object):
                 sm.append(float(f[1])); smax.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                power.append(float(f[3]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[5:9]):
                 if v.lower().startswith('active'):
                     reasons.add(n)
         os.unlink(self.path)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                       samples=len(sm))
+                       samples=len(sm), power_w=float(np.median(power)) if power else None)
         return out
 
 

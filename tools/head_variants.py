@@ -68,17 +68,23 @@ def main():
                 for _ in range(2):
                     head_pass()
                 torch.cuda.synchronize()
-                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                for i in range(3):
+                # HV_REPS timed passes (default 3); HV_CLOCKS=1 samples nvidia-smi clocks / power / throttle reasons meanwhile
+                reps = int(os.environ.get('HV_REPS', '3'))
+                sampler = bench.ClockSampler(0) if os.environ.get('HV_CLOCKS') else None
+                if sampler:
+                    sampler.start()
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+                for i in range(reps):
                     e[i].record(stream); head_pass()
-                e[3].record(stream)
+                e[reps].record(stream)
                 torch.cuda.synchronize()
-                ms = [e[i].elapsed_time(e[i + 1]) for i in range(3)]
+                clocks = sampler.stop() if sampler else None
+                ms = [e[i].elapsed_time(e[i + 1]) for i in range(reps)]
                 with _lib.profile(stream.cuda_stream) as prof:
                     head_pass()
                 tot = {k: round(t, 3) for k, (n, t) in prof.totals().items()}
             best = min(ms)
-            print(json.dumps({'spec': spec, 'head_ms': round(best, 3), 'all': [round(m, 3) for m in ms],
+            print(json.dumps({'spec': spec, 'head_ms': round(best, 3), 'all': [round(m, 3) for m in ms[:6]], 'clocks': clocks,
                               'ktracklets_s': round(J / best, 1),
                               'hbm_frac': round(J * bench.BYTES_PER_TRACKLET / (best * 1e-3) / 1e9 / 6545.9, 4),
                               'checksum': float(feats.double().sum()), 'kernels': tot}), flush=True)
