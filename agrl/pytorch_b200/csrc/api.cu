@@ -84,6 +84,10 @@ static const OptionDef kOptionDefs[kOptCount] = {
     // of every sub-batch but the last is launched on gemm_sms CTAs (0 = all SMs minus pool_sms).  Experimental: off.
     {"pool_sms", "AGRL_POOL_SMS", 0, 0, 148},
     {"gemm_sms", "AGRL_GEMM_SMS", 0, 0, 148},
+    // 1: the FIRST graph layer runs its X.W^T on the quarter-strip rows only (the pooled nodes of a frame are linear
+    // combinations of its four quarter strips: G.X.W^T = (G.T).(Q.W^T), 4S GEMM rows per tracklet instead of 7S), then a
+    // per-tracklet mixing kernel applies G.T and the layer's epilogue.  Same result to ~1e-7 (tests/test_lowrank_layer1.py).
+    {"head_lowrank", "AGRL_HEAD_LOWRANK", 0, 0, 1},
 };
 static std::atomic<int64_t> g_options[kOptCount];
 static std::atomic<int> g_options_init{0};

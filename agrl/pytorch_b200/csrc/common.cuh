@@ -21,7 +21,7 @@ void        after_launch(cudaStream_t st, const char *name);   // counts; record
 void        before_launch(cudaStream_t st);
 
 // Process-wide tuning knobs (agrl_set_option / agrl_get_option; defaults may come from AGRL_* env vars).
-enum Option { kOptHeadSubBatch = 0, kOptPoolTma, kOptPoolStages, kOptPoolCtasPerSm, kOptGraphVariant, kOptPoolHint, kOptOverlapMode, kOptGemmPair, kOptPoolSms, kOptGemmSms, kOptCount };
+enum Option { kOptHeadSubBatch = 0, kOptPoolTma, kOptPoolStages, kOptPoolCtasPerSm, kOptGraphVariant, kOptPoolHint, kOptOverlapMode, kOptGemmPair, kOptPoolSms, kOptGemmSms, kOptHeadLowrank, kOptCount };
 int64_t     option(Option o);
 
 #define AGRL_CUDA_TRY(expr)                                                            \

@@ -307,6 +307,36 @@ struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
         out[static_cast<size_t>(row) * ldo + col] = fmaf(gamma, h, (1.0f - gamma) * xin);
     }
 };
+// Plain store of the accumulator as fp32 (first graph layer on the quarter-strip rows: Z = Q.W^T, the layer's element-wise
+// part follows in graph_mix_kernel).  Same direct-epilogue interface as EpiGraphLayerT; nothing to prefetch or reload.
+template <bool kScaled>
+struct EpiPlainT {
+    static constexpr const char *kName = "gemm_graph_layer";
+    static constexpr bool kF16 = kScaled;
+    static constexpr bool kDirect = true;
+    static constexpr int kChunkKb = 0;
+    float *out; int64_t ldo;
+    const float *row_unscale;   // kScaled: 2^-k per tracklet
+    const float *w_unscale;     // kScaled: 2^-k of the layer's W
+    int rows_per_unit;          // GEMM rows per tracklet
+    __device__ __forceinline__ void prefetch(int, int, int, bool) const {}
+    __device__ __forceinline__ void load_row32(int, int, float4 (&)[8]) const {}
+    __device__ __forceinline__ void store_row32(int row, int col0, int n_cols, const uint32_t (&acc)[32], const float4 (&)[8],
+                                                float &) const {
+        if (col0 + 32 > n_cols) return;
+        const float unscale = kScaled ? __ldg(row_unscale + row / rows_per_unit) * __ldg(w_unscale) : 1.0f;
+        float4 *orow = reinterpret_cast<float4 *>(out + static_cast<size_t>(row) * ldo + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float4 o;
+            o.x = __uint_as_float(acc[4 * q + 0]); o.y = __uint_as_float(acc[4 * q + 1]);
+            o.z = __uint_as_float(acc[4 * q + 2]); o.w = __uint_as_float(acc[4 * q + 3]);
+            if (kScaled) { o.x *= unscale; o.y *= unscale; o.z *= unscale; o.w *= unscale; }
+            orow[q] = o;
+        }
+    }
+    __device__ __forceinline__ void store_sumsq(int, int, float) const {}
+};
 using EpiGraphLayer = EpiGraphLayerT<false>;
 using EpiGraphLayerF16 = EpiGraphLayerT<true>;
 

@@ -443,6 +443,10 @@ struct GraphArgs {
     int use_pose, learn_graph;
     int fp16;                          // P == 1: one fp16 plane of y * 2^k, k per tracklet
     float *y_unscale;                  // (B): 2^-k
+    // low-rank first layer (graph_kernel_tc only): instead of Y = G.X the kernel writes G.T (B, V, 4S) and the planes of
+    // the quarter-strip rows -- y_planes / plane_stride then describe [P][B*4S][C]
+    int lowrank = 0;
+    float *gt = nullptr;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -1177,6 +1181,52 @@ graph_kernel_tc(GraphArgs a) {
         __syncthreads();
         y_scale = s_scale[0];
     }
+    if (a.lowrank) {
+        // ---- low-rank first layer: the nodes of a frame are T.(its four quarter strips), so G.X.W^T = (G.T).(Q.W^T).
+        // Emit G.T (V x 4S) and the quarter-strip rows Q as GEMM operand planes; the message passing happens after the
+        // GEMM, on 4S instead of 7S rows (graph_mix_kernel). ----
+        if (worker) {
+            const int S4 = (V / kParts) * 4;
+            float *gt = a.gt + static_cast<size_t>(b) * V * S4;
+            for (int i = tid; i < V * S4; i += 32 * 12) {
+                const int r = i / S4, j = i - r * S4, k = j & 3;
+                const float *gr = g + r * kGLd + (j >> 2) * kParts;         // frame j / 4 of row r
+                gt[i] = fmaf(0.25f, gr[6], fmaf(0.5f, gr[4 + (k >> 1)], gr[k]));
+            }
+            const int groups = C / 8;
+            for (int i = tid; i < S4 * groups; i += 32 * 12) {
+                const int qr = i / groups, cg = i - qr * groups;
+                const int row = (qr >> 2) * kParts + (qr & 3);
+                const float4 *src = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * C + cg * 8);
+                const float4 lo = __ldg(src), hi = __ldg(src + 1);
+                const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                __nv_bfloat16 *dst = a.y_planes + (static_cast<size_t>(b) * S4 + qr) * C + cg * 8;
+                if (a.fp16) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const __half2 h = __floats2half2_rn(v[2 * t] * y_scale, v[2 * t + 1] * y_scale);
+                        w[t] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                } else if (a.P == 3) {
+                    uint4 pl[3];
+                    split8<3>(v, pl);
+#pragma unroll
+                    for (int pp = 0; pp < 3; ++pp) *reinterpret_cast<uint4 *>(dst + pp * a.plane_stride) = pl[pp];
+                } else {
+                    uint4 pl[2];
+                    split8<2>(v, pl);
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) *reinterpret_cast<uint4 *>(dst + pp * a.plane_stride) = pl[pp];
+                }
+            }
+        }
+        gemm::tc_fence_before();
+        __syncthreads();
+        if (warp == 0) gemm::tmem_dealloc(tmem, 256);
+        return;
+    }
     // ---- G as two bf16 planes, K-major [row = output node][k = input node] ----
     if (gram_worker) {
 #pragma unroll
@@ -1320,6 +1370,55 @@ graph_kernel_tc(GraphArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// low-rank first layer, part 2 (option head_lowrank): out = (1 - gamma) X + gamma LeakyReLU(BN((G.T) . Z)) with
+// Z = Q.W^T (4S rows per tracklet, from the GEMM) and G.T (V x 4S, from graph_kernel_tc).  One thread per channel keeps
+// its column of Z in registers, the rows of G.T come as shared-memory broadcasts; grid (C / 256, tracklets).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMixLd = 36;                             // 4S <= 36 for V <= 64, padded with zeros
+struct MixArgs {
+    const float *x, *z, *gt;           // (B, V, C), (B, 4S, C), (B, V, 4S)
+    float *out;                        // (B, V, C)
+    const float *scale, *shift;        // folded BatchNorm of the layer
+    int V, S4, C;
+    float gamma, slope;
+};
+
+__global__ void __launch_bounds__(kHeadThreads)
+graph_mix_kernel(MixArgs a) {
+    __shared__ __align__(16) float s_gt[kMaxNodes * kMixLd];
+    const int b = blockIdx.y, c = blockIdx.x * kHeadThreads + threadIdx.x;
+    const int V = a.V, S4 = a.S4, C = a.C;
+    const float *gt = a.gt + static_cast<size_t>(b) * V * S4;
+    for (int i = threadIdx.x; i < V * kMixLd; i += kHeadThreads) {
+        const int r = i / kMixLd, k = i - r * kMixLd;
+        s_gt[i] = (k < S4) ? gt[r * S4 + k] : 0.f;
+    }
+    float z[kMixLd];
+    const float *zc = a.z + static_cast<size_t>(b) * S4 * C + c;
+#pragma unroll
+    for (int k = 0; k < kMixLd; ++k) z[k] = (k < S4) ? __ldg(zc + static_cast<size_t>(k) * C) : 0.f;
+    const float sc = __ldg(a.scale + c), sh = __ldg(a.shift + c), keep = 1.0f - a.gamma;
+    const float *xc = a.x + static_cast<size_t>(b) * V * C + c;
+    float *oc = a.out + static_cast<size_t>(b) * V * C + c;
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < V; ++r) {
+        const float xin = __ldg(xc + static_cast<size_t>(r) * C);
+        const float4 *g4 = reinterpret_cast<const float4 *>(s_gt + r * kMixLd);
+        float acc = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < kMixLd / 4; ++k4) {
+            const float4 w = g4[k4];
+            acc = fmaf(w.x, z[4 * k4 + 0], acc); acc = fmaf(w.y, z[4 * k4 + 1], acc);
+            acc = fmaf(w.z, z[4 * k4 + 2], acc); acc = fmaf(w.w, z[4 * k4 + 3], acc);
+        }
+        float h = fmaf(acc, sc, sh);
+        h = h >= 0.f ? h : h * a.slope;
+        oc[static_cast<size_t>(r) * C] = fmaf(a.gamma, h, keep * xin);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // temporal attention + part mean + BN neck: one CTA per tracklet
 // ------------------------------------------------------------------------------------------------
 struct AttnArgs {
@@ -1397,6 +1496,8 @@ attn_kernel(AttnArgs a) {
 struct HeadWorkspace {
     float *x[2];
     __nv_bfloat16 *y_planes;
+    float *z;                          // (batch, 4S, C) low-rank first layer: Q.W^T
+    float *gt;                         // (batch, V, 4S) low-rank first layer: G.T
     float *y_unscale;                  // (batch) fp16 mode
     float *row_sumsq;                  // (batch*V, 32) partial row norms of the last layer's output
     size_t bytes;
@@ -1411,6 +1512,11 @@ static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t bat
     w.y_planes = c.take<__nv_bfloat16>(static_cast<size_t>(p->split) * n);
     w.y_unscale = c.take<float>(static_cast<size_t>(batch));
     w.row_sumsq = c.take<float>(static_cast<size_t>(batch) * S * kParts * 32);
+    // only with option head_lowrank (the option is read when the size is queried AND at the call: a change in between
+    // fails the size check of the call instead of overrunning)
+    const bool lowrank = option(kOptHeadLowrank) != 0;
+    w.z = lowrank ? c.take<float>(static_cast<size_t>(batch) * S * 4 * p->channels) : nullptr;
+    w.gt = lowrank ? c.take<float>(static_cast<size_t>(batch) * S * kParts * S * 4) : nullptr;
     w.bytes = c.total();
     return w;
 }
@@ -1687,14 +1793,49 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
     for (int l = 0; l < L; ++l) {
         const int fp16 = p->split == AGRL_SPLIT_FP16X1;
         GraphArgs ga{x[cur], adj, masks, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph, fp16, hwk.y_unscale + b0};
+        const bool pair = option(kOptGemmPair) != 0;
+        const int bn = p->split == AGRL_SPLIT_BF16X3 ? 128 : 256;
+        float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
+        // Low-rank first layer (option head_lowrank): only layer 0 sees nodes that are T.(quarter strips); needs the
+        // tensor-core graph kernel (it emits G.T and the Q planes) and whole frames of 7 nodes
+        const bool lowrank = l == 0 && hwk.z && graph_variant() >= 8 && V <= kMaxNodes && V % kParts == 0 && C % 256 == 0 && !pair;
+        if (lowrank) {
+            const int S4 = (V / kParts) * 4;
+            const int64_t qrows = n * S4, q_all = batch * S4;
+            __nv_bfloat16 *yq = hwk.y_planes + b0 * S4 * C;
+            float *z = hwk.z + b0 * S4 * C;
+            ga.y_planes = yq; ga.plane_stride = q_all * C; ga.lowrank = 1; ga.gt = hwk.gt + b0 * V * S4;
+            if (gate && (rc = gate->partner(l, L, st))) return rc;
+            AGRL_LAUNCH_BEGIN(st);
+            if ((rc = launch_graph<14>(ga, n, st))) return rc;
+            CUtensorMap map_q;
+            if ((rc = gemm::make_plane_tensor_map(&map_q, yq, qrows, C, p->split, gemm::BM, q_all))) return rc;
+            if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, bn, C))) return rc;
+            if (gate && (rc = gate->join(l, st))) return rc;
+            AGRL_LAUNCH_BEGIN(st);
+            if (fp16) {
+                gemm::EpiPlainT<true> ez{z, C, hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, S4};
+                rc = gemm::launch_split_gemm<1, 256, false>(map_q, map_w, static_cast<int>(qrows), C, C, ez, st, gemm_ctas);
+            } else {
+                gemm::EpiPlainT<false> ez{z, C, nullptr, nullptr, S4};
+                rc = p->split == AGRL_SPLIT_BF16X3
+                         ? gemm::launch_split_gemm<3, 128, false>(map_q, map_w, static_cast<int>(qrows), C, C, ez, st, gemm_ctas)
+                         : gemm::launch_split_gemm<2, 256, false>(map_q, map_w, static_cast<int>(qrows), C, C, ez, st, gemm_ctas);
+            }
+            if (rc) return rc;
+            MixArgs ma{x[cur], z, ga.gt, dst, pr.scale[l], pr.shift[l], V, S4, C, p->gamma, p->leaky_slope};
+            AGRL_LAUNCH_BEGIN(st);
+            graph_mix_kernel<<<dim3(C / kHeadThreads, static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
+            AGRL_LAUNCH_CHECK(st, "graph_mix");
+            if (dst == nodes_out) x[cur ^ 1] = nodes_out;
+            cur ^= 1;
+            continue;
+        }
         if (gate && (rc = gate->partner(l, L, st))) return rc;
         AGRL_LAUNCH_BEGIN(st);
         if (V == 56) rc = launch_graph<14>(ga, n, st); else rc = launch_graph<16>(ga, n, st);
         if (rc) return rc;
-        const bool pair = option(kOptGemmPair) != 0;
-        const int bn = p->split == AGRL_SPLIT_BF16X3 ? 128 : 256;
         if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, pair ? bn / 2 : bn, C))) return rc;
-        float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
         gemm::EpiGraphLayer epi{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope, nullptr, nullptr, V};
         const int sumsq_slots = 2 * ((C + bn - 1) / bn);                 // (column tile, half) pairs of the direct epilogue
         float *sumsq = (l == L - 1 && C % bn == 0) ? hwk.row_sumsq + row0 * 32 : nullptr;

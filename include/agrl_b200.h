@@ -93,9 +93,11 @@ AGRL_API int         agrl_profile_end(char *text, size_t capacity);
  * pooling CTA), "pool_ctas_per_sm", "pool_l2_hint", "graph_variant" (8 = tensor-core graph kernel, default;
  * 6 = CUDA-core graph_kernel_v2; 0-5 = graph_kernel flavours), "gemm_pair" (1 = cta_group::2 GEMMs; default 0),
  * "pool_sms" / "gemm_sms" (experimental spatial partition of the sub-batched pipeline with overlap_mode = 0: poolings
- * 1.. as one shared-memory-filling CTA per SM on pool_sms SMs, persistent GEMMs on gemm_sms CTAs, 0 = the rest; default 0 = off).
+ * 1.. as one shared-memory-filling CTA per SM on pool_sms SMs, persistent GEMMs on gemm_sms CTAs, 0 = the rest; default 0 = off),
+ * "head_lowrank" (1 = the first graph layer's X.W^T on the 4S quarter-strip rows per tracklet instead of the 7S node rows,
+ * G.X.W^T = (G.T).(Q.W^T); needs more workspace, so set it before agrl_head_workspace_bytes; default 0).
  * Defaults can also come from the AGRL_HEAD_SUB / AGRL_OVERLAP_MODE / AGRL_POOL_TMA / AGRL_POOL_STAGES /
- * AGRL_POOL_CTAS / AGRL_POOL_HINT / AGRL_GRAPH_VARIANT / AGRL_GEMM_PAIR / AGRL_POOL_SMS / AGRL_GEMM_SMS environment variables.  set returns AGRL_E_INVALID for an unknown name or a value
+ * AGRL_POOL_CTAS / AGRL_POOL_HINT / AGRL_GRAPH_VARIANT / AGRL_GEMM_PAIR / AGRL_POOL_SMS / AGRL_GEMM_SMS / AGRL_HEAD_LOWRANK environment variables.  set returns AGRL_E_INVALID for an unknown name or a value
  * out of range; get returns -1 for an unknown name. */
 AGRL_API int         agrl_set_option(const char *name, int64_t value);
 AGRL_API int64_t     agrl_get_option(const char *name);

@@ -156,7 +156,7 @@ def test_clip_pooling_strided_rows_and_cpu_input():
 def restore_options():
     from agrl.pytorch_b200 import _lib
     names = ('head_sub_batch', 'pool_tma', 'pool_stages', 'pool_ctas_per_sm', 'graph_variant', 'pool_l2_hint',
-             'overlap_mode', 'gemm_pair', 'pool_sms', 'gemm_sms')
+             'overlap_mode', 'gemm_pair', 'pool_sms', 'gemm_sms', 'head_lowrank')
     saved = {n: _lib.get_option(n) for n in names}
     yield _lib
     for n, v in saved.items():
@@ -239,6 +239,39 @@ def test_spatially_partitioned_pipeline_agrees(split, restore_options):
                 emax, enrm = rel_err(out.cpu(), ref)
                 assert emax < TOL and enrm < TOL, (sub, psms, gsms, stages, emax, enrm)
                 assert rel_err(out.cpu(), base)[0] < 2e-6
+
+
+@pytest.mark.parametrize('split', [1, 2, 3])
+@pytest.mark.parametrize('use_pose,learn_graph', [(True, True), (False, True), (True, False)])
+def test_lowrank_first_layer_agrees(split, use_pose, learn_graph, restore_options):
+    """option head_lowrank: the first layer's X.W^T runs on the 4S quarter-strip rows per tracklet, G.T and the layer's
+    element-wise part follow in graph_mix_kernel (identity and rounding pinned on the CPU in test_lowrank_layer1.py).
+    Same bar as the default path, and within 1e-5 of it; other sequence lengths, one layer only, sub-batched."""
+    lib = restore_options
+    for S, B, num_gb, sub in ((8, 5, 2, 0), (4, 3, 2, 0), (9, 2, 2, 0), (8, 3, 1, 0), (8, 7, 2, 3)):
+        x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=120 + S + B, scale=2.0)
+        adj = synth.pose_adjacency(B, S, 7, seed=121 + S)
+        wts = synth.head_weights(2048, num_gb, seed=122, randomise_bn=True)
+        model = make_model(wts, use_pose, learn_graph, split=split, num_gb=num_gb)
+        ref, _, nodes_ref = ohead.head_forward(x1, x2, adj, wts, S=S, num_gb=num_gb, use_pose=use_pose,
+                                               learn_graph=learn_graph, dtype=torch.float64, return_nodes=True)
+        args = (x1.cuda(), x2.cuda(), adj.cuda() if use_pose else None, S)
+        lib.set_option('head_sub_batch', sub); lib.set_option('overlap_mode', 0)
+        lib.set_option('head_lowrank', 0)
+        with torch.no_grad():
+            base = model.head(*args).cpu()
+        lib.set_option('head_lowrank', 1)
+        for _ in range(2):
+            with torch.no_grad():
+                out, nodes = model.head(*args, return_nodes=True)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out).all())
+        emax, enrm = rel_err(out.cpu(), ref)
+        assert emax < TOL and enrm < TOL, (S, B, num_gb, sub, emax, enrm)
+        nmax, nnrm = rel_err(nodes.cpu(), nodes_ref)
+        assert nmax < TOL and nnrm < TOL, (S, B, num_gb, sub, nmax, nnrm)
+        bmax, _ = rel_err(out.cpu(), base)
+        assert bmax < (1e-4 if split == 1 else 1e-5), (S, B, num_gb, sub, bmax)
 
 
 def test_sub_batched_head_into_preallocated_rows_and_nodes(restore_options):

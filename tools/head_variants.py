@@ -1,5 +1,5 @@
 """Head-pipeline variants on one resident input pool (one process, options switched at run time).
-usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split pair psms gsms nhwc call gb)
+usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split pair psms gsms lr nhwc call gb)
 `gb` = number of graph layers of the model (0: pooling + attention only -> the pooling kernels run practically alone).
 `call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
 import json
@@ -13,7 +13,7 @@ import bench
 from agrl.pytorch_b200 import _lib
 
 KEYS = {'sub': 'head_sub_batch', 'tma': 'pool_tma', 'stages': 'pool_stages', 'ctas': 'pool_ctas_per_sm', 'graph': 'graph_variant',
-        'mode': 'overlap_mode', 'hint': 'pool_l2_hint', 'pair': 'gemm_pair', 'psms': 'pool_sms', 'gsms': 'gemm_sms'}
+        'mode': 'overlap_mode', 'hint': 'pool_l2_hint', 'pair': 'gemm_pair', 'psms': 'pool_sms', 'gsms': 'gemm_sms', 'lr': 'head_lowrank'}
 
 
 def main():
