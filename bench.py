@@ -258,6 +258,36 @@ def run_b200(args):
             head_pass()                                  # features of the default mode again (for e2e / result parity)
             barrier()
 
+        # ---- the same head pass with the opt-in low-rank first layer (option head_lowrank; reported beside) -----------
+        lowrank = None
+        if not args.no_lowrank:
+            try:
+                _lib.set_option('head_lowrank', 1)
+                for _ in range(2):
+                    head_pass()
+                torch.cuda.synchronize(dev)      # (no collective inside the guarded block)
+                l0, l1 = ev(), ev()
+                l0.record(stream)
+                for _ in range(args.steps):
+                    head_pass()
+                l1.record(stream)
+                torch.cuda.synchronize(dev)      # (no collective inside the guarded block)
+                low_ms = l0.elapsed_time(l1) / args.steps
+                with _lib.profile(stream.cuda_stream) as lprof:
+                    head_pass()
+                lowrank = dict(head_ms=low_ms, kernels={k: round(t, 4) for k, (n, t) in lprof.totals().items()})
+            except Exception as exc:                     # an extra figure must never cost the bench line
+                lowrank = {'unavailable': '%s: %s' % (type(exc).__name__, exc)}
+            finally:
+                _lib.set_option('head_lowrank', 0)
+            if world > 1:                                # every rank takes part, whatever happened on it
+                t = torch.tensor([lowrank.get('head_ms', -1.0)], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if 'head_ms' in lowrank:
+                    lowrank['head_ms'] = float(t.cpu())
+            head_pass()                                  # features of the default mode again
+            barrier()
+
         # ---- kernel timeline of one more step (CUDA events after every kernel, same stream) ------
         # (every rank runs the pass -- eval_pass holds collectives at N > 1 -- rank 0's timeline is reported)
         barrier()
@@ -352,6 +382,16 @@ def run_b200(args):
                     'tests/test_gpu_head.py); NOT the configuration `value` is measured in',
             'head_ms': fast['head_ms'], 'head_tracklets_per_s_per_gpu': J / (fast['head_ms'] * 1e-3),
             'head_hbm_frac': fgbs / pk['hbm_gbs'], 'kernels_ms': fast['kernels']}
+    if lowrank is not None:
+        if 'head_ms' in lowrank:
+            lgbs = J * BYTES_PER_TRACKLET / (lowrank['head_ms'] * 1e-3) / 1e9
+            lowrank = {'what': 'opt-in head_lowrank=1: the first graph layer runs X.W^T on the 32 quarter-strip rows per tracklet '
+                               '(G.X.W^T = (G.T).(Q.W^T)) and applies G.T afterwards; same fp32-accurate arithmetic class as the '
+                               'default (tests/test_lowrank_layer1.py, test_gpu_head.py::test_lowrank_first_layer_agrees); NOT the '
+                               'configuration `value` is measured in this round',
+                       'head_ms': lowrank['head_ms'], 'head_tracklets_per_s_per_gpu': J / (lowrank['head_ms'] * 1e-3),
+                       'head_hbm_frac': lgbs / pk['hbm_gbs'], 'kernels_ms': lowrank['kernels']}
+        line['lowrank_mode'] = lowrank
     if eager is not None:
         if 'head_ms_per_pass' in eager:
             eager['b200_head_speedup'] = eager['head_ms_per_pass'] / head_ms
@@ -702,6 +742,7 @@ def main():
     ap.add_argument('--sweep-gallery', type=int, default=1000000)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-lowrank', action='store_true', help='skip the extra head pass with the low-rank first layer')
     ap.add_argument('--no-eager', action='store_true', help='skip the stock-PyTorch-on-this-GPU comparator (SURVEY 8d)')
     ap.add_argument('--eager-sample', type=int, default=256, help='tracklets of the pool the comparator head is timed on')
     ap.add_argument('--no-fast-mode', action='store_true', help='skip the extra head pass with the fp16 single-plane GEMM')
