@@ -238,7 +238,7 @@ def test_spatially_partitioned_pipeline_agrees(split, restore_options):
             else:
                 emax, enrm = rel_err(out.cpu(), ref)
                 assert emax < TOL and enrm < TOL, (sub, psms, gsms, stages, emax, enrm)
-                assert rel_err(out.cpu(), base)[0] < 2e-6
+                assert rel_err(out.cpu(), base)[0] < 1e-5     # (CTA pairs do not take the low-rank route, should it be on)
 
 
 @pytest.mark.parametrize('split', [1, 2, 3])
