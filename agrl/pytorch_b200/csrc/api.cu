@@ -87,7 +87,7 @@ static const OptionDef kOptionDefs[kOptCount] = {
     // 1: the FIRST graph layer runs its X.W^T on the quarter-strip rows only (the pooled nodes of a frame are linear
     // combinations of its four quarter strips: G.X.W^T = (G.T).(Q.W^T), 4S GEMM rows per tracklet instead of 7S), then a
     // per-tracklet mixing kernel applies G.T and the layer's epilogue.  Same result to ~1e-7 (tests/test_lowrank_layer1.py).
-    {"head_lowrank", "AGRL_HEAD_LOWRANK", 0, 0, 1},
+    {"head_lowrank", "AGRL_HEAD_LOWRANK", 0, 0, 2},            // 2: graph_mix2_kernel (two channels per thread; unmeasured)
 };
 static std::atomic<int64_t> g_options[kOptCount];
 static std::atomic<int> g_options_init{0};

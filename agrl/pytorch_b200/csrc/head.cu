@@ -1418,6 +1418,61 @@ graph_mix_kernel(MixArgs a) {
     }
 }
 
+// Variant (option head_lowrank = 2, not yet measured): two channels per thread -- every shared-memory broadcast of four
+// G.T weights feeds eight FMAs instead of four -- and the residual rows of eight nodes loaded ahead of their use, so that
+// the row loop is not bound by the latency of one 4-byte load per 36 FMAs.  Same per-element arithmetic order as
+// graph_mix_kernel (k ascending, one fused multiply-add each): bit-identical results.  grid (C / 512, tracklets).
+constexpr int kMixRows = 8;
+__global__ void __launch_bounds__(kHeadThreads, 2)
+graph_mix2_kernel(MixArgs a) {
+    __shared__ __align__(16) float s_gt[kMaxNodes * kMixLd];
+    const int b = blockIdx.y, c = (blockIdx.x * kHeadThreads + threadIdx.x) * 2;
+    const int V = a.V, S4 = a.S4, C = a.C;
+    const float *gt = a.gt + static_cast<size_t>(b) * V * S4;
+    for (int i = threadIdx.x; i < V * kMixLd; i += kHeadThreads) {
+        const int r = i / kMixLd, k = i - r * kMixLd;
+        s_gt[i] = (k < S4) ? gt[r * S4 + k] : 0.f;
+    }
+    float2 z[kMixLd];
+    const float *zc = a.z + static_cast<size_t>(b) * S4 * C + c;
+#pragma unroll
+    for (int k = 0; k < kMixLd; ++k)
+        z[k] = (k < S4) ? __ldg(reinterpret_cast<const float2 *>(zc + static_cast<size_t>(k) * C)) : make_float2(0.f, 0.f);
+    const float2 sc = __ldg(reinterpret_cast<const float2 *>(a.scale + c)), sh = __ldg(reinterpret_cast<const float2 *>(a.shift + c));
+    const float keep = 1.0f - a.gamma;
+    const float *xc = a.x + static_cast<size_t>(b) * V * C + c;
+    float *oc = a.out + static_cast<size_t>(b) * V * C + c;
+    __syncthreads();
+    for (int r0 = 0; r0 < V; r0 += kMixRows) {
+        float2 xin[kMixRows];
+#pragma unroll
+        for (int i = 0; i < kMixRows; ++i)
+            xin[i] = (r0 + i < V) ? __ldg(reinterpret_cast<const float2 *>(xc + static_cast<size_t>(r0 + i) * C)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < kMixRows; ++i) {
+            if (r0 + i < V) {
+                const float4 *g4 = reinterpret_cast<const float4 *>(s_gt + (r0 + i) * kMixLd);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < kMixLd / 4; ++k4) {
+                    const float4 w = g4[k4];
+                    a0 = fmaf(w.x, z[4 * k4 + 0].x, a0); a1 = fmaf(w.x, z[4 * k4 + 0].y, a1);
+                    a0 = fmaf(w.y, z[4 * k4 + 1].x, a0); a1 = fmaf(w.y, z[4 * k4 + 1].y, a1);
+                    a0 = fmaf(w.z, z[4 * k4 + 2].x, a0); a1 = fmaf(w.z, z[4 * k4 + 2].y, a1);
+                    a0 = fmaf(w.w, z[4 * k4 + 3].x, a0); a1 = fmaf(w.w, z[4 * k4 + 3].y, a1);
+                }
+                float h0 = fmaf(a0, sc.x, sh.x), h1 = fmaf(a1, sc.y, sh.y);
+                h0 = h0 >= 0.f ? h0 : h0 * a.slope;
+                h1 = h1 >= 0.f ? h1 : h1 * a.slope;
+                float2 o;
+                o.x = fmaf(a.gamma, h0, keep * xin[i].x);
+                o.y = fmaf(a.gamma, h1, keep * xin[i].y);
+                *reinterpret_cast<float2 *>(oc + static_cast<size_t>(r0 + i) * C) = o;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // temporal attention + part mean + BN neck: one CTA per tracklet
 // ------------------------------------------------------------------------------------------------
@@ -1825,7 +1880,10 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
             if (rc) return rc;
             MixArgs ma{x[cur], z, ga.gt, dst, pr.scale[l], pr.shift[l], V, S4, C, p->gamma, p->leaky_slope};
             AGRL_LAUNCH_BEGIN(st);
-            graph_mix_kernel<<<dim3(C / kHeadThreads, static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
+            if (option(kOptHeadLowrank) >= 2 && C % (2 * kHeadThreads) == 0)
+                graph_mix2_kernel<<<dim3(C / (2 * kHeadThreads), static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
+            else
+                graph_mix_kernel<<<dim3(C / kHeadThreads, static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
             AGRL_LAUNCH_CHECK(st, "graph_mix");
             if (dst == nodes_out) x[cur ^ 1] = nodes_out;
             cur ^= 1;

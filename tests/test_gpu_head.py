@@ -272,6 +272,12 @@ def test_lowrank_first_layer_agrees(split, use_pose, learn_graph, restore_option
         assert nmax < TOL and nnrm < TOL, (S, B, num_gb, sub, nmax, nnrm)
         bmax, _ = rel_err(out.cpu(), base)
         assert bmax < (1e-4 if split == 1 else 1e-5), (S, B, num_gb, sub, bmax)
+        if os.environ.get('AGRL_EXPERIMENTAL'):
+            # head_lowrank = 2 (graph_mix2_kernel, written after the round's GPU budget ended): same arithmetic order
+            lib.set_option('head_lowrank', 2)
+            with torch.no_grad():
+                out2 = model.head(*args)
+            assert torch.equal(out2.cpu(), out.cpu()), (S, B, num_gb, sub)
 
 
 def test_sub_batched_head_into_preallocated_rows_and_nodes(restore_options):
