@@ -77,7 +77,7 @@ static const OptionDef kOptionDefs[kOptCount] = {
     // 1: the tcgen05 GEMMs run as CTA pairs (cta_group::2, 256-row tiles, each CTA loads half of the B tile).
     // Parity-tested; measured SLOWER than one CTA per tile on B200 (24.6 vs 23.3 ms, fp16 plane 19.8 vs 11.9 ms per
     // pass; tensor pipe 68 % vs 79 % active, a third less L2->SM traffic) -- default off, see DESIGN.md
-    {"gemm_pair", "AGRL_GEMM_PAIR", 0, 0, 1},
+    {"gemm_pair", "AGRL_GEMM_PAIR", 0, 0, 2},            // 2: pairs without the relay warp (unmeasured, see gemm_sm100.cuh)
     // Spatial partition of the sub-batched pipeline (free-running mode, overlap_mode = 0): with pool_sms > 0 the
     // poolings of sub-batches 1.. run as ONE wide CTA per SM on pool_sms SMs (two producer/consumer lanes per CTA and
     // a ring that fills the SM's shared memory, so no graph / GEMM CTA can share the SM), while the persistent GEMM

@@ -343,7 +343,7 @@ using EpiGraphLayerF16 = EpiGraphLayerT<true>;
 // ---- the kernel --------------------------------------------------------------------------------
 template <int P, int BN, bool kSplit, class Epi, bool kPair>
 __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const CUtensorMap &map_b,
-                                                int M, int N, int k_pad, const Epi &epi) {
+                                                int M, int N, int k_pad, const Epi &epi, int pair_direct = 0) {
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, kPair>;
     constexpr int kAccCols = Cfg::kAccCols;
     extern __shared__ unsigned char smem_dyn[];
@@ -411,7 +411,26 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                     const uint32_t sb = sa + P * kTileBytesA;
-                    if (kPair) {
+                    if (kPair && pair_direct) {
+                        // direct signalling (gemm_pair = 2, unmeasured): BOTH CTAs' loads complete on the leader's full
+                        // barrier, which expects the bytes of both stages; no relay warp, one wait in the MMA issuer.
+                        // (The peer's bytes may land before the leader's expect_tx of the phase: the transaction count
+                        // goes negative until then, the phase cannot complete before the leader's arrive.)
+                        if (rank == 0) {
+                            const uint32_t full = bar_full + 8 * stage;
+                            mbar_arrive_expect_tx(full, 2 * Cfg::kStageBytes);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kTileBytesA, &map_a, full, kb * BK, m0, p);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::kTileBytesB, &map_b, full, kb * BK, nb, p);
+                        } else {
+                            const uint32_t lfull = mapa_shared(bar_full + 8 * stage, 0);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) tma_load_3d_pair(sa + p * kTileBytesA, &map_a, lfull, kb * BK, m0, p);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) tma_load_3d_pair(sb + p * Cfg::kTileBytesB, &map_b, lfull, kb * BK, nb, p);
+                        }
+                    } else if (kPair) {
                         // every CTA's loads complete on its OWN full barrier (local signalling); the peer's relay warp
                         // forwards "landed" to the leader
                         const uint32_t full = bar_full + 8 * stage;
@@ -433,7 +452,7 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (kPair && warp == 3 && rank == 1) {
+    } else if (kPair && !pair_direct && warp == 3 && rank == 1) {
         // ================= relay (peer CTA): stage landed here -> tell the leader =================
         int stage = 0; uint32_t phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -464,7 +483,7 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 const uint32_t d_corr = kSplit ? d_main + BN : d_main;
                 for (int kb = kb0; kb < kb_end; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
-                    if (kPair) mbar_wait(bar_pfull + 8 * stage, phase);   // ... in the peer CTA too
+                    if (kPair && !pair_direct) mbar_wait(bar_pfull + 8 * stage, phase);   // ... in the peer CTA too
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -656,8 +675,8 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 template <int P, int BN, bool kSplit, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
 pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 int M, int N, int k_pad, Epi epi) {
-    split_gemm_body<P, BN, kSplit, Epi, true>(map_a, map_b, M, N, k_pad, epi);
+                 int M, int N, int k_pad, Epi epi, int pair_direct) {
+    split_gemm_body<P, BN, kSplit, Epi, true>(map_a, map_b, M, N, k_pad, epi, pair_direct);
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -670,7 +689,7 @@ int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, in
 // CTA-pair flavour; map_b must have been built with box_rows = BN / 2.
 template <int P, int BN, bool kSplit, class Epi>
 int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,
-                     const Epi &epi, cudaStream_t st, int max_ctas = 0) {
+                     const Epi &epi, cudaStream_t st, int max_ctas = 0, int pair_direct = 0) {
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, true>;
     static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
     auto kern = pair_gemm_kernel<P, BN, kSplit, Epi>;
@@ -691,7 +710,7 @@ int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, 
     const int tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + BN - 1) / BN);
     int pairs = tiles < max_pairs ? tiles : max_pairs;
     if (max_ctas > 0 && pairs > max_ctas / 2) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;   // the caller's SM partition
-    kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
+    kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi, pair_direct);
     AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;
 }

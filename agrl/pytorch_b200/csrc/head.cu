@@ -1849,6 +1849,7 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
         const int fp16 = p->split == AGRL_SPLIT_FP16X1;
         GraphArgs ga{x[cur], adj, masks, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph, fp16, hwk.y_unscale + b0};
         const bool pair = option(kOptGemmPair) != 0;
+        const int pair_direct = option(kOptGemmPair) >= 2;      // both CTAs' loads signal the leader's barrier
         const int bn = p->split == AGRL_SPLIT_BF16X3 ? 128 : 256;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
         // Low-rank first layer (option head_lowrank): only layer 0 sees nodes that are T.(quarter strips); needs the
@@ -1904,13 +1905,13 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
             gemm::EpiGraphLayerF16 epi16{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
                                          hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
             epi16.row_sumsq = epi.row_sumsq; epi16.sumsq_slots = epi.sumsq_slots;
-            rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas)
+            rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas, pair_direct)
                       : gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas);
         } else if (p->split == AGRL_SPLIT_BF16X3) {
-            rc = pair ? gemm::launch_pair_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas)
+            rc = pair ? gemm::launch_pair_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas, pair_direct)
                       : gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
         } else {
-            rc = pair ? gemm::launch_pair_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas)
+            rc = pair ? gemm::launch_pair_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas, pair_direct)
                       : gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
         }
         if (rc) return rc;
