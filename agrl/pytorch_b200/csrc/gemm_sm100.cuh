@@ -341,9 +341,12 @@ using EpiGraphLayer = EpiGraphLayerT<false>;
 using EpiGraphLayerF16 = EpiGraphLayerT<true>;
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int P, int BN, bool kSplit, class Epi, bool kPair>
+// kPairDirect (pairs only): both CTAs' loads complete on the leader's full barrier instead of going through the peer's
+// relay warp (gemm_pair = 2; compiled as its own instantiation so that the measured relay flavour stays byte-identical)
+template <int P, int BN, bool kSplit, class Epi, bool kPair, bool kPairDirect = false>
 __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const CUtensorMap &map_b,
-                                                int M, int N, int k_pad, const Epi &epi, int pair_direct = 0) {
+                                                int M, int N, int k_pad, const Epi &epi) {
+    constexpr bool pair_direct = kPair && kPairDirect;
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, kPair>;
     constexpr int kAccCols = Cfg::kAccCols;
     extern __shared__ unsigned char smem_dyn[];
@@ -675,8 +678,15 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 template <int P, int BN, bool kSplit, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
 pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 int M, int N, int k_pad, Epi epi, int pair_direct) {
-    split_gemm_body<P, BN, kSplit, Epi, true>(map_a, map_b, M, N, k_pad, epi, pair_direct);
+                 int M, int N, int k_pad, Epi epi) {
+    split_gemm_body<P, BN, kSplit, Epi, true>(map_a, map_b, M, N, k_pad, epi);
+}
+
+template <int P, int BN, bool kSplit, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
+pair_direct_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        int M, int N, int k_pad, Epi epi) {
+    split_gemm_body<P, BN, kSplit, Epi, true, true>(map_a, map_b, M, N, k_pad, epi);
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -693,7 +703,9 @@ int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, 
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, true>;
     static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
     auto kern = pair_gemm_kernel<P, BN, kSplit, Epi>;
+    auto kern_direct = pair_direct_gemm_kernel<P, BN, kSplit, Epi>;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (pair_direct) AGRL_CUDA_TRY(cudaFuncSetAttribute(kern_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     // persistent grid = the number of CTA pairs that can be resident at once (a GPC with an odd SM left over
     // hosts no pair there), asked once per kernel
     static const int max_pairs = [&] {
@@ -710,7 +722,8 @@ int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, 
     const int tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + BN - 1) / BN);
     int pairs = tiles < max_pairs ? tiles : max_pairs;
     if (max_ctas > 0 && pairs > max_ctas / 2) pairs = max_ctas / 2 > 0 ? max_ctas / 2 : 1;   // the caller's SM partition
-    kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi, pair_direct);
+    if (pair_direct) kern_direct<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
+    else kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
     AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;
 }
