@@ -564,8 +564,8 @@ def run_e2e(args, model, dev, rank, world, labels):
         dt = float(t.cpu())
     del hx1, hx2, bufs
     return {'value': world * J / dt, 'unit': 'tracklets/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-            'ms_per_step': dt * 1e3, 'steps': steps,
-            'note': 'layer4 maps start in pinned host memory (16.8 MB/tracklet over PCIe); eval via CPU-tensor / numpy API'}
+            'ms_per_step': dt * 1e3, 'steps': steps, 'h2d_gb_per_s': h2d / dt / 1e9,
+            'note': 'layer4 maps start in pinned host memory (16.8 MB/tracklet over PCIe: the step is bound by the host link, see h2d_gb_per_s); eval via CPU-tensor / numpy API'}
 
 
 # ------------------------------------------------------------------------------------------------
