@@ -229,7 +229,7 @@ def test_spatially_partitioned_pipeline_agrees(split, restore_options):
         lib.set_option('pool_stages', stages)
         # pair: CTA-pair GEMMs + pooling CTAs launched as clusters of two; 2 = pairs without the relay warp (written after
         # the round's GPU budget ended: run it under a timeout first)
-        for pair in ((0, 1, 2) if os.environ.get('AGRL_EXPERIMENTAL') else (0, 1)):
+        for pair in ((0, 1, 2) if 'pair2' in os.environ.get('AGRL_EXPERIMENTAL', '') else (0, 1)):
             lib.set_option('gemm_pair', pair)
             for _ in range(2):
                 with torch.no_grad():
@@ -274,7 +274,7 @@ def test_lowrank_first_layer_agrees(split, use_pose, learn_graph, restore_option
         assert nmax < TOL and nnrm < TOL, (S, B, num_gb, sub, nmax, nnrm)
         bmax, _ = rel_err(out.cpu(), base)
         assert bmax < (1e-4 if split == 1 else 1e-5), (S, B, num_gb, sub, bmax)
-        if os.environ.get('AGRL_EXPERIMENTAL'):
+        if 'mix2' in os.environ.get('AGRL_EXPERIMENTAL', ''):
             # head_lowrank = 2 (graph_mix2_kernel, written after the round's GPU budget ended): same arithmetic order
             lib.set_option('head_lowrank', 2)
             with torch.no_grad():

@@ -9,7 +9,7 @@
 set -u
 mkdir -p gpurun_out
 (AGRL_HEAD_LOWRANK=1 timeout 150 python -m pytest tests -m gpu -q > gpurun_out/pytest_lowrank_default.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_lowrank_default.log)
-(AGRL_EXPERIMENTAL=1 timeout 90 python -m pytest tests/test_gpu_head.py -q -k "lowrank or spatially" > gpurun_out/pytest_experimental.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_experimental.log)
+(AGRL_EXPERIMENTAL=mix2 timeout 90 python -m pytest tests/test_gpu_head.py -q -k "lowrank" > gpurun_out/pytest_experimental.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_experimental.log)
 HV_CLOCKS=1 HV_REPS=10 timeout 120 python tools/head_variants.py 1764 \
   "split=2" "split=2,lr=1" "split=2,lr=2" "split=2,pair=1" "split=2,lr=1,call=882" "split=2,lr=2,call=882" \
   "split=1" "split=1,lr=1" "split=1,lr=2" "split=1,pair=1" \
@@ -19,5 +19,6 @@ echo "rc=$?" >> gpurun_out/round2_first.err
 HV_REPS=5 timeout 40 python tools/head_variants.py 882 "split=2,pair=2" "split=1,pair=2" \
   > gpurun_out/round2_pair_direct.log 2> gpurun_out/round2_pair_direct.err
 echo "rc=$?" >> gpurun_out/round2_pair_direct.err
-tail -n 5 gpurun_out/pytest_lowrank_default.log gpurun_out/pytest_experimental.log gpurun_out/round2_first.err gpurun_out/round2_pair_direct.err
+(AGRL_EXPERIMENTAL=pair2 timeout 60 python -m pytest tests/test_gpu_head.py -q -k "spatially" > gpurun_out/pytest_pair_direct.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_pair_direct.log)
+tail -n 5 gpurun_out/pytest_lowrank_default.log gpurun_out/pytest_experimental.log gpurun_out/round2_first.err gpurun_out/round2_pair_direct.err gpurun_out/pytest_pair_direct.log
 cat gpurun_out/round2_first.log gpurun_out/round2_pair_direct.log
