@@ -9,6 +9,13 @@ labels go up and ``max_rank + 1`` numbers (or, with ``return_distmat``, the matr
 its options from a module-global ``args``; here they are keyword arguments with the same names (``test_sample``,
 ``dist_metric``, ``re_rank``), or an ``args`` namespace carrying them.
 
+Several GPUs: with ``torch.distributed`` initialised (one process per GPU) every rank passes the
+loader of ITS gallery shard -- contiguous shards in rank order, e.g. ``sharded.shard_bounds`` -- and the query loader
+(rank 0's query features are the ones used); the head runs on each rank's own tracklets without any collective and the
+ranking is the gallery-sharded one of ``sharded.evaluate_mars_sharded`` (per-rank distance block and top-``max_rank``,
+one all-gather + one all-reduce, merge).  Every rank returns the same ``(cmc[0], mAP)``, bit-identical to the
+single-GPU result.  Re-ranking needs the whole gallery on one device and is refused in that mode.
+
 There is no CPU path: ``use_gpu=False`` raises, as every other entry of this package does without a B200.
 """
 import time
@@ -16,7 +23,7 @@ import time
 import numpy as np
 import torch
 
-from . import metrics
+from . import metrics, sharded
 from .models import pool_clips
 from .utils.re_ranking import re_ranking_dev
 
@@ -71,8 +78,18 @@ def extract_features(model, loader, pool='avg', test_sample='evenly', device=Non
     return feats, np.asarray(pids_all), np.asarray(camids_all), spent, batches, batch_imgs
 
 
+def _report(say, cmc, mAP, ranks):
+    say("Results ----------")
+    say("mAP: {:.2%}".format(mAP))
+    say("CMC curve")
+    for r in ranks:
+        say("Rank-{:<3}: {:.2%}".format(r, cmc[r - 1]))
+    say("------------------")
+
+
 def test(model, queryloader, galleryloader, pool='avg', use_gpu=True, ranks=(1, 5, 10, 20), return_distmat=False,
-         test_sample='evenly', dist_metric='euclidean', re_rank=False, max_rank=50, args=None, verbose=True):
+         test_sample='evenly', dist_metric='euclidean', re_rank=False, max_rank=50, args=None, verbose=True,
+         group=None, sharded_ops=None):
     """Drop-in for the reference's test(): returns ``(cmc[0], mAP)``, or the (num_query, num_gallery) distance
     matrix as a numpy array with ``return_distmat``.  Raises what the reference raises: ``ZeroDivisionError`` for a
     query without a cross-camera match (rank.py:203), ``ValueError`` for an unknown metric (distance.py:50-54)."""
@@ -82,7 +99,12 @@ def test(model, queryloader, galleryloader, pool='avg', use_gpu=True, ranks=(1, 
         test_sample = getattr(args, 'test_sample', test_sample)
         dist_metric = getattr(args, 'dist_metric', dist_metric)
         re_rank = getattr(args, 're_rank', re_rank)
+    world = torch.distributed.get_world_size(group) if torch.distributed.is_initialized() else 1
+    if world > 1 and torch.distributed.get_rank(group) != 0:
+        verbose = False                                   # one copy of the progress lines
     say = print if verbose else (lambda *a, **k: None)
+    if world > 1 and re_rank:
+        raise NotImplementedError('re-ranking needs the whole gallery on one device; run it on one GPU')
 
     model.eval()
     with torch.no_grad():
@@ -93,6 +115,16 @@ def test(model, queryloader, galleryloader, pool='avg', use_gpu=True, ranks=(1, 
     say("==> BatchTime(s)/BatchSize(img): {:.3f}/{}".format((tq + tg) / max(nq + ng, 1), max(bq, bg)))
 
     say('Computing distance matrix with metric={} ...'.format(dist_metric))
+    if world > 1:
+        # gallery-sharded: this rank's distance block + top-max_rank, merged over the ranks (sharded.py)
+        say("Computing CMC and mAP")
+        if return_distmat:
+            ops = sharded_ops or sharded.CudaOps()
+            return ops.distance(qf, gf, dist_metric).cpu().numpy()      # this rank's (num_q, num_g_local) block
+        cmc, mAP = sharded.evaluate_mars_sharded(qf, gf, q_pids, g_pids, q_camids, g_camids, metric=dist_metric,
+                                                 max_rank=max_rank, group=group, ops=sharded_ops)
+        _report(say, cmc, mAP, ranks)
+        return cmc[0], mAP
     distmat = metrics.compute_distance_matrix(qf, gf, dist_metric)
 
     if re_rank:
@@ -105,12 +137,7 @@ def test(model, queryloader, galleryloader, pool='avg', use_gpu=True, ranks=(1, 
     cmc, mAP = metrics.evaluate_rank(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=max_rank,
                                      use_metric_mars=True)
 
-    say("Results ----------")
-    say("mAP: {:.2%}".format(mAP))
-    say("CMC curve")
-    for r in ranks:
-        say("Rank-{:<3}: {:.2%}".format(r, cmc[r - 1]))
-    say("------------------")
+    _report(say, cmc, mAP, ranks)
 
     if return_distmat:
         return distmat.cpu().numpy() if isinstance(distmat, torch.Tensor) else distmat
