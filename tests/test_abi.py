@@ -78,3 +78,18 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
                 assert 'oracle/' not in text and 'liboracle' not in text, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch / CUDA types in the signatures)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'abi.c'
+    src.write_text('#include "agrl_b200.h"\nint main(void) { return agrl_abi_version() == 0; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', inc, '-c', str(src), '-o',
+                        str(tmp_path / 'abi.o')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
