@@ -1,0 +1,130 @@
+"""Control flow of bench.py's B200 arm with every device call replaced by a stand-in (no GPU): all the extra figures
+(fast mode, low-rank mode, tuned mode, stock-PyTorch comparator switched off here) are assembled into ONE JSON line
+with the keys the contract names, the options they switch are restored, and a failure inside an extra figure is
+reported as `unavailable` instead of costing the line."""
+import json
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import bench
+from agrl.pytorch_b200 import _lib, metrics
+
+
+class FakeEvent(object):
+    clock = [0.0]
+
+    def __init__(self, enable_timing=True):
+        self.t = None
+
+    def record(self, stream=None):
+        FakeEvent.clock[0] += 1.0
+        self.t = FakeEvent.clock[0]
+
+    def elapsed_time(self, other):
+        return 10.0 * (other.t - self.t)
+
+
+class FakeProfile(object):
+    def __init__(self, stream):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def totals(self):
+        return {'pool': (13, 29.0), 'gemm_graph_layer': (26, 23.0), 'graph': (26, 11.0), 'attn': (13, 1.0),
+                'gemm_distance': (1, 0.7), 'rank_mars': (1, 0.3)}
+
+
+class FakeModel(object):
+    def __init__(self, fail_when=None):
+        self.head_split = _lib.SPLIT_BF16X2
+        self.calls = []
+        self.fail_when = fail_when
+
+    def head(self, x1, x2, adj, S, out=None):
+        state = (self.head_split, _lib.get_option('head_lowrank'), _lib.get_option('pool_sms'))
+        if self.fail_when is not None and self.fail_when(state):
+            raise RuntimeError('injected failure')
+        self.calls.append(state + (adj.shape[0],))
+        out.zero_()
+        return out
+
+
+@pytest.fixture
+def fake_device(monkeypatch):
+    cpu = torch.device('cpu')
+    real_device = torch.device
+    monkeypatch.setattr(bench.torch, 'device', lambda *a, **k: cpu if a and a[0] == 'cuda' else real_device(*a, **k))
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    monkeypatch.setattr(torch.cuda, 'Event', FakeEvent)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda d=None: None)
+    monkeypatch.setattr(torch.cuda, 'empty_cache', lambda: None)
+    monkeypatch.setattr(_lib, 'require_device', lambda: None)
+    monkeypatch.setattr(_lib, 'launch_count', lambda: 0)
+    monkeypatch.setattr(_lib, 'profile', FakeProfile)
+    monkeypatch.setattr(bench, 'make_pool', lambda n, dev, seed, pinned=False: (
+        torch.zeros(n * bench.S, 1), torch.zeros(n * bench.S, 1), torch.zeros(n, 1)))
+    monkeypatch.setattr(bench, 'C', 4)
+    monkeypatch.setattr(metrics, 'compute_distance_matrix', lambda a, b, m='euclidean': torch.zeros(a.shape[0], b.shape[0]))
+    monkeypatch.setattr(metrics, 'evaluate_rank', lambda *a, **k: (np.ones(50), np.float64(0.5)))
+
+    class Sampler(object):
+        def __init__(self, i):
+            pass
+
+        def start(self):
+            pass
+
+        def stop(self):
+            return dict(sm_mhz=1700.0, sm_max_mhz=1965.0, reasons=['sw_power_cap'], samples=3, power_w=990.0)
+    monkeypatch.setattr(bench, 'ClockSampler', Sampler)
+    saved = {k: _lib.get_option(k) for k in ('head_lowrank', 'head_sub_batch', 'overlap_mode', 'pool_sms', 'pool_stages')}
+    yield
+    for k, v in saved.items():
+        assert _lib.get_option(k) == v, 'bench must restore option %s' % k
+
+
+def run(monkeypatch, capsys, model, argv=()):
+    monkeypatch.setattr(bench, 'make_model', lambda dev, w: model)
+    monkeypatch.setattr(bench.sys, 'argv', ['bench.py', '--steps', '2', '--no-e2e', '--no-cpu-baseline', '--no-eager'] + list(argv))
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    return json.loads(lines[0])
+
+
+def test_b200_arm_line_and_extra_figures(fake_device, monkeypatch, capsys):
+    model = FakeModel()
+    line = run(monkeypatch, capsys, model)
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'kernels', 'gpu_launches', 'clocks', 'head_hbm',
+                'fast_mode', 'lowrank_mode', 'tuned_fast_mode'):
+        assert key in line, key
+    assert line['steps'] == 2 and line['warmup'] == 3 and line['n_gpus'] == 1 and line['clocks']['power_w'] == 990.0
+    assert line['roofline']['kernel'] == 'pool' and line['roofline']['bound'] == 'hbm'
+    assert 'head_ms' in line['lowrank_mode'] and 'head_hbm_frac' in line['lowrank_mode']
+    assert line['tuned_fast_mode']['call_tracklets'] == 2 * 882 and line['tuned_fast_mode']['options']['pool_sms'] == 64
+    # what the head was called with: default, fp16 plane, low-rank, everything at once on double-size calls -- and the
+    # last passes (kernel timeline) are in the default configuration again
+    states = set(c[:3] for c in model.calls)
+    assert (_lib.SPLIT_BF16X2, 0, 0) in states and (_lib.SPLIT_FP16X1, 0, 0) in states
+    assert (_lib.SPLIT_BF16X2, 1, 0) in states and (_lib.SPLIT_FP16X1, 1, 64) in states
+    assert model.calls[-1][:3] == (_lib.SPLIT_BF16X2, 0, 0) and model.head_split == _lib.SPLIT_BF16X2
+    assert max(c[3] for c in model.calls if c[2] == 64) == 1764
+
+
+def test_a_failing_extra_figure_does_not_cost_the_line(fake_device, monkeypatch, capsys):
+    model = FakeModel(fail_when=lambda st: st[1] == 1)            # anything with the low-rank option on raises
+    line = run(monkeypatch, capsys, model)
+    assert 'injected failure' in line['lowrank_mode']['unavailable']
+    assert 'injected failure' in line['tuned_fast_mode']['unavailable']
+    assert line['value'] > 0 and 'head_ms' in line['fast_mode']
+    assert model.head_split == _lib.SPLIT_BF16X2
