@@ -53,6 +53,12 @@ def gemm_variants(y, w):
     ry8, y8 = q8(ry, True), q8(y64, True)
     rw8, w8 = q8(rw, False), q8(w64, False)
     out['fp16 + 2x e4m3 corrections (2 pass-equivalents)'] = yh @ wh.t() + ry8 @ w8.t() + y8 @ rw8.t()
+    # the same with scales TIED to the fp16 product's (so that all three products can share one TMEM accumulator):
+    # residuals x 2^6, full operands x 2^-6 on top of the fp16 scaling (max 2^14 -> 2^8 <= 448, half-ulp 2^2 -> 2^8)
+    def q8_tied(t, s, shift):
+        return rnd((t * s * 2.0 ** shift).float(), f8) / (s * 2.0 ** shift)
+    out['same, scales tied to the fp16 product (one accumulator)'] = (
+        yh @ wh.t() + q8_tied(ry, sy, 6) @ q8_tied(w64, sw, -6).t() + q8_tied(y64, sy, -6) @ q8_tied(rw, sw, 6).t())
     return out
 
 
