@@ -87,7 +87,9 @@ static const OptionDef kOptionDefs[kOptCount] = {
     // 1: the FIRST graph layer runs its X.W^T on the quarter-strip rows only (the pooled nodes of a frame are linear
     // combinations of its four quarter strips: G.X.W^T = (G.T).(Q.W^T), 4S GEMM rows per tracklet instead of 7S), then a
     // per-tracklet mixing kernel applies G.T and the layer's epilogue.  Same result to ~1e-7 (tests/test_lowrank_layer1.py).
-    {"head_lowrank", "AGRL_HEAD_LOWRANK", 0, 0, 2},            // 2: graph_mix2_kernel (two channels per thread; unmeasured)
+    // Default since round 2: whole GPU suite green with it, 64.8 -> 60.3 ms per 11310-tracklet pass (profiles/r2/first_call.log).
+    // 2: graph_mix2_kernel (two channels per thread, bit-identical to 1 and 0.6 ms faster per pass); 0: off
+    {"head_lowrank", "AGRL_HEAD_LOWRANK", 2, 0, 2},
 };
 static std::atomic<int64_t> g_options[kOptCount];
 static std::atomic<int> g_options_init{0};
@@ -268,7 +270,9 @@ extern "C" int agrl_rank_market1501_host(const float *distmat, const int64_t *q_
                                       reinterpret_cast<float *>(d_out + off_ap),
                                       reinterpret_cast<int64_t *>(d_out + off_nv),
                                       reinterpret_cast<uint32_t *>(d_out + off_st), ws, wsb, st));
-    char small[16];
+    // [map f32][status u32][pad to 8][num_valid i64]: 16 bytes when off_map is a multiple of 8, 20 when rank_len is odd
+    char small[24];
+    if (off_ap - off_map > sizeof(small)) return AGRL_E_INVALID;
     AGRL_CUDA_TRY(cudaMemcpyAsync(cmc, d_out, sizeof(float) * rank_len, cudaMemcpyDeviceToHost, st));
     AGRL_CUDA_TRY(cudaMemcpyAsync(small, d_out + off_map, off_ap - off_map, cudaMemcpyDeviceToHost, st));
     if (all_ap) AGRL_CUDA_TRY(cudaMemcpyAsync(all_ap, d_out + off_ap, sizeof(float) * num_q, cudaMemcpyDeviceToHost, st));

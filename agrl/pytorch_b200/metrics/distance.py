@@ -15,10 +15,13 @@ _ws_cache = {}
 
 
 def _workspace(dev, nbytes):
-    ws = _ws_cache.get(dev)
+    """Operand-plane scratch, one buffer per (device, stream): two streams (or DataParallel threads) working on the same
+    device never share planes, and a buffer is only ever reused / released in the order of the stream that uses it."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _ws_cache[dev] = ws
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)       # allocated on (and tied to) the current stream
+        _ws_cache[key] = ws
     return ws
 
 

@@ -131,9 +131,8 @@ class VMGN(nn.Module):
         _init_neck(self.att_bottleneck, self.att_classifier)
 
         self.head_split = head_split
-        self._prep_key = None            # what the cached prepared buffer was built from
-        self._prep_buf = None
-        self._ws = None
+        self._prep = {}                  # device -> (key, prepared buffer): what the cached buffer was built from
+        self._ws = {}                    # (device, stream) -> workspace
 
     # -- weights ---------------------------------------------------------------------------------
     def _load_imagenet(self):
@@ -162,9 +161,12 @@ class VMGN(nn.Module):
         P.use_pose, P.learn_graph = int(self.use_pose), int(self.learn_graph)
         P.gamma = self.graph_layers[0].gamma if self.num_gb else 0.1
         P.leaky_slope, P.bn_eps, P.split = 0.1, 1e-5, self.head_split
-        tensors = []
+        tensors, key = [], []
 
         def ptr(t):
+            # the cache key describes the module's OWN parameter / buffer (a converted temporary has _version 0 and an
+            # address the allocator may recycle: it cannot tell a reloaded weight from the old one)
+            key.append((id(t), t.data_ptr(), t._version, t.dtype))
             t = t.detach()
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
@@ -177,18 +179,24 @@ class VMGN(nn.Module):
             P.bn_mean[i], P.bn_var[i] = ptr(gl.bn.running_mean), ptr(gl.bn.running_var)
         for dst, bn in ((P.global_bn, self.global_bottleneck), (P.att_bn, self.att_bottleneck)):
             dst[0], dst[1], dst[2], dst[3] = ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var)
-        return P, tensors
+        return P, tensors, tuple(key)
 
-    def _prepared(self, lib, P, tensors, dev, stream):
-        key = (dev, self.head_split) + tuple((t.data_ptr(), t._version) for t in tensors)
-        if key != self._prep_key:
+    def _prepared(self, lib, P, key, dev, stream):
+        """bf16 planes of W + folded BN, rebuilt when a parameter is replaced or modified in place.  nn.DataParallel
+        replicas are rebuilt on every forward (fresh tensors at possibly recycled addresses), so a replica never trusts a
+        cached buffer: one process per GPU (or one module per device) is the supported way to scale."""
+        key = (self.head_split,) + key
+        hit = self._prep.get(dev)
+        if hit is None or hit[0] != key or getattr(self, '_is_replica', False):
             nbytes = lib.agrl_head_prepared_bytes(ctypes.byref(P))
             if nbytes == 0:
                 _lib.check(_lib.E_UNSUPPORTED)
             buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.check(lib.agrl_head_prepare_dev(ctypes.byref(P), buf.data_ptr(), nbytes, stream))
-            self._prep_key, self._prep_buf = key, buf
-        return self._prep_buf
+            hit = (key, buf)
+            if not getattr(self, '_is_replica', False):
+                self._prep[dev] = hit
+        return hit[1]
 
     def head(self, x4_1, x4_2, adj, seq_len, return_nodes=False, out=None):
         """vmgn.py:296-321 on the GPU: (B*S,C,h,w) x2 + (B,V,V) -> (B, 2C).
@@ -225,12 +233,13 @@ class VMGN(nn.Module):
                 adj = adj.to(device=dev, dtype=torch.float32).contiguous()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            P, tensors = self._head_params()
+            P, tensors, key = self._head_params()
             P.maps_nhwc = int(nhwc)
-            prepared = self._prepared(lib, P, tensors, dev, stream)
+            prepared = self._prepared(lib, P, key, dev, stream)
             wsb = lib.agrl_head_workspace_bytes(ctypes.byref(P), B, seq_len)
-            if self._ws is None or self._ws.device != dev or self._ws.numel() < wsb:
-                self._ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            ws = self._ws.get((dev, stream))                         # one workspace per (device, stream)
+            if ws is None or ws.numel() < wsb:
+                ws = self._ws[(dev, stream)] = torch.empty(wsb, dtype=torch.uint8, device=dev)
             if out is None:
                 out = torch.empty(B, 2 * C, dtype=torch.float32, device=dev)
             else:
@@ -242,7 +251,7 @@ class VMGN(nn.Module):
                 ctypes.byref(P), prepared.data_ptr(), x4_1.data_ptr(), x4_2.data_ptr(),
                 adj.data_ptr() if self.use_pose else None, out.data_ptr(), out.stride(0),
                 nodes.data_ptr() if return_nodes else None, B, seq_len, h, w,
-                self._ws.data_ptr(), wsb, stream))
+                ws.data_ptr(), wsb, stream))
         return (out, nodes) if return_nodes else out
 
     def forward_clips(self, imgs, adj, pool='avg'):

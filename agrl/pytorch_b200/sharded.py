@@ -37,12 +37,14 @@ class CudaOps(object):
     def __init__(self, split=_lib.SPLIT_BF16X3):
         self.lib = _lib.require_device()
         self.split = split
-        self._ws = None
+        self._ws = {}
 
     def _workspace(self, dev, nbytes):
-        if self._ws is None or self._ws.device != dev or self._ws.numel() < nbytes:
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        return self._ws
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)       # never shared between streams
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return ws
 
     def distance(self, qf, gf, metric):
         from .metrics import compute_distance_matrix
@@ -194,7 +196,7 @@ def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids
         dist.all_gather_into_tensor(cls_all, cls, group=group)
         keys_all, cls_all = keys_all.view(world, nq, max_rank), cls_all.view(world, nq, max_rank)
         dist.all_reduce(ngood, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(status, op=dist.ReduceOp.BOR, group=group)   # status words are bit flags
     else:
         keys_all, cls_all = keys.unsqueeze(0), cls.unsqueeze(0)
     return ops.merge(keys_all, cls_all, ngood, max_rank, status)
@@ -236,14 +238,14 @@ def evaluate_market1501_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_
 
     d = ops.distance(qf, gf_local, metric)
     keys, counts, st2 = ops.market_gather(d, qp, gp, qc, gc, offset, cap)
-    status = torch.maximum(status, st2)
+    status = torch.bitwise_or(status, st2)
     nq = keys.shape[0]
     if world > 1:
         keys_all = torch.empty((world * nq, cap), dtype=keys.dtype, device=dev)
         dist.all_gather_into_tensor(keys_all, keys, group=group)
         keys_all = keys_all.view(world, nq, cap)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(status, op=dist.ReduceOp.BOR, group=group)   # status words are bit flags
     else:
         keys_all = keys.unsqueeze(0)
     cnt, srt = ops.market_bin(d, offset, keys_all)
