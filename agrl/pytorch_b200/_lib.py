@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libagrl_b200.so')
 OK = 0
 E_INVALID, E_NO_DEVICE, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 E_NO_VALID_QUERY, E_ZERO_DIVISION, E_LABEL_RANGE = -6, -7, -8
-ST_NO_VALID_QUERY, ST_ZERO_DIVISION, ST_LABEL_RANGE = 1, 2, 4
+ST_NO_VALID_QUERY, ST_ZERO_DIVISION, ST_LABEL_RANGE, ST_TOPK_OVERFLOW = 1, 2, 4, 8
 METRIC_EUCLIDEAN, METRIC_COSINE = 0, 1
 SPLIT_BF16X3, SPLIT_BF16X2, SPLIT_FP16X1 = 3, 2, 1
 CLIP_POOL_AVG, CLIP_POOL_MAX = 0, 1
@@ -73,6 +73,11 @@ _SIGNATURES = {
     'agrl_distance_prepare_operand_dev': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_sz, c_vp]),
     'agrl_distance_prepared_dev': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
     'agrl_distance_host': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int]),
+    'agrl_distance_topk_workspace_bytes': (c_sz, [c_i64]),
+    'agrl_distance_topk_dev': (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'agrl_rank_mars_classify_workspace_bytes': (c_sz, [c_i64, c_i64]),
+    'agrl_rank_mars_classify_dev': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp,
+                                            c_vp, c_sz, c_vp]),
     'agrl_pose_part_masks_dev': (c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, ctypes.c_double, c_vp, c_vp]),
     'agrl_pose_adjacency_dev': (c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'agrl_head_forward_compact_dev': (c_int, [ctypes.POINTER(HeadParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,

@@ -222,6 +222,7 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
     static constexpr bool kF16 = false;
     static constexpr bool kDirect = false;      // rows of arbitrary alignment: coalesce through smem
     static constexpr int kChunkKb = 4;          // drain the accumulator every 256 k (fp32-accurate sums)
+    static constexpr bool kRowwise = false;
     const float *qn, *gn;       // squared norms (euclidean); unused for cosine
     float *out;
     int64_t ld;
@@ -238,6 +239,47 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
     }
 };
 
+// Distance -> per-query top-k candidates, fused (the num_q x num_g matrix is never written).  Same
+// accumulation and the same final expression as EpiDistance, so every distance has the bits the matrix would hold; the
+// thread that owns (row, 64 columns) turns them into ranking keys (order-preserving distance bits << 32 | GLOBAL gallery
+// index) and appends the ones below the row's threshold -- the K-th smallest key of the columns seen by earlier
+// launches -- to the row's candidate list.  Launches cover growing column ranges; topk_compact_kernel (distance.cu) cuts
+// each list back to its K smallest keys and tightens the threshold in between, so after the first few thousand columns
+// only ~K ln(growth) candidates per row and launch pass the filter.
+struct EpiTopK {
+    static constexpr const char *kName = "gemm_distance_topk";
+    static constexpr bool kF16 = false;
+    static constexpr bool kDirect = false;
+    static constexpr int kChunkKb = 4;
+    static constexpr bool kRowwise = true;
+    const float *qn, *gn;               // squared norms (euclidean), gn already offset to this launch's first column
+    int metric;
+    const unsigned long long *tau;      // [M] threshold key per row (all-ones: accept everything)
+    unsigned int *cnt;                  // [M] candidates appended so far (may run past `cap`: overflow, detected later)
+    unsigned long long *cand;           // [M][cap]
+    int cap;
+    uint32_t idx_base;                  // global gallery index of this launch's column 0
+    __device__ __forceinline__ void consume(int row, int col0, int n_cols, const float (&sum)[64]) const {
+        const unsigned long long t = tau[row];
+        const float q = (metric == AGRL_METRIC_EUCLIDEAN) ? __ldg(qn + row) : 0.f;
+        unsigned long long *list = cand + static_cast<size_t>(row) * cap;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const int col = col0 + j;
+            if (col < n_cols) {
+                float v;
+                if (metric == AGRL_METRIC_EUCLIDEAN) v = fmaf(-2.0f, sum[j], __fadd_rn(q, __ldg(gn + col)));
+                else v = 1.0f - sum[j];
+                const unsigned long long key = rank_key(v, idx_base + static_cast<uint32_t>(col));
+                if (key < t) {
+                    const unsigned int slot = atomicAdd(cnt + row, 1u);
+                    if (slot < static_cast<unsigned int>(cap)) list[slot] = key;
+                }
+            }
+        }
+    }
+};
+
 // kScaled: single-plane fp16 operands (AGRL_SPLIT_FP16X1).  Both operands were multiplied by powers of two to sit
 // in the middle of the fp16 range (per tracklet for Y, per layer for W); the epilogue undoes that exactly.
 template <bool kScaled>
@@ -246,6 +288,7 @@ struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) +
     static constexpr bool kF16 = kScaled;
     static constexpr bool kDirect = true;       // C % 4 == 0 and 16-byte aligned rows: vector accesses
     static constexpr int kChunkKb = 0;          // one accumulation over all of K
+    static constexpr bool kRowwise = false;
     // pull this thread's slice of the residual row into L2 before the accumulator is ready
     __device__ __forceinline__ void prefetch(int row, int col0, int ncols, bool valid) const {
         if (!valid) return;
@@ -315,6 +358,7 @@ struct EpiPlainT {
     static constexpr bool kF16 = kScaled;
     static constexpr bool kDirect = true;
     static constexpr int kChunkKb = 0;
+    static constexpr bool kRowwise = false;
     float *out; int64_t ldo;
     const float *row_unscale;   // kScaled: 2^-k per tracklet
     const float *w_unscale;     // kScaled: 2^-k of the layer's W
@@ -373,11 +417,20 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
     const int num_kb = k_pad / BK;
     const int chunk_kb = Cfg::kChunk > 0 ? Cfg::kChunk : num_kb;       // k-blocks per accumulator drain
     // Raster: the operand with FEWER tiles varies fastest, so the CTAs running at any moment share it
-    // (L2-resident) while the larger operand streams through exactly once.
+    // (L2-resident) while the larger operand streams through exactly once.  When even the smaller operand is too big
+    // to stay in L2 (10 000 queries x 2048 x 3 planes = 123 MB), its tiles are taken in groups of kGroupM row tiles
+    // (25 MB at K = 2048): the other operand streams once per group.
+    constexpr int kGroupM = 16;
     const bool m_fast = tiles_m <= tiles_n;
+    const int grp_m = tiles_m < kGroupM ? tiles_m : kGroupM;
+    const int full_tiles = (tiles_m / grp_m) * grp_m * tiles_n;      // tiles in complete groups
     auto tile_origin = [&](int tile, int &m0, int &n0) {
-        if (m_fast) { m0 = (tile % tiles_m) * Cfg::kTileM; n0 = (tile / tiles_m) * BN; }
-        else        { n0 = (tile % tiles_n) * BN; m0 = (tile / tiles_n) * Cfg::kTileM; }
+        if (m_fast) {
+            int base_m, gm, r;
+            if (tile < full_tiles) { const int per = grp_m * tiles_n; const int g = tile / per; base_m = g * grp_m; gm = grp_m; r = tile - g * per; }
+            else { base_m = (tiles_m / grp_m) * grp_m; gm = tiles_m - base_m; r = tile - full_tiles; }
+            m0 = (base_m + r % gm) * Cfg::kTileM; n0 = (r / gm) * BN;
+        } else { n0 = (tile % tiles_n) * BN; m0 = (tile / tiles_n) * Cfg::kTileM; }
         m0 += static_cast<int>(rank) * BM;                            // this CTA's 128 rows of the tile
     };
 
@@ -601,22 +654,27 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                     tc_fence_before();
                     if (lane == 0) release_acc(acc);
                 }
-                float *buf = epi_buf + ew * 32 * kEpiPad;
+                if constexpr (Epi::kRowwise) {
+                    static_assert(BN == 128, "row-wise consumers take 64 columns per thread");
+                    if (row_base + lane < M) epi.consume(row_base + lane, n0 + col_half, N, sum);
+                } else {
+                    float *buf = epi_buf + ew * 32 * kEpiPad;
 #pragma unroll
-                for (int c = 0; c < BN / 2; c += 32) {
+                    for (int c = 0; c < BN / 2; c += 32) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) buf[lane * kEpiPad + j] = sum[c + j];
-                    __syncwarp();
-                    const int col = n0 + col_half + c + lane;
-                    if (col < N) {
-                        const typename Epi::Col cs = epi.col_state(col);
+                        for (int j = 0; j < 32; ++j) buf[lane * kEpiPad + j] = sum[c + j];
+                        __syncwarp();
+                        const int col = n0 + col_half + c + lane;
+                        if (col < N) {
+                            const typename Epi::Col cs = epi.col_state(col);
 #pragma unroll 8
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int row = row_base + rr;
-                            if (row < M) epi.store(row, col, buf[rr * kEpiPad + lane], cs);
+                            for (int rr = 0; rr < 32; ++rr) {
+                                const int row = row_base + rr;
+                                if (row < M) epi.store(row, col, buf[rr * kEpiPad + lane], cs);
+                            }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             } else {
                 const int acc = cit & 1;

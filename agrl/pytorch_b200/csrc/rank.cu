@@ -1217,3 +1217,160 @@ extern "C" size_t agrl_rank_market1501_finalize_workspace_bytes(int64_t num_q, i
     if (num_q < 1 || parts < 1 || cap < 1 || max_rank < 1 || parts * cap > 8192) return 0;
     return carve_rank(nullptr, num_q, 0, max_rank).bytes + align_up(static_cast<size_t>(num_q) * market_n2(parts, cap) * 8, 256) + 256;
 }
+
+// ------------------------------------------------------------------------------------------------
+// MARS metric after the fused distance -> top-k (agrl_distance_topk_dev): the candidates' class bytes and the per-query
+// good-image count (rank.py:166-169) from the labels alone.  The count must not cost a pass over num_q x num_g label
+// pairs (10^10 for the retrieval sweep): the queries' identities go into two small open-addressing tables -- by pid and
+// by (pid, camera), slot = index of a representative query -- one pass over the gallery labels counts into them, and
+// good(q) = count[pid_q] - count[pid_q, cam_q].  O(num_q + num_g).
+// ------------------------------------------------------------------------------------------------
+namespace agrl {
+
+struct ClassifyWorkspace {
+    int32_t *q_pid, *q_cam, *g_pid, *g_cam;
+    int32_t *tab_p, *tab_pc, *cnt_p, *cnt_pc;      // [slots] each
+    int slots;
+    size_t bytes;
+};
+
+static ClassifyWorkspace carve_classify(void *ws, int64_t nq, int64_t ng) {
+    Carver c(ws);
+    ClassifyWorkspace w;
+    w.q_pid = c.take<int32_t>(nq); w.q_cam = c.take<int32_t>(nq);
+    w.g_pid = c.take<int32_t>(ng); w.g_cam = c.take<int32_t>(ng);
+    int slots = 64;
+    while (slots < 4 * nq) slots <<= 1;
+    w.slots = slots;
+    w.tab_p = c.take<int32_t>(4 * static_cast<size_t>(slots));      // tab_p | tab_pc | cnt_p | cnt_pc, contiguous
+    w.tab_pc = w.tab_p ? w.tab_p + slots : nullptr;
+    w.cnt_p = w.tab_p ? w.tab_p + 2 * slots : nullptr;
+    w.cnt_pc = w.tab_p ? w.tab_p + 3 * slots : nullptr;
+    w.bytes = c.total();
+    return w;
+}
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t hash_pid_cam(int pid, int cam) {
+    return hash_u32(static_cast<uint32_t>(pid) * 0x9E3779B1U + hash_u32(static_cast<uint32_t>(cam) + 0x85EBCA6BU));
+}
+
+__global__ void classify_insert_kernel(ClassifyWorkspace w, int nq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int pid = w.q_pid[q], cam = w.q_cam[q];
+    const uint32_t mask = static_cast<uint32_t>(w.slots - 1);
+    for (uint32_t h = hash_u32(static_cast<uint32_t>(pid)) & mask;; h = (h + 1) & mask) {
+        const int cur = atomicCAS(&w.tab_p[h], -1, q);
+        if (cur == -1 || w.q_pid[cur] == pid) break;
+    }
+    for (uint32_t h = hash_pid_cam(pid, cam) & mask;; h = (h + 1) & mask) {
+        const int cur = atomicCAS(&w.tab_pc[h], -1, q);
+        if (cur == -1 || (w.q_pid[cur] == pid && w.q_cam[cur] == cam)) break;
+    }
+}
+
+__global__ void classify_count_kernel(ClassifyWorkspace w, int64_t ng) {
+    const uint32_t mask = static_cast<uint32_t>(w.slots - 1);
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < ng;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int pid = w.g_pid[j], cam = w.g_cam[j];
+        for (uint32_t h = hash_u32(static_cast<uint32_t>(pid)) & mask;; h = (h + 1) & mask) {
+            const int cur = w.tab_p[h];
+            if (cur == -1) break;
+            if (w.q_pid[cur] == pid) { atomicAdd(&w.cnt_p[h], 1); break; }
+        }
+        for (uint32_t h = hash_pid_cam(pid, cam) & mask;; h = (h + 1) & mask) {
+            const int cur = w.tab_pc[h];
+            if (cur == -1) break;
+            if (w.q_pid[cur] == pid && w.q_cam[cur] == cam) { atomicAdd(&w.cnt_pc[h], 1); break; }
+        }
+    }
+}
+
+// one thread per (query, slot): class byte of the listed gallery item; thread of slot 0 also looks up the good count
+__global__ void classify_keys_kernel(ClassifyWorkspace w, const uint64_t *__restrict__ keys, int nq, int K, int64_t ng,
+                                     uint32_t index_offset, uint8_t *cls, int32_t *ngood) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= static_cast<int64_t>(nq) * K) return;
+    const int q = static_cast<int>(i / K), n = static_cast<int>(i - static_cast<int64_t>(q) * K);
+    const int pid = w.q_pid[q], cam = w.q_cam[q];
+    const uint64_t key = keys[i];
+    uint8_t c = 0;
+    if (key != kKeyMax) {
+        const int64_t g = static_cast<int64_t>(static_cast<uint32_t>(key)) - index_offset;
+        if (g >= 0 && g < ng) {
+            const int gp = w.g_pid[g], gc = w.g_cam[g];
+            const bool good = (gp == pid) && (gc != cam);
+            const bool junk = (gp == -1) || ((gp == pid) && (gc == cam));
+            c = static_cast<uint8_t>((good ? 1 : 0) | (junk ? 2 : 0));
+        }
+    }
+    cls[i] = c;
+    if (n == 0) {
+        const uint32_t mask = static_cast<uint32_t>(w.slots - 1);
+        int same_pid = 0, same_both = 0;
+        for (uint32_t h = hash_u32(static_cast<uint32_t>(pid)) & mask;; h = (h + 1) & mask) {
+            const int cur = w.tab_p[h];
+            if (cur == -1) break;
+            if (w.q_pid[cur] == pid) { same_pid = w.cnt_p[h]; break; }
+        }
+        for (uint32_t h = hash_pid_cam(pid, cam) & mask;; h = (h + 1) & mask) {
+            const int cur = w.tab_pc[h];
+            if (cur == -1) break;
+            if (w.q_pid[cur] == pid && w.q_cam[cur] == cam) { same_both = w.cnt_pc[h]; break; }
+        }
+        ngood[q] = same_pid - same_both;
+    }
+}
+
+}  // namespace agrl
+
+extern "C" size_t agrl_rank_mars_classify_workspace_bytes(int64_t num_q, int64_t num_g) {
+    if (num_q < 0 || num_g < 0) return 0;
+    return carve_classify(nullptr, num_q, num_g).bytes;
+}
+
+extern "C" int agrl_rank_mars_classify_dev(const uint64_t *keys, const int64_t *q_pids, const int64_t *g_pids,
+                                           const int64_t *q_camids, const int64_t *g_camids,
+                                           int64_t num_q, int64_t num_g, int64_t max_rank, int64_t index_offset,
+                                           uint8_t *cls, int32_t *ngood, uint32_t *status,
+                                           void *ws, size_t ws_bytes, void *stream) {
+    if (!keys || !q_pids || !g_pids || !q_camids || !g_camids || !cls || !ngood || !status) return AGRL_E_INVALID;
+    if (num_q < 1 || num_g < 0 || max_rank < 1 || index_offset < 0) return AGRL_E_INVALID;
+    if (num_q > (1 << 28) || index_offset + num_g > 0xFFFFFFFFll) return AGRL_E_UNSUPPORTED;
+    int rc = agrl_device_ok();
+    if (rc) return rc;
+    ClassifyWorkspace w = carve_classify(ws, num_q, num_g);
+    if (!ws || ws_bytes < w.bytes) return AGRL_E_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LabelArrays la;
+    la.src[0] = q_pids; la.dst[0] = w.q_pid; la.n[0] = num_q;
+    la.src[1] = q_camids; la.dst[1] = w.q_cam; la.n[1] = num_q;
+    la.src[2] = g_pids; la.dst[2] = w.g_pid; la.n[2] = num_g;
+    la.src[3] = g_camids; la.dst[3] = w.g_cam; la.n[3] = num_g;
+    const int64_t nmax = num_q > num_g ? num_q : num_g;
+    int blocks = static_cast<int>((nmax + 255) / 256);
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    narrow_labels_kernel<<<dim3(blocks, 4), 256, 0, st>>>(la, status);
+    AGRL_LAUNCH_CHECK(st, "narrow_labels");
+    AGRL_CUDA_TRY(cudaMemsetAsync(w.tab_p, 0xFF, sizeof(int32_t) * 2 * w.slots, st));       // both tables: empty (-1)
+    AGRL_CUDA_TRY(cudaMemsetAsync(w.cnt_p, 0, sizeof(int32_t) * 2 * w.slots, st));
+    const int nq = static_cast<int>(num_q);
+    classify_insert_kernel<<<(nq + 255) / 256, 256, 0, st>>>(w, nq);
+    AGRL_LAUNCH_CHECK(st, "classify_insert");
+    if (num_g > 0) {
+        int cb = static_cast<int>((num_g + 255) / 256);
+        if (cb > 8 * kNumSMs) cb = 8 * kNumSMs;
+        classify_count_kernel<<<cb, 256, 0, st>>>(w, num_g);
+        AGRL_LAUNCH_CHECK(st, "classify_count");
+    }
+    const int64_t total = num_q * max_rank;
+    classify_keys_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        w, keys, nq, static_cast<int>(max_rank), num_g, static_cast<uint32_t>(index_offset), cls, ngood);
+    AGRL_LAUNCH_CHECK(st, "classify_keys");
+    return AGRL_OK;
+}

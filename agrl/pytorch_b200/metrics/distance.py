@@ -101,6 +101,25 @@ class PreparedOperand(object):
                 nbytes, torch.cuda.current_stream(x.device).cuda_stream))
 
 
+    def rows_view(self, r0, r1):
+        """Rows [r0, r1) as an operand of their own (a copy of those rows' planes and norms; the plane layout
+        [P][rows][K_pad] is not sliceable in place)."""
+        lib = _lib.require_device()
+        k_pad = (self.dim + 63) // 64 * 64
+        n = r1 - r0
+        v = object.__new__(PreparedOperand)
+        v.rows, v.dim, v.metric, v.split, v.device = n, self.dim, self.metric, self.split, self.device
+        nbytes = lib.agrl_distance_operand_bytes(n, self.dim, self.split)
+        v.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        plane_b = self.rows * k_pad * 2
+        src = self.buf[:self.split * plane_b].view(self.split, self.rows, k_pad * 2)
+        v.buf[:self.split * n * k_pad * 2].view(self.split, n, k_pad * 2).copy_(src[:, r0:r1])
+        off_src = (self.split * plane_b + 255) // 256 * 256
+        off_dst = (self.split * n * k_pad * 2 + 255) // 256 * 256
+        v.buf[off_dst:off_dst + 4 * n].copy_(self.buf[off_src + 4 * r0:off_src + 4 * r1])
+        return v
+
+
 def distance_prepared(q, g, out=None):
     """Distance matrix between two PreparedOperand (same metric, split, dim, device)."""
     assert isinstance(q, PreparedOperand) and isinstance(g, PreparedOperand)

@@ -6,8 +6,9 @@ signature (rank.py:215-216), dispatch (:232-238) and return types, computed on t
     neither flag          -> None, like the reference (the function falls off its end)
     use_metric_cuhk03     -> NotImplementedError (random-sampling metric, out of scope)
 
-``use_cython`` is accepted for signature compatibility and ignored: the native evaluator is the
-only implementation here (there is no Python fallback to select).
+``use_cython=False`` selects the reference's float64 numpy evaluator (rank.py:95-150); here it only changes the
+RETURN TYPE of mAP to numpy.float64 as that function has -- the native evaluator is the only implementation
+(there is no Python fallback to select), so the value is rank_cy's fp32-accumulated one (equal to ~1e-9).
 
 Beyond the reference: ``distmat`` may also be a CUDA torch tensor, in which case nothing is copied
 through the host (labels may then be numpy arrays or CUDA int64 tensors).
@@ -50,7 +51,12 @@ def evaluate_rank(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=50, use_
                   use_metric_market1501=False, use_metric_mars=False, use_cython=True):
     """Evaluate CMC and mAP (signature of rank.py:215-216)."""
     if use_metric_market1501 or use_metric_cuhk03:
-        return evaluate_cy(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, use_metric_cuhk03)
+        res = evaluate_cy(distmat, q_pids, g_pids, q_camids, g_camids, max_rank, use_metric_cuhk03)
+        if not use_cython:
+            # rank.py:236 -> eval_market1501 (:95-150) returns (np.float32[max_rank], np.float64); the VALUE here is still the
+            # native evaluator's fp32-accumulated mAP (the float64 numpy path agrees with it to ~1e-9, SURVEY App. A)
+            return res[0], np.float64(res[1])
+        return res
     elif use_metric_mars:
         return evaluate_mars(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
 

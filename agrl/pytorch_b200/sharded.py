@@ -66,6 +66,51 @@ class CudaOps(object):
                 status.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream))
         return keys, cls, ngood, status
 
+    def topk_fused(self, qop, gop, q_pids, g_pids, q_camids, g_camids, max_rank, offset, allow_fallback=True):
+        """Same outputs as ``partial`` from two PreparedOperand, with the distance -> top-k fused into the GEMM epilogue
+        (agrl_distance_topk_dev + agrl_rank_mars_classify_dev): no (num_q x num_g) matrix is allocated.  When a query's
+        candidate list overflows (a gallery ordered by distance to the query) the call falls back to distance blocks +
+        ``partial`` -- the results are the same either way."""
+        from .metrics.distance import _METRICS
+        assert (qop.metric, qop.split, qop.dim, qop.device) == (gop.metric, gop.split, gop.dim, gop.device)
+        dev, nq, ng = qop.device, qop.rows, gop.rows
+        keys = torch.empty(nq, max_rank, dtype=torch.int64, device=dev)
+        cls = torch.empty(nq, max_rank, dtype=torch.uint8, device=dev)
+        ngood = torch.empty(nq, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        lib = self.lib
+        wsb = max(lib.agrl_distance_topk_workspace_bytes(nq), lib.agrl_rank_mars_classify_workspace_bytes(nq, ng))
+        ws = self._workspace(dev, wsb)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.agrl_distance_topk_dev(
+                qop.buf.data_ptr(), nq, gop.buf.data_ptr(), ng, qop.dim, _METRICS[qop.metric], qop.split, max_rank, offset,
+                keys.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, stream))
+            _lib.check(lib.agrl_rank_mars_classify_dev(
+                keys.data_ptr(), q_pids.data_ptr(), g_pids.data_ptr(), q_camids.data_ptr(), g_camids.data_ptr(),
+                nq, ng, max_rank, offset, cls.data_ptr(), ngood.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, stream))
+        if allow_fallback and int(status.cpu()) & _lib.ST_TOPK_OVERFLOW:
+            return self.topk_unfused(qop, gop, q_pids, g_pids, q_camids, g_camids, max_rank, offset)
+        return keys, cls, ngood, status
+
+    def topk_unfused(self, qop, gop, q_pids, g_pids, q_camids, g_camids, max_rank, offset, block_bytes=1 << 31):
+        """distance blocks (at most ``block_bytes`` each) written to HBM + the streaming top-k kernel"""
+        from .metrics.distance import distance_prepared
+        dev, nq, ng = qop.device, qop.rows, gop.rows
+        rows = max(1, min(nq, block_bytes // max(4 * ng, 1)))
+        keys = torch.empty(nq, max_rank, dtype=torch.int64, device=dev)
+        cls = torch.empty(nq, max_rank, dtype=torch.uint8, device=dev)
+        ngood = torch.empty(nq, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        dbuf = torch.empty(rows, ng, device=dev)
+        for q0 in range(0, nq, rows):
+            q1 = min(nq, q0 + rows)
+            dm = distance_prepared(qop.rows_view(q0, q1), gop, out=dbuf[:q1 - q0])
+            k, c, n, st = self.partial(dm, q_pids[q0:q1], g_pids, q_camids[q0:q1], g_camids, max_rank, offset)
+            keys[q0:q1], cls[q0:q1], ngood[q0:q1] = k, c, n
+            status |= st
+        return keys, cls, ngood, status
+
     def merge(self, keys_all, cls_all, ngood, max_rank, status_parts):
         dev = keys_all.device
         parts, nq = keys_all.shape[0], keys_all.shape[1]
@@ -154,13 +199,18 @@ def _as_dev_i64(x, dev):
     return torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.int64)).to(dev)
 
 
+FUSED_MIN_GALLERY = 32768        # gallery rows per shard from which the fused distance -> top-k is the default
+
+
 def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids_local, metric='euclidean',
-                          max_rank=50, group=None, broadcast_queries=True, ops=None):
+                          max_rank=50, group=None, broadcast_queries=True, ops=None, fused=None):
     """MARS-metric CMC/mAP (rank.py:160-212) of ``qf`` against the union of every rank's gallery shard.
 
     qf (num_q, d) and the query labels must be the same on every rank (``broadcast_queries`` copies
     rank 0's); gf_local (num_g_r, d) and its labels are this rank's rows.  Gallery indices are global:
     shard r starts at sum(num_g_0..r-1), which is also how ties are broken (by global index).
+    ``fused``: distance -> top-k in the GEMM epilogue, no (num_q x num_g_r) matrix (default: from FUSED_MIN_GALLERY
+    gallery rows per shard on; same result either way).
     Returns (numpy.float64[max_rank], numpy.float64) on every rank.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -186,8 +236,15 @@ def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids
         raise ValueError('could not broadcast input array from shape ({},) into shape ({},)'.format(total, max_rank))
     offset = sum(counts[:rank])
 
-    d = ops.distance(qf, gf_local, metric)
-    keys, cls, ngood, status = ops.partial(d, qp, gp, qc, gc, max_rank, offset)
+    if fused is None:
+        fused = gf_local.shape[0] >= FUSED_MIN_GALLERY and hasattr(ops, 'topk_fused') and max_rank <= 256
+    if fused:
+        from .metrics.distance import PreparedOperand
+        keys, cls, ngood, status = ops.topk_fused(PreparedOperand(qf, metric, ops.split), PreparedOperand(gf_local, metric, ops.split),
+                                                  qp, gp, qc, gc, max_rank, offset)
+    else:
+        d = ops.distance(qf, gf_local, metric)
+        keys, cls, ngood, status = ops.partial(d, qp, gp, qc, gc, max_rank, offset)
     if world > 1:
         nq = keys.shape[0]
         keys_all = torch.empty((world * nq, max_rank), dtype=keys.dtype, device=dev)   # rank-major concatenation

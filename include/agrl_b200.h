@@ -58,6 +58,7 @@ extern "C" {
 #define AGRL_ST_NO_VALID_QUERY  1u
 #define AGRL_ST_ZERO_DIVISION   2u
 #define AGRL_ST_LABEL_RANGE     4u
+#define AGRL_ST_TOPK_OVERFLOW   8u   /* agrl_distance_topk_dev: a candidate list ran out of slots; take the unfused route */
 
 /* ---- distance metrics (torchreid/metrics/distance.py:46-54) -------------------------------- */
 #define AGRL_METRIC_EUCLIDEAN 0   /* squared euclidean, no clamp, no sqrt (distance.py:59-73)     */
@@ -239,6 +240,33 @@ AGRL_API int agrl_distance_prepare_operand_dev(const float *x_dev, int64_t ld, i
 AGRL_API int agrl_distance_prepared_dev(const void *q_operand_dev, int64_t num_q,
                                const void *g_operand_dev, int64_t num_g, int64_t dim, int metric, int split,
                                float *out_dev, int64_t ld_out, void *stream);
+
+/* Fused distance -> per-query top-k (compute_distance_matrix distance.py:11-89 followed by
+ * `np.argsort(score)[:max_rank]` of evaluate_mars, rank.py:171-172): the (num_q x num_g) matrix is never written.  The
+ * distance of every pair has exactly the bits agrl_distance_prepared_dev would store; the GEMM epilogue turns them into
+ * ranking keys (order-preserving distance bits << 32 | index_offset + gallery row, i.e. numpy's stable order) and keeps,
+ * per query, the max_rank smallest.
+ *   keys_dev    out (num_q, max_rank) uint64, ascending, all-ones = empty slot (num_g < max_rank)
+ *   status_dev  out, 1 uint32: zeroed, then AGRL_ST_TOPK_OVERFLOW if a query's candidate list ran out of slots (a
+ *               gallery ordered by distance to the query defeats the running threshold): keys are then NOT valid and
+ *               the caller takes agrl_distance_prepared_dev + agrl_rank_mars_partial_dev instead.
+ * Same result as agrl_rank_mars_partial_dev's keys on the materialised matrix.  max_rank <= 256.
+ * agrl_rank_mars_classify_dev then gives what agrl_rank_mars_merge_dev needs besides the keys: the class bytes of the
+ * listed items (bit0 good, bit1 junk, rank.py:166-169) and the per-query good-image count of this shard, from the labels
+ * alone in O(num_q + num_g); it ORs AGRL_ST_LABEL_RANGE into *status_dev (which the caller, or agrl_distance_topk_dev,
+ * initialised). */
+AGRL_API size_t agrl_distance_topk_workspace_bytes(int64_t num_q);
+AGRL_API int agrl_distance_topk_dev(const void *q_operand_dev, int64_t num_q, const void *g_operand_dev, int64_t num_g,
+                           int64_t dim, int metric, int split, int64_t max_rank, int64_t index_offset,
+                           uint64_t *keys_dev, uint32_t *status_dev,
+                           void *workspace_dev, size_t workspace_bytes, void *stream);
+AGRL_API size_t agrl_rank_mars_classify_workspace_bytes(int64_t num_q, int64_t num_g);
+AGRL_API int agrl_rank_mars_classify_dev(const uint64_t *keys_dev,
+                                const int64_t *q_pids_dev, const int64_t *g_pids_dev,
+                                const int64_t *q_camids_dev, const int64_t *g_camids_dev,
+                                int64_t num_q, int64_t num_g, int64_t max_rank, int64_t index_offset,
+                                uint8_t *cls_dev, int32_t *ngood_dev, uint32_t *status_dev,
+                                void *workspace_dev, size_t workspace_bytes, void *stream);
 
 AGRL_API int agrl_distance_host(const float *q_host, const float *g_host, float *out_host,
                        int64_t num_q, int64_t num_g, int64_t dim, int metric, int split);

@@ -1,7 +1,7 @@
-"""Control flow of bench.py's B200 arm with every device call replaced by a stand-in (no GPU): all the extra figures
-(fast mode, low-rank mode, tuned mode, stock-PyTorch comparator switched off here) are assembled into ONE JSON line
-with the keys the contract names, the options they switch are restored, and a failure inside an extra figure is
-reported as `unavailable` instead of costing the line."""
+"""Control flow of bench.py's B200 arm with every device call replaced by a stand-in (no GPU): the timed region, the
+kernel table, the whole-head roofline and the extra figures are assembled into ONE JSON line with the keys the
+contract names, the options they switch are restored, and a failure inside an extra figure is reported as
+`unavailable` instead of costing the line.  Also the reference arm's line on a tiny sample."""
 import json
 import types
 
@@ -86,7 +86,7 @@ def fake_device(monkeypatch):
         def stop(self):
             return dict(sm_mhz=1700.0, sm_max_mhz=1965.0, reasons=['sw_power_cap'], samples=3, power_w=990.0)
     monkeypatch.setattr(bench, 'ClockSampler', Sampler)
-    saved = {k: _lib.get_option(k) for k in ('head_lowrank', 'head_sub_batch', 'overlap_mode', 'pool_sms', 'pool_stages')}
+    saved = {k: _lib.get_option(k) for k in ('head_lowrank', 'head_sub_batch', 'pool_stages')}
     yield
     for k, v in saved.items():
         assert _lib.get_option(k) == v, 'bench must restore option %s' % k
@@ -94,7 +94,8 @@ def fake_device(monkeypatch):
 
 def run(monkeypatch, capsys, model, argv=()):
     monkeypatch.setattr(bench, 'make_model', lambda dev, w: model)
-    monkeypatch.setattr(bench.sys, 'argv', ['bench.py', '--steps', '2', '--no-e2e', '--no-cpu-baseline', '--no-eager'] + list(argv))
+    monkeypatch.setattr(bench.sys, 'argv', ['bench.py', '--steps', '2', '--no-e2e', '--no-cpu-baseline', '--no-eager', '--no-configs',
+                                            '--no-parity', '--no-curve', '--no-energy'] + list(argv))
     bench.main()
     lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -105,26 +106,52 @@ def test_b200_arm_line_and_extra_figures(fake_device, monkeypatch, capsys):
     model = FakeModel()
     line = run(monkeypatch, capsys, model)
     for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
-                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'kernels', 'gpu_launches', 'clocks', 'head_hbm',
-                'fast_mode', 'lowrank_mode', 'tuned_fast_mode'):
+                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'kernel_table', 'gpu_launches', 'clocks', 'fast_mode'):
         assert key in line, key
     assert line['steps'] == 2 and line['warmup'] == 3 and line['n_gpus'] == 1 and line['clocks']['power_w'] == 990.0
-    assert line['roofline']['kernel'] == 'pool' and line['roofline']['bound'] == 'hbm'
-    assert 'head_ms' in line['lowrank_mode'] and 'head_hbm_frac' in line['lowrank_mode']
-    assert line['tuned_fast_mode']['call_tracklets'] == 2 * 882 and line['tuned_fast_mode']['options']['pool_sms'] == 64
-    # what the head was called with: default, fp16 plane, low-rank, everything at once on double-size calls -- and the
-    # last passes (kernel timeline) are in the default configuration again
-    states = set(c[:3] for c in model.calls)
-    assert (_lib.SPLIT_BF16X2, 0, 0) in states and (_lib.SPLIT_FP16X1, 0, 0) in states
-    assert (_lib.SPLIT_BF16X2, 1, 0) in states and (_lib.SPLIT_FP16X1, 1, 64) in states
-    assert model.calls[-1][:3] == (_lib.SPLIT_BF16X2, 0, 0) and model.head_split == _lib.SPLIT_BF16X2
-    assert max(c[3] for c in model.calls if c[2] == 64) == 1764
+    # the line's roofline is the WHOLE head against HBM: J x 16 806 144 B / head time; FakeEvent makes a head pass 10 ms
+    roof = line['roofline']
+    assert roof['bound'] == 'hbm' and roof['unit'] == 'GB/s' and 'whole graph head' in roof['scope']
+    J = bench.NQ + bench.NG
+    assert abs(roof['achieved'] - J * bench.BYTES_PER_TRACKLET / 10e-3 / 1e9) < 1e-6 * roof['achieved']
+    assert abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-12
+    assert roof['dominant_kernel']['kernel'] == 'pool' and roof['dominant_kernel']['bound'] == 'hbm'
+    tab = line['kernel_table']
+    assert tab['gemm_graph_layer']['bound'] == 'tensor' and tab['pool']['launches'] == 13 and tab['attn']['bound'] == 'hbm'
+    assert abs(sum(r['share'] for r in tab.values()) - 1.0) < 1e-3
+    assert 'head_ms' in line['fast_mode'] and 'head_hbm_frac' in line['fast_mode']
+    # what the head was called with: default, fp16 plane -- and the last pass is in the default configuration again
+    states = set(c[0] for c in model.calls)
+    assert states == {_lib.SPLIT_BF16X2, _lib.SPLIT_FP16X1}
+    assert model.calls[-1][0] == _lib.SPLIT_BF16X2 and model.head_split == _lib.SPLIT_BF16X2
 
 
 def test_a_failing_extra_figure_does_not_cost_the_line(fake_device, monkeypatch, capsys):
-    model = FakeModel(fail_when=lambda st: st[1] == 1)            # anything with the low-rank option on raises
+    model = FakeModel(fail_when=lambda st: st[0] == _lib.SPLIT_FP16X1)            # the fp16 plane mode raises
     line = run(monkeypatch, capsys, model)
-    assert 'injected failure' in line['lowrank_mode']['unavailable']
-    assert 'injected failure' in line['tuned_fast_mode']['unavailable']
-    assert line['value'] > 0 and 'head_ms' in line['fast_mode']
+    assert 'injected failure' in line['fast_mode']['unavailable']
+    assert line['value'] > 0 and line['roofline']['frac'] > 0
     assert model.head_split == _lib.SPLIT_BF16X2
+
+
+def test_reference_arm_line_reports_what_it_executed(monkeypatch, capsys):
+    """--impl reference: same metric / unit / workload string as the B200 arm, the executed step time as ms_per_step, the
+    extrapolation flagged (tiny sample here so that the CPU suite stays fast)."""
+    monkeypatch.setattr(bench, 'NQ', 40); monkeypatch.setattr(bench, 'NG', 300)
+    monkeypatch.setattr(bench, 'make_labels', lambda r, w: bench_labels())
+    monkeypatch.setattr(bench.sys, 'argv', ['bench.py', '--impl', 'reference', '--steps', '2', '--warmup', '1', '--cpu-head-sample', '2'])
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['metric'] == bench.METRIC and line['unit'] == 'tracklets/s'
+    assert line['config']['workload'] == bench.WORKLOAD % 'euclidean'
+    assert line['extrapolated'] is True and line['cpu_baseline']['steps_executed'] == 2 and line['cpu_baseline']['kind'] == 'port'
+    assert abs(line['ms_per_step'] - line['cpu_baseline']['executed_step_ms']) < 1e-9
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['cpu_baseline']['cores'] >= 1
+    assert line['value'] == line['cpu_baseline']['value'] == line['e2e']['value']
+
+
+def bench_labels():
+    from agrl.pytorch_b200 import synthetic as synth
+    return synth.eval_labels((40, 300, 12, 3), seed=6)
