@@ -15,7 +15,7 @@ E_INVALID, E_NO_DEVICE, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 E_NO_VALID_QUERY, E_ZERO_DIVISION, E_LABEL_RANGE = -6, -7, -8
 ST_NO_VALID_QUERY, ST_ZERO_DIVISION, ST_LABEL_RANGE, ST_TOPK_OVERFLOW = 1, 2, 4, 8
 METRIC_EUCLIDEAN, METRIC_COSINE = 0, 1
-SPLIT_BF16X3, SPLIT_BF16X2, SPLIT_FP16X1 = 3, 2, 1
+SPLIT_BF16X3, SPLIT_BF16X2, SPLIT_FP16X1, SPLIT_FP16_E4M3 = 3, 2, 1, 4
 CLIP_POOL_AVG, CLIP_POOL_MAX = 0, 1
 HEAD_MAX_LAYERS = 4
 
@@ -33,6 +33,7 @@ class HeadParams(ctypes.Structure):
         ('bn_mean', c_vp * HEAD_MAX_LAYERS), ('bn_var', c_vp * HEAD_MAX_LAYERS),
         ('global_bn', c_vp * 4), ('att_bn', c_vp * 4),
         ('maps_nhwc', c_i32),
+        ('lowrank_off', c_i32), ('pool_register_loads', c_i32), ('pool_stages', c_i32), ('pool_no_l2_hint', c_i32),
     ]
 
 
@@ -44,8 +45,6 @@ _SIGNATURES = {
     'agrl_launch_count': (ctypes.c_uint64, []),
     'agrl_profile_begin': (c_int, [c_vp]),
     'agrl_profile_end': (c_int, [ctypes.c_char_p, c_sz]),
-    'agrl_set_option': (c_int, [ctypes.c_char_p, c_i64]),
-    'agrl_get_option': (c_i64, [ctypes.c_char_p]),
     'agrl_rank_workspace_bytes': (c_sz, [c_i64, c_i64, c_i64]),
     'agrl_rank_market1501_dev': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                          c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
@@ -117,7 +116,7 @@ def load(build_if_missing=True):
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the ABI and this table ever diverge
         fn.restype, fn.argtypes = res, args
-    if lib.agrl_abi_version() != 1:
+    if lib.agrl_abi_version() != 2:
         raise ImportError('libagrl_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -151,15 +150,6 @@ def require_device():
     if rc != OK:
         raise AgrlError(rc, lib.agrl_status_string(rc).decode())
     return lib
-
-
-def set_option(name, value):
-    """Tuning knob of the library (agrl_set_option): e.g. ``set_option('head_sub_batch', 0)``."""
-    check(load().agrl_set_option(name.encode(), int(value)))
-
-
-def get_option(name):
-    return int(load().agrl_get_option(name.encode()))
 
 
 def launch_count():

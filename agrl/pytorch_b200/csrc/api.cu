@@ -57,66 +57,6 @@ void after_launch(cudaStream_t st, const char *name) {
     }
 }
 
-// ---- tuning knobs ---------------------------------------------------------------------------------
-struct OptionDef { const char *name, *env; int64_t def, lo, hi; };
-static const OptionDef kOptionDefs[kOptCount] = {
-    // tracklets per internal sub-batch of agrl_head_forward_dev (pooling of sub-batch i+1 runs on a side
-    // stream under the graph layers of sub-batch i); 0 = one pass, no side stream.  Measured on B200
-    // (profiles/r1/overlap_experiment.txt): co-running the pooling with the GEMM saturates L2, with the graph
-    // kernel the shared-memory pipe -- no net gain, so the default is one pass.
-    {"head_sub_batch", "AGRL_HEAD_SUB", 0, 0, 1 << 20},
-    // 1: persistent bulk-copy (TMA) pooling kernel; 0: the register-load pooling kernel
-    {"pool_tma", "AGRL_POOL_TMA", 1, 0, 1},
-    {"pool_stages", "AGRL_POOL_STAGES", 4, 2, 12},            // 16 KiB ring stages per pooling CTA
-    {"pool_ctas_per_sm", "AGRL_POOL_CTAS", 1, 1, 4},
-    {"graph_variant", "AGRL_GRAPH_VARIANT", 8, 0, 8},
-    {"pool_l2_hint", "AGRL_POOL_HINT", 1, 0, 1},              // evict-first hint on the pooling bulk copies
-    // sub-batched pipeline: 0 = poolings free-run on the side stream; 1 = pooling of sub-batch i+1 is cut into
-    // pieces that run only under the graph / attention kernels of sub-batch i (the GEMMs wait for their piece)
-    {"overlap_mode", "AGRL_OVERLAP_MODE", 1, 0, 1},
-    // 1: the tcgen05 GEMMs run as CTA pairs (cta_group::2, 256-row tiles, each CTA loads half of the B tile).
-    // Parity-tested; measured SLOWER than one CTA per tile on B200 (24.6 vs 23.3 ms, fp16 plane 19.8 vs 11.9 ms per
-    // pass; tensor pipe 68 % vs 79 % active, a third less L2->SM traffic) -- default off, see DESIGN.md
-    {"gemm_pair", "AGRL_GEMM_PAIR", 0, 0, 2},            // 2: pairs without the relay warp (unmeasured, see gemm_sm100.cuh)
-    // Spatial partition of the sub-batched pipeline (free-running mode, overlap_mode = 0): with pool_sms > 0 the
-    // poolings of sub-batches 1.. run as ONE wide CTA per SM on pool_sms SMs (two producer/consumer lanes per CTA and
-    // a ring that fills the SM's shared memory, so no graph / GEMM CTA can share the SM), while the persistent GEMM
-    // of every sub-batch but the last is launched on gemm_sms CTAs (0 = all SMs minus pool_sms).  Experimental: off.
-    {"pool_sms", "AGRL_POOL_SMS", 0, 0, 148},
-    {"gemm_sms", "AGRL_GEMM_SMS", 0, 0, 148},
-    // 1: the FIRST graph layer runs its X.W^T on the quarter-strip rows only (the pooled nodes of a frame are linear
-    // combinations of its four quarter strips: G.X.W^T = (G.T).(Q.W^T), 4S GEMM rows per tracklet instead of 7S), then a
-    // per-tracklet mixing kernel applies G.T and the layer's epilogue.  Same result to ~1e-7 (tests/test_lowrank_layer1.py).
-    // Default since round 2: whole GPU suite green with it, 64.8 -> 60.3 ms per 11310-tracklet pass (profiles/r2/first_call.log).
-    // 2: graph_mix2_kernel (two channels per thread, bit-identical to 1 and 0.6 ms faster per pass); 0: off
-    {"head_lowrank", "AGRL_HEAD_LOWRANK", 2, 0, 2},
-};
-static std::atomic<int64_t> g_options[kOptCount];
-static std::atomic<int> g_options_init{0};
-
-static void init_options() {
-    if (g_options_init.load(std::memory_order_acquire) == 2) return;
-    int expect = 0;
-    if (g_options_init.compare_exchange_strong(expect, 1)) {
-        for (int i = 0; i < kOptCount; ++i) {
-            int64_t v = kOptionDefs[i].def;
-            const char *e = getenv(kOptionDefs[i].env);
-            if (e && *e) v = atoll(e);
-            if (v < kOptionDefs[i].lo) v = kOptionDefs[i].lo;
-            if (v > kOptionDefs[i].hi) v = kOptionDefs[i].hi;
-            g_options[i].store(v, std::memory_order_relaxed);
-        }
-        g_options_init.store(2, std::memory_order_release);
-    } else {
-        while (g_options_init.load(std::memory_order_acquire) != 2) {}
-    }
-}
-
-int64_t option(Option o) {
-    init_options();
-    return g_options[o].load(std::memory_order_relaxed);
-}
-
 // per-thread stream + stream-ordered scratch for the *_host entry points
 struct HostCtx {
     cudaStream_t stream = nullptr;
@@ -184,26 +124,6 @@ extern "C" const char *agrl_status_string(int code) {
 
 extern "C" const char *agrl_last_cuda_error(void) { return tl_error; }
 
-extern "C" int agrl_set_option(const char *name, int64_t value) {
-    if (!name) return AGRL_E_INVALID;
-    init_options();
-    for (int i = 0; i < kOptCount; ++i) {
-        if (strcmp(name, kOptionDefs[i].name) == 0) {
-            if (value < kOptionDefs[i].lo || value > kOptionDefs[i].hi) return AGRL_E_INVALID;
-            g_options[i].store(value, std::memory_order_relaxed);
-            return AGRL_OK;
-        }
-    }
-    return AGRL_E_INVALID;
-}
-
-extern "C" int64_t agrl_get_option(const char *name) {
-    if (!name) return -1;
-    init_options();
-    for (int i = 0; i < kOptCount; ++i)
-        if (strcmp(name, kOptionDefs[i].name) == 0) return g_options[i].load(std::memory_order_relaxed);
-    return -1;
-}
 extern "C" uint64_t agrl_launch_count(void) { return tl_launches; }
 
 extern "C" int agrl_device_ok(void) {

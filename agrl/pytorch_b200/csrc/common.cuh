@@ -20,10 +20,6 @@ void        after_launch(cudaStream_t st, const char *name);   // counts; record
 // kernel is timed from the previous event (consecutive launches on one busy stream).
 void        before_launch(cudaStream_t st);
 
-// Process-wide tuning knobs (agrl_set_option / agrl_get_option; defaults may come from AGRL_* env vars).
-enum Option { kOptHeadSubBatch = 0, kOptPoolTma, kOptPoolStages, kOptPoolCtasPerSm, kOptGraphVariant, kOptPoolHint, kOptOverlapMode, kOptGemmPair, kOptPoolSms, kOptGemmSms, kOptHeadLowrank, kOptCount };
-int64_t     option(Option o);
-
 #define AGRL_CUDA_TRY(expr)                                                            \
     do {                                                                               \
         cudaError_t _e = (expr);                                                       \

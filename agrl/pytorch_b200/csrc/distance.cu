@@ -66,16 +66,12 @@ extern "C" int agrl_distance_prepared_dev(const void *q_operand, int64_t num_q, 
     const int kp = static_cast<int>(gemm::pad_k(dim));
     CUtensorMap map_q, map_g;
     if ((rc = gemm::make_plane_tensor_map(&map_q, q.planes, num_q, kp, split, gemm::BM, num_q))) return rc;
-    const bool pair = option(kOptGemmPair) != 0;
-    if ((rc = gemm::make_plane_tensor_map(&map_g, g.planes, num_g, kp, split, pair ? 64 : 128, num_g))) return rc;
+    if ((rc = gemm::make_plane_tensor_map(&map_g, g.planes, num_g, kp, split, 128, num_g))) return rc;
     gemm::EpiDistance epi{q.sumsq, g.sumsq, out, ld_out, metric};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nq = static_cast<int>(num_q), ng = static_cast<int>(num_g);
-    if (split == AGRL_SPLIT_BF16X3)
-        return pair ? gemm::launch_pair_gemm<3, 128, true>(map_q, map_g, nq, ng, kp, epi, st)
-                    : gemm::launch_split_gemm<3, 128, true>(map_q, map_g, nq, ng, kp, epi, st);
-    return pair ? gemm::launch_pair_gemm<2, 128, true>(map_q, map_g, nq, ng, kp, epi, st)
-                : gemm::launch_split_gemm<2, 128, true>(map_q, map_g, nq, ng, kp, epi, st);
+    if (split == AGRL_SPLIT_BF16X3) return gemm::launch_split_gemm<3, 128, true>(map_q, map_g, nq, ng, kp, epi, st);
+    return gemm::launch_split_gemm<2, 128, true>(map_q, map_g, nq, ng, kp, epi, st);
 }
 
 extern "C" size_t agrl_distance_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int split) {

@@ -11,8 +11,10 @@
 //   graph_kernel_tc    one CTA per tracklet: Gram matrix of the centred nodes and the message passing Y = G.X (vmgn.py:168,
 //                      re-associated as (G.X).W^T) as tcgen05 MMAs on operands the CTA converts itself in shared memory;
 //                      affinity 2/(exp(d)+1) (vmgn.py:114-120), L1 row normalisation of affinity and pose graph (:157,:162),
-//                      average (:164) on CUDA cores in between.  Y leaves as operand planes for the GEMM.
-//                      graph_kernel_v2 / graph_kernel are the CUDA-core versions (fallback: V > 64 or C % 128 != 0).
+//                      average (:164) on CUDA cores in between.  Y leaves as operand planes for the GEMM.  First layer:
+//                      the nodes of a frame are T.(its four quarter strips), so G.X.W^T = (G.T).(Q.W^T): the kernel stops
+//                      after the graph, emits G.T and the planes of the 4S quarter rows; graph_mix_kernel applies G.T and
+//                      the layer's element-wise part after the GEMM.
 //   split_gemm_kernel  (gemm_sm100.cuh) Y.W^T on tcgen05 with the layer's epilogue fused:
 //                      0.9*X + 0.1*LeakyReLU(BN(.)) (vmgn.py:169-172).
 //   attn_kernel        temporal attention (vmgn.py:276-277), part mean, BN neck -> out[:, C:] (:317-321).
@@ -20,12 +22,17 @@
 #include "gemm_sm100.cuh"
 
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace agrl {
 
 constexpr int kParts = 7;              // calc_splits(4) = [4,2,1] (utils/reidtools.py:13-15)
 constexpr int kMaxNodes = 64;
 constexpr int kHeadThreads = 256;
+
+// operand planes of a GEMM mode: bf16 x2 / x3, ONE scaled fp16 plane, or the fp16 plane + one plane of E4M3 pairs
+static inline int planes_of(int split) { return split == AGRL_SPLIT_FP16_E4M3 ? 2 : split; }
+static inline bool scaled_mode(int split) { return split == AGRL_SPLIT_FP16X1 || split == AGRL_SPLIT_FP16_E4M3; }
 
 // ------------------------------------------------------------------------------------------------
 // weight preparation: folded BN vectors
@@ -80,7 +87,7 @@ static Prepared carve_prepared(const agrl_head_params *p, void *buf) {
     Carver c(buf);
     Prepared r;
     const size_t C = static_cast<size_t>(p->channels);
-    for (int l = 0; l < p->num_layers; ++l) r.w_planes[l] = c.take<__nv_bfloat16>(p->split * C * C);
+    for (int l = 0; l < p->num_layers; ++l) r.w_planes[l] = c.take<__nv_bfloat16>(planes_of(p->split) * C * C);
     for (int l = 0; l < p->num_layers + 2; ++l) { r.scale[l] = c.take<float>(C); r.shift[l] = c.take<float>(C); }
     r.w_scale = c.take<float>(4 * AGRL_HEAD_MAX_LAYERS);
     r.bytes = c.total();
@@ -231,9 +238,8 @@ pool_nhwc_kernel(PoolArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // pooling, bulk-copy (TMA) flavour: a persistent, deliberately small CTA (1 producer + 4 consumer
-// warps, < 64 registers) that keeps its loads in flight in a shared-memory ring instead of in
-// registers, so that it can sit NEXT TO the graph / GEMM CTAs of the previous sub-batch on the same SM
-// and stream the maps at HBM speed underneath them.
+// warps, < 64 registers, two per SM) that keeps its loads in flight in a shared-memory ring instead of in
+// registers.
 //   work unit   (tracklet b, 32-channel chunk): 2*S ring stages of 16 KiB, each one frame of one map
 //               (32 channels x 128 floats are contiguous in NCHW), fetched with one cp.async.bulk
 //               (L2 evict-first) that completes on the stage's mbarrier
@@ -257,14 +263,11 @@ struct PoolTmaArgs {
     int l2_hint;                       // 1: evict-first cache hint on the bulk copies
 };
 
-// bytes of one producer/consumer lane: ring | two node tiles | barriers, rounded up to 128
-static __host__ __device__ inline size_t pool_tma_lane_bytes(int S, int stages) {
+// dynamic shared memory: ring | two node tiles | barriers (+ alignment slack)
+static size_t pool_tma_smem(int S, int stages) {
     const size_t b = static_cast<size_t>(stages) * kTpStageBytes + 2 * static_cast<size_t>(S) * kParts * kTpCh * sizeof(float) +
                      2 * static_cast<size_t>(stages) * 8;
-    return (b + 127) & ~static_cast<size_t>(127);
-}
-static size_t pool_tma_smem(int S, int stages, int lanes = 1) {
-    return lanes * pool_tma_lane_bytes(S, stages) + 128;
+    return ((b + 127) & ~static_cast<size_t>(127)) + 128;
 }
 
 __device__ __forceinline__ void bulk_load_evict_first(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
@@ -298,30 +301,23 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// kLanes independent producer/consumer groups ("lanes") per CTA, each with its own ring, node tiles, barriers and
-// work units.  kLanes = 1 is the default kernel (two such CTAs per SM).  kLanes = 2 is the spatially partitioned
-// flavour: ONE CTA that fills an SM's shared memory, launched on a subset of the SMs while the graph / GEMM kernels of
-// the previous sub-batch own the others (option pool_sms) -- the block scheduler would spread two narrow CTAs over
-// two SMs, so the pair is fused into one CTA.
-template <int kLanes>
-__device__ __forceinline__ void pool_tma_body(const PoolTmaArgs &a) {
+__global__ void __maxnreg__(48)
+pool_tma_kernel(PoolTmaArgs a) {
     extern __shared__ __align__(16) unsigned char tp_smem_dyn[];
     const int stages = a.stages, S = a.S, C = a.C, V = S * kParts;
-    const int group = kLanes > 1 ? static_cast<int>(threadIdx.x) / kTpThreads : 0;     // which lane this thread serves
     // align to 128 B by OFFSET (not by casting through an integer) so that the compiler keeps emitting LDS / STS
-    unsigned char *smem = tp_smem_dyn + ((128u - (gemm::smem_u32(tp_smem_dyn) & 127u)) & 127u) +
-                          (kLanes > 1 ? group * pool_tma_lane_bytes(S, stages) : 0);
+    unsigned char *smem = tp_smem_dyn + ((128u - (gemm::smem_u32(tp_smem_dyn) & 127u)) & 127u);
     const float4 *ring_f4 = reinterpret_cast<const float4 *>(smem);
     float *s_nodes = reinterpret_cast<float *>(smem + stages * kTpStageBytes);   // [2][V][32]
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_nodes + 2 * V * kTpCh);
     const uint32_t ring = gemm::smem_u32(smem);
     const uint32_t bar_full = gemm::smem_u32(bars), bar_empty = bar_full + 8 * stages;
-    const int tid = static_cast<int>(threadIdx.x) - group * kTpThreads;                 // thread index within the lane
+    const int tid = static_cast<int>(threadIdx.x);
     const int warp = tid >> 5, lane = tid & 31;
     const int chunks = C / kTpCh;
     const int units = a.unit1;
-    const int first = a.unit0 + static_cast<int>(blockIdx.x) * kLanes + group;
-    const int stride = static_cast<int>(gridDim.x) * kLanes;
+    const int first = a.unit0 + static_cast<int>(blockIdx.x);
+    const int stride = static_cast<int>(gridDim.x);
 
     if (tid == 0) {
         for (int i = 0; i < stages; ++i) { gemm::mbar_init(bar_full + 8 * i, 1); gemm::mbar_init(bar_empty + 8 * i, kTpConsumerWarps); }
@@ -410,9 +406,8 @@ __device__ __forceinline__ void pool_tma_body(const PoolTmaArgs &a) {
                     a.out[static_cast<size_t>(b) * a.ld_out + c] = fmaf(t * inv_all, a.g_scale[c], a.g_shift[c]);
                 }
             }
-            // node tile complete (one named barrier per lane)
-            if (kLanes > 1 && group == 1) asm volatile("bar.sync 2, %0;" ::"n"(32 * kTpConsumerWarps) : "memory");
-            else asm volatile("bar.sync 1, %0;" ::"n"(32 * kTpConsumerWarps) : "memory");
+            // node tile complete (named barrier of the consumer warps)
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kTpConsumerWarps) : "memory");
             float *nodes = a.nodes + static_cast<size_t>(b) * V * C + c0;
             for (int v = ct >> 5; v < V; v += kTpConsumerWarps) nodes[static_cast<size_t>(v) * C + lane] = sn[v * kTpCh + lane];
             // (the other s_nodes buffer is used next; this one is rewritten only after the next unit's barrier)
@@ -420,17 +415,12 @@ __device__ __forceinline__ void pool_tma_body(const PoolTmaArgs &a) {
     }
 }
 
-__global__ void __maxnreg__(48)
-pool_tma_kernel(PoolTmaArgs a) { pool_tma_body<1>(a); }
 
-__global__ void __maxnreg__(48)
-pool_tma_wide_kernel(PoolTmaArgs a) { pool_tma_body<2>(a); }
 
 // ------------------------------------------------------------------------------------------------
 // graph kernel: one CTA per tracklet
 // ------------------------------------------------------------------------------------------------
-constexpr int kChunk = 128;                 // channels staged per step (double buffered)
-constexpr int kXsLd = kChunk + 4;           // padded row stride (floats), keeps float4 alignment
+constexpr int kChunk = 128;                 // channel granularity of the graph kernel (C % 128 == 0)
 constexpr int kGLd = kMaxNodes + 4;         // graph row stride: float4-aligned rows
 
 struct GraphArgs {
@@ -447,53 +437,10 @@ struct GraphArgs {
     // the quarter-strip rows -- y_planes / plane_stride then describe [P][B*4S][C]
     int lowrank = 0;
     float *gt = nullptr;
+    // with fp16: second plane of E4M3 pairs (AGRL_SPLIT_FP16_E4M3), per 64-channel k-block 64 bytes
+    // e4m3((y s - fp16(y s)) 2^6) then 64 bytes e4m3(y s 2^-6) -- the A-operand order, W has them swapped (split.cu)
+    int fp8 = 0;
 };
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// start staging X[:, c0:c0+kChunk] (V rows; rows V.. stay zero) into one of the two smem buffers
-__device__ __forceinline__ void stage_chunk_async(float *xs, const float *x, int V, int C, int c0, int tid) {
-    constexpr int per_row = kChunk / 4;
-    for (int i = tid; i < V * per_row; i += kHeadThreads) {
-        const int r = i / per_row, q = i % per_row;
-        cp_async16(xs + r * kXsLd + q * 4, x + static_cast<size_t>(r) * C + c0 + q * 4);
-    }
-    cp_async_commit();
-}
-
-// Run `body(buffer)` over all channel chunks of x.  kBufs = 2: the next chunk is in flight (cp.async)
-// while the current one is consumed; kBufs = 1: single buffer, latency hidden by the other resident CTAs.
-template <int kBufs, class F>
-__device__ __forceinline__ void for_each_chunk(float *xs0, float *xs1, const float *x, int V, int C, int tid, F &&body) {
-    const int n = C / kChunk;
-    if (kBufs == 2) {
-        stage_chunk_async(xs0, x, V, C, 0, tid);
-        for (int i = 0; i < n; ++i) {
-            float *cur = (i & 1) ? xs1 : xs0;
-            if (i + 1 < n) {
-                stage_chunk_async((i & 1) ? xs0 : xs1, x, V, C, (i + 1) * kChunk, tid);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncthreads();                       // chunk i is visible to every thread
-            body(cur, i * kChunk);
-            __syncthreads();                       // everyone is done with `cur` before it is refilled
-        }
-    } else {
-        for (int i = 0; i < n; ++i) {
-            stage_chunk_async(xs0, x, V, C, i * kChunk, tid);
-            cp_async_wait<0>();
-            __syncthreads();
-            body(xs0, i * kChunk);
-            __syncthreads();
-        }
-    }
-}
 
 // element (r, c) of the pose graph: the dense matrix, or the three membership masks it is made of
 // (dataset_loader.py:373-387: every ordered pair of DISTINCT nodes that share a body-part class)
@@ -513,412 +460,8 @@ struct PoseGraph {
     }
 };
 
-template <int NT, int kBufs, int kMaxRegs>     // NT = ceil(V/4): 14 for the canonical V = 56
-__global__ void __maxnreg__(kMaxRegs)
-graph_kernel(GraphArgs a) {
-    constexpr int kRows = 4 * NT;                      // staged rows (>= V; the rest stay zero)
-    constexpr int kTiles = NT * (NT + 1) / 2;          // 4x4 Gram tiles of the upper triangle
-    constexpr int kGroups = (2 * kTiles <= kHeadThreads) ? 2 : 1;      // split the chunk's k range
-    constexpr int kRpg = NT / 2;                       // rows per thread in Y = G.X (8 row groups)
-    static_assert(NT % 2 == 0 && kTiles <= kHeadThreads, "tiling");
-    extern __shared__ __align__(16) float smem_f[];
-    float *xs0 = smem_f;                               // [kRows][kXsLd] x kBufs
-    float *xs1 = xs0 + (kBufs - 1) * kRows * kXsLd;
-    float *g = xs0 + kBufs * kRows * kXsLd;            // [64][68]: Gram, then the mixed graph
-    float *sq = g + kMaxNodes * kGLd;                  // [64]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int V = a.V, C = a.C;
-    const int b = blockIdx.x;
-    const float *x = a.x + static_cast<size_t>(b) * V * C;
-
-    for (int i = tid; i < kBufs * kRows * kXsLd; i += kHeadThreads) xs0[i] = 0.f;   // pad rows stay zero
-    for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
-    __syncthreads();
-
-    if (a.learn_graph) {
-        // ---- Gram matrix, upper triangle only: thread (ti <= tj) owns rows {ti+NT*e} x {tj+NT*f} ----
-        const int u = tid % kTiles, kg = tid / kTiles;
-        const bool active = kg < kGroups;
-        int ti = 0, tj = u;
-        while (tj >= NT - ti) { tj -= NT - ti; ++ti; }          // u -> (ti, tj), tj counted from ti
-        tj += ti;
-        float acc[4][4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int f = 0; f < 4; ++f) acc[e][f] = 0.f;
-        for_each_chunk<kBufs>(xs0, xs1, x, V, C, tid, [&](const float *xs, int) {
-            if (!active) return;
-            const int k0 = kg * (kChunk / kGroups);
-#pragma unroll 2
-            for (int k = k0; k < k0 + kChunk / kGroups; k += 4) {
-                float4 av[4], bv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    av[e] = *reinterpret_cast<const float4 *>(xs + (ti + NT * e) * kXsLd + k);
-                    bv[e] = *reinterpret_cast<const float4 *>(xs + (tj + NT * e) * kXsLd + k);
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        acc[e][f] = fmaf(av[e].x, bv[f].x, acc[e][f]);
-                        acc[e][f] = fmaf(av[e].y, bv[f].y, acc[e][f]);
-                        acc[e][f] = fmaf(av[e].z, bv[f].z, acc[e][f]);
-                        acc[e][f] = fmaf(av[e].w, bv[f].w, acc[e][f]);
-                    }
-            }
-        });
-        // combine the k groups and mirror into the lower triangle
-#pragma unroll
-        for (int grp = 0; grp < kGroups; ++grp) {
-            if (active && kg == grp) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        const int r = ti + NT * e, c = tj + NT * f;
-                        const float v = (grp == 0) ? acc[e][f] : g[r * kGLd + c] + acc[e][f];
-                        g[r * kGLd + c] = v;
-                        if (ti != tj) g[c * kGLd + r] = v;     // a diagonal tile holds both (r,c) and (c,r) itself
-                    }
-            }
-            __syncthreads();
-        }
-        if (tid < V) sq[tid] = g[tid * kGLd + tid];
-        __syncthreads();
-        // ---- affinity 2 / (exp(sqrt(max(d2, 1e-12))) + 1)  (vmgn.py:116-120) ----
-        for (int i = tid; i < V * V; i += kHeadThreads) {
-            const int r = i / V, c = i % V;
-            float d2 = __fadd_rn(sq[c], sq[r]);
-            d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
-            const float d = sqrtf(fmaxf(d2, 1e-12f));
-            g[r * kGLd + c] = __fdiv_rn(2.0f, expf(d) + 1.0f);
-        }
-        __syncthreads();
-    }
-    // ---- L1 row normalisation + mixing: one warp per row ----
-    const PoseGraph pose(a, b);
-    for (int r = warp; r < V; r += kHeadThreads / 32) {
-        float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
-        const int c1 = lane + 32;
-        if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
-        if (a.use_pose) { a0 = (lane < V) ? pose.at(r, lane) : 0.f; a1 = (c1 < V) ? pose.at(r, c1) : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
-        rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);              // F.normalize eps
-        float m0, m1;
-        if (a.learn_graph && a.use_pose) {
-            m0 = __fdiv_rn(__fdiv_rn(a0, ra) + __fdiv_rn(s0, rs), 2.0f);
-            m1 = __fdiv_rn(__fdiv_rn(a1, ra) + __fdiv_rn(s1, rs), 2.0f);
-        } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
-        else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
-        __syncwarp();
-        g[r * kGLd + lane] = (lane < V) ? m0 : 0.f;
-        g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
-    }
-    // graph rows >= V are never stored; graph columns >= V are zero
-    __syncthreads();
-    // fp16 plane: |y_ij| <= max_v ||x_v|| (rows of G have L1 norm <= 1), so one power of two per tracklet
-    // puts every y below 2^14; the GEMM epilogue undoes it (y_unscale)
-    float y_scale = 1.0f;
-    if (a.fp16) {
-        __shared__ float s_scale[2];
-        if (!a.learn_graph) {                            // no Gram diagonal: one norm pass over the rows (L2-resident)
-            for (int r = warp; r < V; r += kHeadThreads / 32) {
-                const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
-                float t = 0.f;
-                for (int i = lane; i < C / 4; i += 32) {
-                    const float4 v = __ldg(row + i);
-                    t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
-                }
-                t = warp_sum(t);
-                if (lane == 0) sq[r] = t;
-            }
-            __syncthreads();
-        }
-        if (warp == 0) {
-            float m = fmaxf(lane < V ? sq[lane] : 0.f, lane + 32 < V ? sq[lane + 32] : 0.f);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == 0) {
-                m = (m < 3.0e38f) ? sqrtf(m) : 0.f;       // inf / NaN rows: leave unscaled
-                pow2_scales(m, &s_scale[0], &s_scale[1]);
-                a.y_unscale[b] = s_scale[1];
-            }
-        }
-        __syncthreads();
-        y_scale = s_scale[0];
-    }
-
-    // ---- Y = G . X : thread (rg, cq) owns rows {rg*kRpg ..+kRpg-1} x 4 channels of the chunk ----
-    const int rg = tid >> 5, cq = tid & 31;              // a warp shares rg -> graph weights broadcast
-    const size_t row0 = static_cast<size_t>(b) * V;
-    const int jmax = (V + 3) & ~3;
-    for_each_chunk<kBufs>(xs0, xs1, x, V, C, tid, [&](const float *xs, int c0) {
-        float acc[kRpg][4];
-#pragma unroll
-        for (int r = 0; r < kRpg; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-        for (int j = 0; j < jmax; j += 4) {
-            float4 xv[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) xv[jj] = *reinterpret_cast<const float4 *>(xs + (j + jj) * kXsLd + cq * 4);
-#pragma unroll
-            for (int r = 0; r < kRpg; ++r) {
-                const float4 w = *reinterpret_cast<const float4 *>(g + (rg * kRpg + r) * kGLd + j);
-                acc[r][0] = fmaf(w.x, xv[0].x, acc[r][0]); acc[r][1] = fmaf(w.x, xv[0].y, acc[r][1]);
-                acc[r][2] = fmaf(w.x, xv[0].z, acc[r][2]); acc[r][3] = fmaf(w.x, xv[0].w, acc[r][3]);
-                acc[r][0] = fmaf(w.y, xv[1].x, acc[r][0]); acc[r][1] = fmaf(w.y, xv[1].y, acc[r][1]);
-                acc[r][2] = fmaf(w.y, xv[1].z, acc[r][2]); acc[r][3] = fmaf(w.y, xv[1].w, acc[r][3]);
-                acc[r][0] = fmaf(w.z, xv[2].x, acc[r][0]); acc[r][1] = fmaf(w.z, xv[2].y, acc[r][1]);
-                acc[r][2] = fmaf(w.z, xv[2].z, acc[r][2]); acc[r][3] = fmaf(w.z, xv[2].w, acc[r][3]);
-                acc[r][0] = fmaf(w.w, xv[3].x, acc[r][0]); acc[r][1] = fmaf(w.w, xv[3].y, acc[r][1]);
-                acc[r][2] = fmaf(w.w, xv[3].z, acc[r][2]); acc[r][3] = fmaf(w.w, xv[3].w, acc[r][3]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kRpg; ++r) {
-            const int row = rg * kRpg + r;
-            if (row < V) {
-                float v0 = acc[r][0], v1 = acc[r][1], v2 = acc[r][2], v3 = acc[r][3];
-                __nv_bfloat16 *dst = a.y_planes + (row0 + row) * C + c0 + cq * 4;
-                if (a.fp16) {
-                    const __half2 lo = __floats2half2_rn(v0 * y_scale, v1 * y_scale), hi = __floats2half2_rn(v2 * y_scale, v3 * y_scale);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-                    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-                    *reinterpret_cast<uint2 *>(dst) = pk;
-                    continue;
-                }
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    if (p < a.P) {
-                        // packed conversions (F2FP, full rate) -- the scalar F2F path runs at a quarter of it
-                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-                        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-                        *reinterpret_cast<uint2 *>(dst + p * a.plane_stride) = pk;
-                        v0 = __fsub_rn(v0, __uint_as_float(pk.x << 16)); v1 = __fsub_rn(v1, __uint_as_float(pk.x & 0xffff0000u));
-                        v2 = __fsub_rn(v2, __uint_as_float(pk.y << 16)); v3 = __fsub_rn(v3, __uint_as_float(pk.y & 0xffff0000u));
-                    }
-                }
-            }
-        }
-    });
-}
-
 // ------------------------------------------------------------------------------------------------
-// graph kernel, second tiling (V <= 56, C % 256 == 0): same algorithm and shared-memory footprint as
-// graph_kernel, larger register tiles so that the shared-memory pipe is no longer the limit.
-//   Gram   lane = one of the 28 (i <= j) pairs of 8x8 tiles over rows {i + 7e} x {j + 7f}; the 8 warps split
-//          the k range of every 128-channel chunk.  16 conflict-free LDS.64 per 128 FMA (was 8 LDS.128 per 64).
-//   Y=G.X  warp = (14-row group, one of two 128-channel buffers), lane = 4 channels: 14x4 register tile,
-//          4 LDS.128 of X + 14 broadcast LDS.128 of G per 224 FMA (was 4 + 7 per 112); the next pair of
-//          chunks is fetched (cp.async) while the current one is rounded to operand planes and stored.
-// ------------------------------------------------------------------------------------------------
-constexpr int kNB = 7;                     // 8x8 tiles: rows i + 7e, e = 0..7 -> 56 rows
-constexpr int kV2Rows = 8 * kNB;
-
-template <int kMaxRegs>
-__global__ void __maxnreg__(kMaxRegs)
-graph_kernel_v2(GraphArgs a) {
-    extern __shared__ __align__(16) float smem_f[];
-    float *xs0 = smem_f;                               // [56][kXsLd] x 2
-    float *xs1 = xs0 + kV2Rows * kXsLd;
-    float *g = xs1 + kV2Rows * kXsLd;                  // [64][68]: Gram, then the mixed graph
-    float *sq = g + kMaxNodes * kGLd;                  // [64]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int V = a.V, C = a.C;
-    const int b = blockIdx.x;
-    const float *x = a.x + static_cast<size_t>(b) * V * C;
-
-    for (int i = tid; i < 2 * kV2Rows * kXsLd; i += kHeadThreads) xs0[i] = 0.f;     // pad rows stay zero
-    for (int i = tid; i < kMaxNodes * kGLd; i += kHeadThreads) g[i] = 0.f;
-    __syncthreads();
-
-    if (a.learn_graph) {
-        int pi = 0, pj = lane;
-        const bool active = lane < kNB * (kNB + 1) / 2;
-        if (active) { while (pj >= kNB - pi) { pj -= kNB - pi; ++pi; } pj += pi; } else { pj = 0; }
-        float acc[8][8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-#pragma unroll
-            for (int f = 0; f < 8; ++f) acc[e][f] = 0.f;
-        for_each_chunk<2>(xs0, xs1, x, V, C, tid, [&](const float *xs, int) {
-            if (!active) return;
-            const float *pa = xs + pi * kXsLd + warp * (kChunk / 8);
-            const float *pb = xs + pj * kXsLd + warp * (kChunk / 8);
-#pragma unroll 1
-            for (int k = 0; k < kChunk / 8; k += 2) {
-                float2 av[8], bv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    av[e] = *reinterpret_cast<const float2 *>(pa + e * kNB * kXsLd + k);
-                    bv[e] = *reinterpret_cast<const float2 *>(pb + e * kNB * kXsLd + k);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-#pragma unroll
-                    for (int f = 0; f < 8; ++f) {
-                        acc[e][f] = fmaf(av[e].x, bv[f].x, acc[e][f]);
-                        acc[e][f] = fmaf(av[e].y, bv[f].y, acc[e][f]);
-                    }
-            }
-        });
-        // combine the 8 k groups in a fixed order (deterministic sums)
-#pragma unroll 1
-        for (int w = 0; w < kHeadThreads / 32; ++w) {
-            if (warp == w && active) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-#pragma unroll
-                    for (int f = 0; f < 8; ++f) {
-                        float *dst = g + (pi + kNB * e) * kGLd + pj + kNB * f;
-                        *dst = (w == 0) ? acc[e][f] : *dst + acc[e][f];
-                    }
-            }
-            __syncthreads();
-        }
-        if (warp == 0 && active && pi != pj) {                  // mirror into the lower triangle
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-#pragma unroll
-                for (int f = 0; f < 8; ++f) g[(pj + kNB * f) * kGLd + pi + kNB * e] = g[(pi + kNB * e) * kGLd + pj + kNB * f];
-        }
-        __syncthreads();
-        if (tid < V) sq[tid] = g[tid * kGLd + tid];
-        __syncthreads();
-        for (int i = tid; i < V * V; i += kHeadThreads) {       // affinity (vmgn.py:116-120)
-            const int r = i / V, c = i % V;
-            float d2 = __fadd_rn(sq[c], sq[r]);
-            d2 = fmaf(-2.0f, g[r * kGLd + c], d2);
-            const float d = sqrtf(fmaxf(d2, 1e-12f));
-            g[r * kGLd + c] = __fdiv_rn(2.0f, expf(d) + 1.0f);
-        }
-        __syncthreads();
-    }
-    // ---- L1 row normalisation + mixing: one warp per row ----
-    const PoseGraph pose(a, b);
-    for (int r = warp; r < V; r += kHeadThreads / 32) {
-        float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f, ra = 0.f, rs = 0.f;
-        const int c1 = lane + 32;
-        if (a.learn_graph) { s0 = (lane < V) ? g[r * kGLd + lane] : 0.f; s1 = (c1 < V) ? g[r * kGLd + c1] : 0.f; rs = warp_sum(fabsf(s0) + fabsf(s1)); }
-        if (a.use_pose) { a0 = (lane < V) ? pose.at(r, lane) : 0.f; a1 = (c1 < V) ? pose.at(r, c1) : 0.f; ra = warp_sum(fabsf(a0) + fabsf(a1)); }
-        rs = fmaxf(rs, 1e-12f); ra = fmaxf(ra, 1e-12f);
-        float m0, m1;
-        if (a.learn_graph && a.use_pose) {
-            m0 = __fdiv_rn(__fdiv_rn(a0, ra) + __fdiv_rn(s0, rs), 2.0f);
-            m1 = __fdiv_rn(__fdiv_rn(a1, ra) + __fdiv_rn(s1, rs), 2.0f);
-        } else if (a.learn_graph) { m0 = __fdiv_rn(s0, rs); m1 = __fdiv_rn(s1, rs); }
-        else { m0 = __fdiv_rn(a0, ra); m1 = __fdiv_rn(a1, ra); }
-        __syncwarp();
-        g[r * kGLd + lane] = (lane < V) ? m0 : 0.f;
-        g[r * kGLd + c1] = (c1 < V) ? m1 : 0.f;
-    }
-    __syncthreads();
-    float y_scale = 1.0f;
-    if (a.fp16) {                                                // see graph_kernel
-        __shared__ float s_scale[2];
-        if (!a.learn_graph) {
-            for (int r = warp; r < V; r += kHeadThreads / 32) {
-                const float4 *row = reinterpret_cast<const float4 *>(x + static_cast<size_t>(r) * C);
-                float t = 0.f;
-                for (int i = lane; i < C / 4; i += 32) {
-                    const float4 v = __ldg(row + i);
-                    t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
-                }
-                t = warp_sum(t);
-                if (lane == 0) sq[r] = t;
-            }
-            __syncthreads();
-        }
-        if (warp == 0) {
-            float m = fmaxf(lane < V ? sq[lane] : 0.f, lane + 32 < V ? sq[lane + 32] : 0.f);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == 0) {
-                m = (m < 3.0e38f) ? sqrtf(m) : 0.f;
-                pow2_scales(m, &s_scale[0], &s_scale[1]);
-                a.y_unscale[b] = s_scale[1];
-            }
-        }
-        __syncthreads();
-        y_scale = s_scale[0];
-    }
-
-    // ---- Y = G . X ----
-    constexpr int kRows = 14;
-    const int rg = warp & 3, half = warp >> 2;
-    const float *xs = (half ? xs1 : xs0) + lane * 4;
-    const float *gr = g + rg * kRows * kGLd;
-    const size_t row0 = static_cast<size_t>(b) * V + rg * kRows;
-    const int n_pairs = C / (2 * kChunk);
-    stage_chunk_async(xs0, x, V, C, 0, tid);
-    stage_chunk_async(xs1, x, V, C, kChunk, tid);
-#pragma unroll 1
-    for (int it = 0; it < n_pairs; ++it) {
-        cp_async_wait<0>();
-        __syncthreads();
-        float acc[kRows][4];
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
-#pragma unroll 1
-        for (int j = 0; j < kV2Rows; j += 4) {
-            float4 xv[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) xv[jj] = *reinterpret_cast<const float4 *>(xs + (j + jj) * kXsLd);
-#pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                const float4 w = *reinterpret_cast<const float4 *>(gr + r * kGLd + j);
-                acc[r][0] = fmaf(w.x, xv[0].x, acc[r][0]); acc[r][1] = fmaf(w.x, xv[0].y, acc[r][1]);
-                acc[r][2] = fmaf(w.x, xv[0].z, acc[r][2]); acc[r][3] = fmaf(w.x, xv[0].w, acc[r][3]);
-                acc[r][0] = fmaf(w.y, xv[1].x, acc[r][0]); acc[r][1] = fmaf(w.y, xv[1].y, acc[r][1]);
-                acc[r][2] = fmaf(w.y, xv[1].z, acc[r][2]); acc[r][3] = fmaf(w.y, xv[1].w, acc[r][3]);
-                acc[r][0] = fmaf(w.z, xv[2].x, acc[r][0]); acc[r][1] = fmaf(w.z, xv[2].y, acc[r][1]);
-                acc[r][2] = fmaf(w.z, xv[2].z, acc[r][2]); acc[r][3] = fmaf(w.z, xv[2].w, acc[r][3]);
-                acc[r][0] = fmaf(w.w, xv[3].x, acc[r][0]); acc[r][1] = fmaf(w.w, xv[3].y, acc[r][1]);
-                acc[r][2] = fmaf(w.w, xv[3].z, acc[r][2]); acc[r][3] = fmaf(w.w, xv[3].w, acc[r][3]);
-            }
-        }
-        __syncthreads();                                         // every warp is done reading both buffers
-        if (it + 1 < n_pairs) {                                  // next pair flies while this one is stored
-            stage_chunk_async(xs0, x, V, C, (2 * it + 2) * kChunk, tid);
-            stage_chunk_async(xs1, x, V, C, (2 * it + 3) * kChunk, tid);
-        }
-        const int c0 = (2 * it + half) * kChunk + lane * 4;
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-            if (rg * kRows + r < V) {
-                float v0 = acc[r][0], v1 = acc[r][1], v2 = acc[r][2], v3 = acc[r][3];
-                __nv_bfloat16 *dst = a.y_planes + (row0 + r) * C + c0;
-                if (a.fp16) {
-                    const __half2 lo = __floats2half2_rn(v0 * y_scale, v1 * y_scale), hi = __floats2half2_rn(v2 * y_scale, v3 * y_scale);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-                    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-                    *reinterpret_cast<uint2 *>(dst) = pk;
-                    continue;
-                }
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    if (p < a.P) {
-                        // packed conversions (F2FP, full rate) -- the scalar F2F path runs at a quarter of it
-                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-                        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-                        *reinterpret_cast<uint2 *>(dst + p * a.plane_stride) = pk;
-                        v0 = __fsub_rn(v0, __uint_as_float(pk.x << 16)); v1 = __fsub_rn(v1, __uint_as_float(pk.x & 0xffff0000u));
-                        v2 = __fsub_rn(v2, __uint_as_float(pk.y << 16)); v3 = __fsub_rn(v3, __uint_as_float(pk.y & 0xffff0000u));
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// graph kernel on the tensor cores (graph_variant 8): the two 56 x 56 x 2048 products of a graph layer -- the Gram
+// graph kernel on the tensor cores: the two 56 x 56 x 2048 products of a graph layer -- the Gram
 // matrix X.X^T and the message passing Y = G.X -- as tcgen05 MMAs whose operands the CTA converts itself in shared
 // memory (no extra HBM traffic: X is read twice, Y planes written once, exactly as in the CUDA-core kernels).
 //   Gram   of the CENTRED nodes x_v - x_ref (x_ref = the whole-frame strip of frame 0): distances are translation
@@ -972,6 +515,23 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 (&out)[P]) {
         }
         out[p] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+// 8 scaled fp32 -> 8 fp16 (16 B), their residuals x 2^6 as E4M3 (8 B), the values x 2^-6 as E4M3 (8 B)
+__device__ __forceinline__ void split8_f16e4(const float (&v)[8], uint4 &h16, uint2 &res8, uint2 &val8) {
+    uint32_t hw[4], r[4], c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        hw[i] = *reinterpret_cast<const uint32_t *>(&h);
+        const float2 hf = __half22float2(h);
+        r[i] = __nv_cvt_float2_to_fp8x2(make_float2(__fsub_rn(v[2 * i], hf.x) * 64.0f, __fsub_rn(v[2 * i + 1], hf.y) * 64.0f),
+                                        __NV_SATFINITE, __NV_E4M3);
+        c[i] = __nv_cvt_float2_to_fp8x2(make_float2(v[2 * i] * 0.015625f, v[2 * i + 1] * 0.015625f), __NV_SATFINITE, __NV_E4M3);
+    }
+    h16 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    res8 = make_uint2(r[0] | (r[1] << 16), r[2] | (r[3] << 16));
+    val8 = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
 }
 
 __global__ void __launch_bounds__(kTcThreads, 2)
@@ -1201,7 +761,18 @@ graph_kernel_tc(GraphArgs a) {
                 const float4 lo = __ldg(src), hi = __ldg(src + 1);
                 const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
                 __nv_bfloat16 *dst = a.y_planes + (static_cast<size_t>(b) * S4 + qr) * C + cg * 8;
-                if (a.fp16) {
+                if (a.fp8) {
+                    float vs[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) vs[t] = v[t] * y_scale;
+                    uint4 h16; uint2 r8, c8;
+                    split8_f16e4(vs, h16, r8, c8);
+                    *reinterpret_cast<uint4 *>(dst) = h16;
+                    unsigned char *row8 = reinterpret_cast<unsigned char *>(a.y_planes + a.plane_stride + (static_cast<size_t>(b) * S4 + qr) * C) +
+                                          (cg >> 3) * 128 + (cg & 7) * 8;
+                    *reinterpret_cast<uint2 *>(row8) = r8;
+                    *reinterpret_cast<uint2 *>(row8 + 64) = c8;
+                } else if (a.fp16) {
                     uint32_t w[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -1329,7 +900,26 @@ graph_kernel_tc(GraphArgs a) {
 #pragma unroll
                 for (int hq = 0; hq < 2; ++hq) {
                     __nv_bfloat16 *dst = a.y_planes + (static_cast<size_t>(b) * V + erow) * C + cb * 128 + ehalf * 64 + hq * 32;
-                    if (a.fp16) {
+                    if (a.fp8) {
+                        // this thread's 64 channels are exactly k-block 2 cb + ehalf of the row
+                        unsigned char *row8 = reinterpret_cast<unsigned char *>(a.y_planes + a.plane_stride + (static_cast<size_t>(b) * V + erow) * C) +
+                                              (cb * 2 + ehalf) * 128 + hq * 32;
+#pragma unroll
+                        for (int qq = 0; qq < 2; ++qq) {
+                            uint4 h16[2]; uint2 r8[2], c8[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                float v[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[hq][16 * qq + 8 * e + i]) * y_scale;
+                                split8_f16e4(v, h16[e], r8[e], c8[e]);
+                            }
+                            reinterpret_cast<uint4 *>(dst)[2 * qq] = h16[0];
+                            reinterpret_cast<uint4 *>(dst)[2 * qq + 1] = h16[1];
+                            *reinterpret_cast<uint4 *>(row8 + qq * 16) = make_uint4(r8[0].x, r8[0].y, r8[1].x, r8[1].y);
+                            *reinterpret_cast<uint4 *>(row8 + 64 + qq * 16) = make_uint4(c8[0].x, c8[0].y, c8[1].x, c8[1].y);
+                        }
+                    } else if (a.fp16) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint32_t w[4];
@@ -1370,9 +960,9 @@ graph_kernel_tc(GraphArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// low-rank first layer, part 2 (option head_lowrank): out = (1 - gamma) X + gamma LeakyReLU(BN((G.T) . Z)) with
-// Z = Q.W^T (4S rows per tracklet, from the GEMM) and G.T (V x 4S, from graph_kernel_tc).  One thread per channel keeps
-// its column of Z in registers, the rows of G.T come as shared-memory broadcasts; grid (C / 256, tracklets).
+// low-rank first layer, part 2: out = (1 - gamma) X + gamma LeakyReLU(BN((G.T) . Z)) with
+// Z = Q.W^T (4S rows per tracklet, from the GEMM) and G.T (V x 4S, from graph_kernel_tc).  A thread keeps its columns of
+// Z in registers, the rows of G.T come as shared-memory broadcasts.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMixLd = 36;                             // 4S <= 36 for V <= 64, padded with zeros
 struct MixArgs {
@@ -1383,48 +973,12 @@ struct MixArgs {
     float gamma, slope;
 };
 
-__global__ void __launch_bounds__(kHeadThreads)
-graph_mix_kernel(MixArgs a) {
-    __shared__ __align__(16) float s_gt[kMaxNodes * kMixLd];
-    const int b = blockIdx.y, c = blockIdx.x * kHeadThreads + threadIdx.x;
-    const int V = a.V, S4 = a.S4, C = a.C;
-    const float *gt = a.gt + static_cast<size_t>(b) * V * S4;
-    for (int i = threadIdx.x; i < V * kMixLd; i += kHeadThreads) {
-        const int r = i / kMixLd, k = i - r * kMixLd;
-        s_gt[i] = (k < S4) ? gt[r * S4 + k] : 0.f;
-    }
-    float z[kMixLd];
-    const float *zc = a.z + static_cast<size_t>(b) * S4 * C + c;
-#pragma unroll
-    for (int k = 0; k < kMixLd; ++k) z[k] = (k < S4) ? __ldg(zc + static_cast<size_t>(k) * C) : 0.f;
-    const float sc = __ldg(a.scale + c), sh = __ldg(a.shift + c), keep = 1.0f - a.gamma;
-    const float *xc = a.x + static_cast<size_t>(b) * V * C + c;
-    float *oc = a.out + static_cast<size_t>(b) * V * C + c;
-    __syncthreads();
-#pragma unroll 4
-    for (int r = 0; r < V; ++r) {
-        const float xin = __ldg(xc + static_cast<size_t>(r) * C);
-        const float4 *g4 = reinterpret_cast<const float4 *>(s_gt + r * kMixLd);
-        float acc = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < kMixLd / 4; ++k4) {
-            const float4 w = g4[k4];
-            acc = fmaf(w.x, z[4 * k4 + 0], acc); acc = fmaf(w.y, z[4 * k4 + 1], acc);
-            acc = fmaf(w.z, z[4 * k4 + 2], acc); acc = fmaf(w.w, z[4 * k4 + 3], acc);
-        }
-        float h = fmaf(acc, sc, sh);
-        h = h >= 0.f ? h : h * a.slope;
-        oc[static_cast<size_t>(r) * C] = fmaf(a.gamma, h, keep * xin);
-    }
-}
-
-// Variant (option head_lowrank = 2, not yet measured): two channels per thread -- every shared-memory broadcast of four
-// G.T weights feeds eight FMAs instead of four -- and the residual rows of eight nodes loaded ahead of their use, so that
-// the row loop is not bound by the latency of one 4-byte load per 36 FMAs.  Same per-element arithmetic order as
-// graph_mix_kernel (k ascending, one fused multiply-add each): bit-identical results.  grid (C / 512, tracklets).
+// Two channels per thread -- every shared-memory broadcast of four G.T weights feeds eight FMAs -- and the residual rows
+// of eight nodes loaded ahead of their use, so that the row loop is not bound by the latency of one load per 36 FMAs.
+// grid (C / 512, tracklets).
 constexpr int kMixRows = 8;
 __global__ void __launch_bounds__(kHeadThreads, 2)
-graph_mix2_kernel(MixArgs a) {
+graph_mix_kernel(MixArgs a) {
     __shared__ __align__(16) float s_gt[kMaxNodes * kMixLd];
     const int b = blockIdx.y, c = (blockIdx.x * kHeadThreads + threadIdx.x) * 2;
     const int V = a.V, S4 = a.S4, C = a.C;
@@ -1553,10 +1107,15 @@ struct HeadWorkspace {
     __nv_bfloat16 *y_planes;
     float *z;                          // (batch, 4S, C) low-rank first layer: Q.W^T
     float *gt;                         // (batch, V, 4S) low-rank first layer: G.T
-    float *y_unscale;                  // (batch) fp16 mode
+    float *y_unscale;                  // (batch) scaled fp16 modes
     float *row_sumsq;                  // (batch*V, 32) partial row norms of the last layer's output
     size_t bytes;
 };
+
+// the first layer runs low-rank (G.X.W^T = (G.T).(Q.W^T) on the 4S quarter-strip rows) unless switched off or impossible
+static bool lowrank_enabled(const agrl_head_params *p, int S) {
+    return !p->lowrank_off && p->num_layers > 0 && p->channels % (2 * kHeadThreads) == 0 && S * kParts <= kMaxNodes;
+}
 
 static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t batch, int32_t S) {
     Carver c(ws);
@@ -1564,12 +1123,10 @@ static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t bat
     const size_t n = static_cast<size_t>(batch) * S * kParts * p->channels;
     w.x[0] = c.take<float>(n);
     w.x[1] = c.take<float>(n);
-    w.y_planes = c.take<__nv_bfloat16>(static_cast<size_t>(p->split) * n);
+    w.y_planes = c.take<__nv_bfloat16>(static_cast<size_t>(planes_of(p->split)) * n);
     w.y_unscale = c.take<float>(static_cast<size_t>(batch));
     w.row_sumsq = c.take<float>(static_cast<size_t>(batch) * S * kParts * 32);
-    // only with option head_lowrank (the option is read when the size is queried AND at the call: a change in between
-    // fails the size check of the call instead of overrunning)
-    const bool lowrank = option(kOptHeadLowrank) != 0;
+    const bool lowrank = lowrank_enabled(p, S);
     w.z = lowrank ? c.take<float>(static_cast<size_t>(batch) * S * 4 * p->channels) : nullptr;
     w.gt = lowrank ? c.take<float>(static_cast<size_t>(batch) * S * kParts * S * 4) : nullptr;
     w.bytes = c.total();
@@ -1579,58 +1136,19 @@ static HeadWorkspace carve_head(const agrl_head_params *p, void *ws, int64_t bat
 static int check_params(const agrl_head_params *p) {
     if (!p) return AGRL_E_INVALID;
     if (p->num_layers < 0 || p->num_layers > AGRL_HEAD_MAX_LAYERS) return AGRL_E_INVALID;
-    if (p->split != AGRL_SPLIT_BF16X2 && p->split != AGRL_SPLIT_BF16X3 && p->split != AGRL_SPLIT_FP16X1) return AGRL_E_INVALID;
+    if (p->split != AGRL_SPLIT_BF16X2 && p->split != AGRL_SPLIT_BF16X3 && p->split != AGRL_SPLIT_FP16X1 &&
+        p->split != AGRL_SPLIT_FP16_E4M3) return AGRL_E_INVALID;
     if (p->channels < kChunk || p->channels % kChunk != 0) return AGRL_E_UNSUPPORTED;
     if (!p->use_pose && !p->learn_graph) return AGRL_E_INVALID;            // vmgn.py:92 assert
+    if (p->pool_stages != 0 && (p->pool_stages < 2 || p->pool_stages > 12)) return AGRL_E_INVALID;
     return AGRL_OK;
 }
 
-template <int NT, int kBufs, int kMaxRegs>
-static int launch_graph_variant(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
-    const size_t smem = (static_cast<size_t>(kBufs * 4 * NT) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
-    auto kern = graph_kernel<NT, kBufs, kMaxRegs>;
-    AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
-    AGRL_LAUNCH_CHECK(st, "graph");
-    return AGRL_OK;
-}
-
-// option "graph_variant" (staging buffers, register cap -> CTAs per SM; 77 KiB smem double-buffered, 47 KiB single):
-//   0 = double, 128 (2/SM)   1 = single, 80 (3/SM)   2 = single, 128 (2/SM)   3 = double, 80
-//   4 = double, 112 and 5 = single, 112: two CTAs per SM NEXT TO a resident pooling CTA (48 regs x 160 threads)
-//   6 / 7 = graph_kernel_v2 (8x8 Gram tiles, 14x4 message-passing tiles) with 128 / 112 registers
-//   8 = graph_kernel_tc (default: both products on tcgen05, operands converted in shared memory)
-static int graph_variant() { return static_cast<int>(option(kOptGraphVariant)); }
-
-template <int kMaxRegs>
-static int launch_graph_v2(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
-    const size_t smem = (static_cast<size_t>(2 * kV2Rows) * kXsLd + kMaxNodes * kGLd + kMaxNodes) * sizeof(float);
-    auto kern = graph_kernel_v2<kMaxRegs>;
-    AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<static_cast<unsigned>(batch), kHeadThreads, smem, st>>>(ga);
-    AGRL_LAUNCH_CHECK(st, "graph");
-    return AGRL_OK;
-}
-
-template <int NT>
 static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
-    const bool v2_ok = ga.V <= kV2Rows && ga.C % (2 * kChunk) == 0;
-    if (graph_variant() >= 8 && ga.V <= kMaxNodes && ga.C % 128 == 0) {
-        AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-        graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, kTcSmem, st>>>(ga);
-        AGRL_LAUNCH_CHECK(st, "graph");
-        return AGRL_OK;
-    }
-    if (v2_ok && graph_variant() == 6) return launch_graph_v2<128>(ga, batch, st);
-    if (v2_ok && graph_variant() == 7) return launch_graph_v2<112>(ga, batch, st);
-    switch (graph_variant()) {
-        case 1: return launch_graph_variant<NT, 1, 80>(ga, batch, st);
-        case 2: return launch_graph_variant<NT, 1, 128>(ga, batch, st);
-        case 3: return launch_graph_variant<NT, 2, 80>(ga, batch, st);
-        case 4: return launch_graph_variant<NT, 2, 112>(ga, batch, st);
-        case 5: return launch_graph_variant<NT, 1, 112>(ga, batch, st);
-        default: return launch_graph_variant<NT, 2, 128>(ga, batch, st);
-    }
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+    graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, kTcSmem, st>>>(ga);
+    AGRL_LAUNCH_CHECK(st, "graph");
+    return AGRL_OK;
 }
 
 }  // namespace agrl
@@ -1656,8 +1174,8 @@ extern "C" int agrl_head_prepare_dev(const agrl_head_params *p, void *prepared, 
     for (int l = 0; l < p->num_layers; ++l) {
         if (!p->linear_weight[l] || !p->bn_weight[l] || !p->bn_bias[l] || !p->bn_mean[l] || !p->bn_var[l]) return AGRL_E_INVALID;
         fa.w[l] = p->bn_weight[l]; fa.b[l] = p->bn_bias[l]; fa.mean[l] = p->bn_mean[l]; fa.var[l] = p->bn_var[l];
-        gemm::SplitArgs sa{p->linear_weight[l], C, pr.w_planes[l], nullptr, C, C, C, p->split, 0};
-        if (p->split == AGRL_SPLIT_FP16X1) {
+        gemm::SplitArgs sa{p->linear_weight[l], C, pr.w_planes[l], nullptr, C, C, C, planes_of(p->split), 0};
+        if (scaled_mode(p->split)) {
             float *slot = pr.w_scale + 4 * l;
             AGRL_CUDA_TRY(cudaMemsetAsync(slot, 0, 4 * sizeof(float), st));
             absmax_kernel<<<4 * kNumSMs, 256, 0, st>>>(p->linear_weight[l], static_cast<size_t>(C) * C, slot);
@@ -1665,6 +1183,7 @@ extern "C" int agrl_head_prepare_dev(const agrl_head_params *p, void *prepared, 
             w_scale_kernel<<<1, 1, 0, st>>>(slot);
             AGRL_LAUNCH_CHECK(st, "w_scale");
             sa.fp16 = 1; sa.prescale = slot;
+            sa.fp8 = p->split == AGRL_SPLIT_FP16_E4M3;
         }
         if ((rc = gemm::launch_split_planes(sa, st))) return rc;
     }
@@ -1687,50 +1206,10 @@ extern "C" size_t agrl_head_workspace_bytes(const agrl_head_params *p, int64_t b
 
 namespace agrl {
 
-// Side stream + events of the sub-batched pipeline: one set per host thread (the ABI is re-entrant: one
-// host thread per GPU), created at first use and kept.
-constexpr int kMaxSubBatches = 64;
-struct HeadCtx {
-    cudaStream_t side = nullptr;
-    cudaEvent_t entry = nullptr, pooled[kMaxSubBatches] = {};
-    // gated pipeline: per sub-batch and partner kernel (graph layers.., attention) a "partner may start" event on the
-    // caller's stream and a "pooling piece done" event on the side stream
-    cudaEvent_t start[kMaxSubBatches][AGRL_HEAD_MAX_LAYERS + 1] = {}, piece[kMaxSubBatches][AGRL_HEAD_MAX_LAYERS + 1] = {};
-    int device = -1;
-    int ensure() {
-        int dev = -1;
-        AGRL_CUDA_TRY(cudaGetDevice(&dev));
-        if (side && dev == device) return AGRL_OK;
-        if (side) {
-            cudaStreamDestroy(side); side = nullptr;
-            cudaEventDestroy(entry);
-            for (int i = 0; i < kMaxSubBatches; ++i) {
-                cudaEventDestroy(pooled[i]);
-                for (int k = 0; k <= AGRL_HEAD_MAX_LAYERS; ++k) { cudaEventDestroy(start[i][k]); cudaEventDestroy(piece[i][k]); }
-            }
-        }
-        int lo = 0, hi = 0;
-        AGRL_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        AGRL_CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));     // highest priority
-        AGRL_CUDA_TRY(cudaEventCreateWithFlags(&entry, cudaEventDisableTiming));
-        for (int i = 0; i < kMaxSubBatches; ++i) {
-            AGRL_CUDA_TRY(cudaEventCreateWithFlags(&pooled[i], cudaEventDisableTiming));
-            for (int k = 0; k <= AGRL_HEAD_MAX_LAYERS; ++k) {
-                AGRL_CUDA_TRY(cudaEventCreateWithFlags(&start[i][k], cudaEventDisableTiming));
-                AGRL_CUDA_TRY(cudaEventCreateWithFlags(&piece[i][k], cudaEventDisableTiming));
-            }
-        }
-        device = dev;
-        return AGRL_OK;
-    }
-};
-static thread_local HeadCtx tl_head_ctx;
-
 // pooling of `n` tracklets starting at tracklet `b0`, on stream `st`
-// (TMA flavour only: `part` / `parts` selects a contiguous slice of the work units, see the gated pipeline)
 static int launch_pool(const agrl_head_params *p, const Prepared &pr, const HeadWorkspace &hwk, const float *x4_1,
                        const float *x4_2, float *out, int64_t ld_out, int64_t b0, int64_t n, int S, int hw, bool tma,
-                       int ctas_per_sm, cudaStream_t st, int64_t unit_lo = 0, int64_t unit_hi = -1, int wide_sms = 0) {
+                       cudaStream_t st) {
     const int C = p->channels, V = S * kParts, L = p->num_layers;
     const size_t in_off = static_cast<size_t>(b0) * S * C * hw;
     float *nodes = hwk.x[0] + static_cast<size_t>(b0) * V * C;
@@ -1744,44 +1223,12 @@ static int launch_pool(const agrl_head_params *p, const Prepared &pr, const Head
         return AGRL_OK;
     }
     if (tma) {
-        const int64_t all_units = n * (C / kTpCh);
-        if (unit_hi < 0) unit_hi = all_units;
-        if (unit_hi <= unit_lo) return AGRL_OK;
+        const int64_t units = n * (C / kTpCh);
         PoolTmaArgs ta{x4_1 + in_off, x4_2 + in_off, nodes, o, ld_out, pr.scale[L], pr.shift[L], S, C,
-                       static_cast<int>(option(kOptPoolStages)), static_cast<int>(unit_lo), static_cast<int>(unit_hi),
-                       static_cast<int>(option(kOptPoolHint))};
-        const int64_t units = unit_hi - unit_lo;
-        if (wide_sms > 0) {
-            // spatial partition: one two-lane CTA per SM on `wide_sms` SMs; the ring is made as deep as the SM's shared
-            // memory allows (>= 5 stages per lane), which also keeps every graph / GEMM CTA off these SMs
-            int stages = ta.stages < 5 ? 5 : ta.stages;
-            while (stages > 2 && pool_tma_smem(S, stages, 2) > 227u * 1024u) --stages;
-            ta.stages = stages;
-            const size_t wsmem = pool_tma_smem(S, stages, 2);
-            if (wsmem > 227u * 1024u) return AGRL_E_UNSUPPORTED;
-            AGRL_CUDA_TRY(cudaFuncSetAttribute(pool_tma_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem)));
-            int64_t wgrid = wide_sms < kNumSMs ? wide_sms : kNumSMs;
-            if (wgrid * 2 > units) wgrid = (units + 1) / 2;
-            if (option(kOptGemmPair) != 0 && wgrid % 2 == 0) {
-                // the GEMMs run as CTA pairs (two SMs of one TPC): launch the pooling CTAs as clusters of two as well, so
-                // that they fill whole TPCs instead of taking one SM out of twice as many
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(static_cast<unsigned>(wgrid)); cfg.blockDim = dim3(2 * kTpThreads);
-                cfg.dynamicSmemBytes = wsmem; cfg.stream = st;
-                cudaLaunchAttribute at;
-                at.id = cudaLaunchAttributeClusterDimension;
-                at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-                cfg.attrs = &at; cfg.numAttrs = 1;
-                AGRL_CUDA_TRY(cudaLaunchKernelEx(&cfg, pool_tma_wide_kernel, ta));
-            } else {
-                pool_tma_wide_kernel<<<static_cast<unsigned>(wgrid), 2 * kTpThreads, wsmem, st>>>(ta);
-            }
-            AGRL_LAUNCH_CHECK(st, "pool");
-            return AGRL_OK;
-        }
+                       p->pool_stages ? p->pool_stages : 4, 0, static_cast<int>(units), p->pool_no_l2_hint ? 0 : 1};
         const size_t smem = pool_tma_smem(S, ta.stages);
         AGRL_CUDA_TRY(cudaFuncSetAttribute(pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int64_t grid = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+        int64_t grid = static_cast<int64_t>(kNumSMs) * 2;                 // persistent, two small CTAs per SM
         if (grid > units) grid = units;
         pool_tma_kernel<<<static_cast<unsigned>(grid), kTpThreads, smem, st>>>(ta);
         AGRL_LAUNCH_CHECK(st, "pool");
@@ -1797,42 +1244,23 @@ static int launch_pool(const agrl_head_params *p, const Prepared &pr, const Head
     return AGRL_OK;
 }
 
-// Gated pipeline hook: the pooling of the NEXT sub-batch is cut into one piece per "partner" kernel of this
-// sub-batch (graph kernel of each layer, attention).  A piece starts when its partner may start and the GEMM
-// that follows the partner waits for the piece: the HBM stream runs under the CUDA-core kernels only, never
-// under the GEMMs (GEMM and pooling together exceed the L2 throughput and evict each other's lines).
-struct Gate {
-    HeadCtx *ctx;
-    int j;                                   // this sub-batch
-    int64_t next_b0, next_n;                 // the sub-batch whose pooling is hidden here (next_n == 0: none)
-    const agrl_head_params *p; const Prepared *pr; const HeadWorkspace *hwk;
-    const float *x4_1, *x4_2; float *out; int64_t ld_out; int S, hw, ctas;
-    // partner k of L+1: units [lo, hi) of the next sub-batch's pooling
-    int partner(int k, int L, cudaStream_t st) const {
-        if (next_n == 0) return AGRL_OK;
-        const int64_t units = next_n * (p->channels / kTpCh);
-        const double wa = 0.25, tot = L + wa;                       // graph kernels weigh 1, attention 0.25
-        auto edge = [&](int i) { return i >= L + 1 ? units : static_cast<int64_t>(units * (i / tot)); };
-        AGRL_CUDA_TRY(cudaEventRecord(ctx->start[j][k], st));
-        AGRL_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->start[j][k], 0));
-        int rc = launch_pool(p, *pr, *hwk, x4_1, x4_2, out, ld_out, next_b0, next_n, S, hw, true, ctas, ctx->side, edge(k), edge(k + 1));
-        if (rc) return rc;
-        AGRL_CUDA_TRY(cudaEventRecord(ctx->piece[j][k], ctx->side));
-        return AGRL_OK;
+// one GEMM of a graph layer in the caller's operand mode; Epi is built by `make(fp8)` for the scaled modes
+template <class EpiBf16, class EpiF16, class EpiF16E4>
+static int launch_layer_gemm(int split, const CUtensorMap &map_a, const CUtensorMap &map_w, int rows, int C,
+                             const EpiBf16 &e2, const EpiF16 &e1, const EpiF16E4 &e4, cudaStream_t st) {
+    switch (split) {
+        case AGRL_SPLIT_FP16X1: return gemm::launch_split_gemm<1, 256, false>(map_a, map_w, rows, C, C, e1, st);
+        case AGRL_SPLIT_FP16_E4M3: return gemm::launch_split_gemm<2, 256, false>(map_a, map_w, rows, C, C, e4, st);
+        case AGRL_SPLIT_BF16X3: return gemm::launch_split_gemm<3, 128, false>(map_a, map_w, rows, C, C, e2, st);
+        default: return gemm::launch_split_gemm<2, 256, false>(map_a, map_w, rows, C, C, e2, st);
     }
-    int join(int k, cudaStream_t st) const {                      // the caller's stream waits for piece k
-        if (next_n == 0) return AGRL_OK;
-        AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx->piece[j][k], 0));
-        return AGRL_OK;
-    }
-};
+}
 
 // graph layers + attention of `n` tracklets starting at tracklet `b0` (their nodes are in hwk.x[0])
 static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWorkspace hwk, const float *adj,
                          const uint64_t *masks, float *out,
-                         int64_t ld_out, float *nodes_out, int64_t b0, int64_t n, int64_t batch, int S, cudaStream_t st,
-                         const Gate *gate = nullptr, int gemm_ctas = 0) {
-    const int C = p->channels, V = S * kParts, L = p->num_layers;
+                         int64_t ld_out, float *nodes_out, int64_t b0, int64_t n, int64_t batch, int S, cudaStream_t st) {
+    const int C = p->channels, V = S * kParts, L = p->num_layers, P = planes_of(p->split);
     const int64_t rows = n * V, row0 = b0 * V, all_rows = batch * V;
     float *x[2] = {hwk.x[0] + row0 * C, hwk.x[1] + row0 * C};
     __nv_bfloat16 *y = hwk.y_planes + row0 * C;
@@ -1843,100 +1271,72 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
     const float *attn_sumsq = nullptr;
     int attn_slots = 0;
     CUtensorMap map_y, map_w;
-    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, y, rows, C, p->split, gemm::BM, all_rows))) return rc;
+    if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, y, rows, C, P, gemm::BM, all_rows))) return rc;
+    const int scaled = scaled_mode(p->split), fp8 = p->split == AGRL_SPLIT_FP16_E4M3;
+    const int bn = p->split == AGRL_SPLIT_BF16X3 ? 128 : 256;
     int cur = 0;
     for (int l = 0; l < L; ++l) {
-        const int fp16 = p->split == AGRL_SPLIT_FP16X1;
-        GraphArgs ga{x[cur], adj, masks, y, all_rows * C, V, C, p->split, p->use_pose, p->learn_graph, fp16, hwk.y_unscale + b0};
-        const bool pair = option(kOptGemmPair) != 0;
-        const int pair_direct = option(kOptGemmPair) >= 2;      // both CTAs' loads signal the leader's barrier
-        const int bn = p->split == AGRL_SPLIT_BF16X3 ? 128 : 256;
+        GraphArgs ga{x[cur], adj, masks, y, all_rows * C, V, C, P, p->use_pose, p->learn_graph, scaled, hwk.y_unscale + b0};
+        ga.fp8 = fp8;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
-        // Low-rank first layer (option head_lowrank): only layer 0 sees nodes that are T.(quarter strips); needs the
-        // tensor-core graph kernel (it emits G.T and the Q planes) and whole frames of 7 nodes
-        const bool lowrank = l == 0 && hwk.z && graph_variant() >= 8 && V <= kMaxNodes && V % kParts == 0 && C % 256 == 0 && !pair;
-        if (lowrank) {
-            const int S4 = (V / kParts) * 4;
+        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, P, bn, C))) return rc;
+        // Low-rank first layer: only layer 0 sees nodes that are T.(quarter strips)
+        if (l == 0 && hwk.z) {
+            const int S4 = S * 4;
             const int64_t qrows = n * S4, q_all = batch * S4;
             __nv_bfloat16 *yq = hwk.y_planes + b0 * S4 * C;
             float *z = hwk.z + b0 * S4 * C;
             ga.y_planes = yq; ga.plane_stride = q_all * C; ga.lowrank = 1; ga.gt = hwk.gt + b0 * V * S4;
-            if (gate && (rc = gate->partner(l, L, st))) return rc;
             AGRL_LAUNCH_BEGIN(st);
-            if ((rc = launch_graph<14>(ga, n, st))) return rc;
+            if ((rc = launch_graph(ga, n, st))) return rc;
             CUtensorMap map_q;
-            if ((rc = gemm::make_plane_tensor_map(&map_q, yq, qrows, C, p->split, gemm::BM, q_all))) return rc;
-            if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, bn, C))) return rc;
-            if (gate && (rc = gate->join(l, st))) return rc;
+            if ((rc = gemm::make_plane_tensor_map(&map_q, yq, qrows, C, P, gemm::BM, q_all))) return rc;
             AGRL_LAUNCH_BEGIN(st);
-            if (fp16) {
-                gemm::EpiPlainT<true> ez{z, C, hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, S4};
-                rc = gemm::launch_split_gemm<1, 256, false>(map_q, map_w, static_cast<int>(qrows), C, C, ez, st, gemm_ctas);
-            } else {
-                gemm::EpiPlainT<false> ez{z, C, nullptr, nullptr, S4};
-                rc = p->split == AGRL_SPLIT_BF16X3
-                         ? gemm::launch_split_gemm<3, 128, false>(map_q, map_w, static_cast<int>(qrows), C, C, ez, st, gemm_ctas)
-                         : gemm::launch_split_gemm<2, 256, false>(map_q, map_w, static_cast<int>(qrows), C, C, ez, st, gemm_ctas);
-            }
-            if (rc) return rc;
+            gemm::EpiPlainT<false> z2{z, C, nullptr, nullptr, S4};
+            gemm::EpiPlainT<true> z1{z, C, hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, S4};
+            gemm::EpiPlainT<true, true> z4{z, C, hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, S4};
+            if ((rc = launch_layer_gemm(p->split, map_q, map_w, static_cast<int>(qrows), C, z2, z1, z4, st))) return rc;
             MixArgs ma{x[cur], z, ga.gt, dst, pr.scale[l], pr.shift[l], V, S4, C, p->gamma, p->leaky_slope};
             AGRL_LAUNCH_BEGIN(st);
-            if (option(kOptHeadLowrank) >= 2 && C % (2 * kHeadThreads) == 0)
-                graph_mix2_kernel<<<dim3(C / (2 * kHeadThreads), static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
-            else
-                graph_mix_kernel<<<dim3(C / kHeadThreads, static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
+            graph_mix_kernel<<<dim3(C / (2 * kHeadThreads), static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
             AGRL_LAUNCH_CHECK(st, "graph_mix");
             if (dst == nodes_out) x[cur ^ 1] = nodes_out;
             cur ^= 1;
             continue;
         }
-        if (gate && (rc = gate->partner(l, L, st))) return rc;
         AGRL_LAUNCH_BEGIN(st);
-        if (V == 56) rc = launch_graph<14>(ga, n, st); else rc = launch_graph<16>(ga, n, st);
-        if (rc) return rc;
-        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, p->split, pair ? bn / 2 : bn, C))) return rc;
-        gemm::EpiGraphLayer epi{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope, nullptr, nullptr, V};
+        if ((rc = launch_graph(ga, n, st))) return rc;
         const int sumsq_slots = 2 * ((C + bn - 1) / bn);                 // (column tile, half) pairs of the direct epilogue
         float *sumsq = (l == L - 1 && C % bn == 0) ? hwk.row_sumsq + row0 * 32 : nullptr;
-        if (sumsq) { epi.row_sumsq = sumsq; epi.sumsq_slots = sumsq_slots; attn_sumsq = sumsq; attn_slots = sumsq_slots; }
-        if (gate && (rc = gate->join(l, st))) return rc;
+        if (sumsq) { attn_sumsq = sumsq; attn_slots = sumsq_slots; }
+        gemm::EpiGraphLayer e2{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope, nullptr, nullptr, V};
+        gemm::EpiGraphLayerF16 e1{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
+                                  hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
+        gemm::EpiGraphLayerF16E4 e4{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
+                                    hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
+        e2.row_sumsq = e1.row_sumsq = e4.row_sumsq = sumsq;
+        e2.sumsq_slots = e1.sumsq_slots = e4.sumsq_slots = sumsq ? sumsq_slots : 0;
         AGRL_LAUNCH_BEGIN(st);
-        if (fp16) {
-            gemm::EpiGraphLayerF16 epi16{x[cur], pr.scale[l], pr.shift[l], dst, C, C, p->gamma, p->leaky_slope,
-                                         hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, V};
-            epi16.row_sumsq = epi.row_sumsq; epi16.sumsq_slots = epi.sumsq_slots;
-            rc = pair ? gemm::launch_pair_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas, pair_direct)
-                      : gemm::launch_split_gemm<1, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi16, st, gemm_ctas);
-        } else if (p->split == AGRL_SPLIT_BF16X3) {
-            rc = pair ? gemm::launch_pair_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas, pair_direct)
-                      : gemm::launch_split_gemm<3, 128, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
-        } else {
-            rc = pair ? gemm::launch_pair_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas, pair_direct)
-                      : gemm::launch_split_gemm<2, 256, false>(map_y, map_w, static_cast<int>(rows), C, C, epi, st, gemm_ctas);
-        }
-        if (rc) return rc;
+        if ((rc = launch_layer_gemm(p->split, map_y, map_w, static_cast<int>(rows), C, e2, e1, e4, st))) return rc;
         if (dst == nodes_out) x[cur ^ 1] = nodes_out;
         cur ^= 1;
     }
     if (L == 0 && nodes_out)
         AGRL_CUDA_TRY(cudaMemcpyAsync(nodes_out, x[0], sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
     AttnArgs aa{x[cur], out + static_cast<size_t>(b0) * ld_out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C, attn_sumsq, attn_slots};
-    if (gate && (rc = gate->partner(L, L, st))) return rc;
     AGRL_LAUNCH_BEGIN(st);
     attn_kernel<<<static_cast<unsigned>(n), kHeadThreads, 0, st>>>(aa);
     AGRL_LAUNCH_CHECK(st, "attn");
-    if (gate && (rc = gate->join(L, st))) return rc;              // the next sub-batch's nodes are complete
     return AGRL_OK;
 }
 
 }  // namespace agrl
 
-// Pipeline.  The maps are the only HBM-heavy input; everything after the pooling works on the 27x smaller
-// node tensor and is bound by the tensor pipe / CUDA cores.  With batch > head_sub_batch the batch is cut
-// into sub-batches: all poolings are queued on a high-priority side stream (persistent, small CTAs), the
-// graph layers + attention of sub-batch i wait for pooling i on the caller's stream -- so pooling i+1
-// streams from HBM underneath the compute of sub-batch i.  The caller's stream observes every kernel of
-// the call (it waits on each pooling event), so stream-ordered use of `out` stays valid.
+// Pipeline: pooling, then per layer graph kernel -> GEMM (-> mixing kernel for the low-rank first layer), attention; all on
+// the caller's stream, no allocation, no synchronisation, no state outside the caller's buffers (re-entrant).  The
+// maps are the only HBM-heavy input; every phase runs the board at its power limit (profiles/r2/energy_probe.log: the
+// pooling kernel alone draws ~960 W while it streams at the HBM peak), so co-scheduling phases cannot shorten the pass
+// -- the round-1 sub-batch / partition plumbing measured exactly that and is gone.
 static int head_forward_impl(const agrl_head_params *p, const void *prepared,
                              const float *x4_1, const float *x4_2, const float *adj, const uint64_t *masks,
                              float *out, int64_t ld_out, float *nodes_out,
@@ -1959,59 +1359,13 @@ static int head_forward_impl(const agrl_head_params *p, const void *prepared,
     if (adj) masks = nullptr;
 
     if (p->maps_nhwc && (((reinterpret_cast<uintptr_t>(x4_1) | reinterpret_cast<uintptr_t>(x4_2)) & 15u) != 0)) return AGRL_E_UNSUPPORTED;
-    const bool tma = !p->maps_nhwc && option(kOptPoolTma) != 0 && hw == 128 && C % kTpCh == 0 &&
+    const bool tma = !p->maps_nhwc && !p->pool_register_loads && hw == 128 && C % kTpCh == 0 &&
                      ((reinterpret_cast<uintptr_t>(x4_1) | reinterpret_cast<uintptr_t>(x4_2)) & 15u) == 0;
-    int64_t sub = option(kOptHeadSubBatch);
-    if (sub > 0 && (batch + sub - 1) / sub > kMaxSubBatches) sub = (batch + kMaxSubBatches - 1) / kMaxSubBatches;
-    const int ctas = static_cast<int>(option(kOptPoolCtasPerSm));
     constexpr int64_t kMaxPerLaunch = 32768;           // grid.y / int index limits of the per-tracklet kernels
-
-    if (sub <= 0 || batch <= sub) {
-        // one pass on the caller's stream
-        for (int64_t b0 = 0; b0 < batch; b0 += kMaxPerLaunch) {
-            const int64_t n = batch - b0 < kMaxPerLaunch ? batch - b0 : kMaxPerLaunch;
-            if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, tma ? 2 : 1, st))) return rc;
-            if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
-        }
-        return AGRL_OK;
-    }
-    HeadCtx &ctx = tl_head_ctx;
-    if ((rc = ctx.ensure())) return rc;
-    const int nsub = static_cast<int>((batch + sub - 1) / sub);
-    AGRL_CUDA_TRY(cudaEventRecord(ctx.entry, st));
-    AGRL_CUDA_TRY(cudaStreamWaitEvent(ctx.side, ctx.entry, 0));
-    if (tma && option(kOptOverlapMode) == 1) {
-        // gated: pooling 0 alone (2 CTAs per SM), then every sub-batch hides the next one's pooling pieces
-        const int64_t n0 = batch < sub ? batch : sub;
-        if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, 0, n0, S, hw, true, 2, ctx.side))) return rc;
-        AGRL_CUDA_TRY(cudaEventRecord(ctx.pooled[0], ctx.side));
-        AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx.pooled[0], 0));
-        for (int j = 0; j < nsub; ++j) {
-            const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
-            const int64_t nb0 = b0 + n, nn = j + 1 < nsub ? (batch - nb0 < sub ? batch - nb0 : sub) : 0;
-            Gate gate{&ctx, j, nb0, nn, p, &pr, &hwk, x4_1, x4_2, out, ld_out, S, hw, ctas};
-            if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st, &gate))) return rc;
-        }
-        return AGRL_OK;
-    }
-    // Spatial partition (option pool_sms, experimental): pooling 0 has the chip to itself (two CTAs per SM); poolings
-    // 1.. are wide CTAs on pool_sms SMs, and while one of them can be running the persistent GEMMs keep to the other
-    // SMs (gemm_sms, default all minus pool_sms).  The last sub-batch's GEMMs have no pooling beside them: full width.
-    const int psms = tma ? static_cast<int>(option(kOptPoolSms)) : 0;
-    int gsms = static_cast<int>(option(kOptGemmSms));
-    if (psms > 0 && gsms == 0) gsms = kNumSMs - psms > 0 ? kNumSMs - psms : 1;
-    for (int j = 0; j < nsub; ++j) {
-        const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
-        const bool wide = psms > 0 && j > 0;
-        if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, (psms > 0 && j == 0) ? 2 : ctas, ctx.side,
-                              0, -1, wide ? psms : 0))) return rc;
-        AGRL_CUDA_TRY(cudaEventRecord(ctx.pooled[j], ctx.side));
-    }
-    for (int j = 0; j < nsub; ++j) {
-        const int64_t b0 = j * sub, n = batch - b0 < sub ? batch - b0 : sub;
-        AGRL_CUDA_TRY(cudaStreamWaitEvent(st, ctx.pooled[j], 0));
-        const int gemm_ctas = (psms > 0 && j + 1 < nsub) ? gsms : 0;
-        if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st, nullptr, gemm_ctas))) return rc;
+    for (int64_t b0 = 0; b0 < batch; b0 += kMaxPerLaunch) {
+        const int64_t n = batch - b0 < kMaxPerLaunch ? batch - b0 : kMaxPerLaunch;
+        if ((rc = launch_pool(p, pr, hwk, x4_1, x4_2, out, ld_out, b0, n, S, hw, tma, st))) return rc;
+        if ((rc = launch_layers(p, pr, hwk, adj, masks, out, ld_out, nodes_out, b0, n, batch, S, st))) return rc;
     }
     return AGRL_OK;
 }
@@ -2077,3 +1431,4 @@ extern "C" int agrl_clip_pool_dev(const float *feats, int64_t ld_feat, int64_t t
     AGRL_LAUNCH_CHECK(st, "clip_pool");
     return AGRL_OK;
 }
+

@@ -8,6 +8,7 @@
 #include "gemm_sm100.cuh"
 
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <mutex>
 
 namespace agrl {
@@ -60,7 +61,18 @@ split_planes_kernel(SplitArgs a) {
         if (a.normalize) { x0 = __fdiv_rn(x0, inv); x1 = __fdiv_rn(x1, inv); }
         if (a.fp16) {
             const float ps = __ldg(a.prescale);
-            *reinterpret_cast<__half2 *>(dst + i) = __floats2half2_rn(x0 * ps, x1 * ps);
+            const __half2 h = __floats2half2_rn(x0 * ps, x1 * ps);
+            *reinterpret_cast<__half2 *>(dst + i) = h;
+            if (a.fp8) {
+                // B-operand layout of the 8-bit plane: [value copies | residuals] per 64-element k-block
+                const float2 hf = __half22float2(h);
+                unsigned char *row8 = reinterpret_cast<unsigned char *>(dst + plane_stride) + (i >> 6) * 128 + (i & 63);
+                *reinterpret_cast<__nv_fp8x2_storage_t *>(row8) =
+                    __nv_cvt_float2_to_fp8x2(make_float2(x0 * ps * 0.015625f, x1 * ps * 0.015625f), __NV_SATFINITE, __NV_E4M3);
+                *reinterpret_cast<__nv_fp8x2_storage_t *>(row8 + 64) =
+                    __nv_cvt_float2_to_fp8x2(make_float2(__fsub_rn(x0 * ps, hf.x) * 64.0f, __fsub_rn(x1 * ps, hf.y) * 64.0f),
+                                             __NV_SATFINITE, __NV_E4M3);
+            }
             continue;
         }
 #pragma unroll

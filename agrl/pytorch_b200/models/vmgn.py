@@ -95,7 +95,7 @@ class VMGN(nn.Module):
     """GSTA of the reference (vmgn.py:214-357) with the graph head on libagrl_b200."""
 
     def __init__(self, num_classes, loss, num_split, pyramid_part, num_gb, use_pose, learn_graph,
-                 consistent_loss=False, pretrained=True, head_split=_lib.SPLIT_BF16X2, **kwargs):
+                 consistent_loss=False, pretrained=True, head_split=_lib.SPLIT_FP16_E4M3, **kwargs):
         super().__init__()
         self.loss = loss
         self.feature_dim = 512 * _Block.expansion
@@ -131,6 +131,11 @@ class VMGN(nn.Module):
         _init_neck(self.att_bottleneck, self.att_classifier)
 
         self.head_split = head_split
+        # tuning knobs of the head, per module (they travel in agrl_head_params; the library has no global state)
+        self.head_lowrank = True         # first layer's X.W^T on the 4S quarter-strip rows (False: on all 7S node rows)
+        self.pool_tma = True             # bulk-copy (TMA ring) pooling kernel where it applies (False: register loads)
+        self.pool_stages = 0             # ring stages per pooling CTA (0 = library default)
+        self.pool_l2_hint = True         # evict-first hint on the pooling bulk copies
         self._prep = {}                  # device -> (key, prepared buffer): what the cached buffer was built from
         self._ws = {}                    # (device, stream) -> workspace
 
@@ -161,6 +166,8 @@ class VMGN(nn.Module):
         P.use_pose, P.learn_graph = int(self.use_pose), int(self.learn_graph)
         P.gamma = self.graph_layers[0].gamma if self.num_gb else 0.1
         P.leaky_slope, P.bn_eps, P.split = 0.1, 1e-5, self.head_split
+        P.lowrank_off, P.pool_register_loads = int(not self.head_lowrank), int(not self.pool_tma)
+        P.pool_stages, P.pool_no_l2_hint = int(self.pool_stages), int(not self.pool_l2_hint)
         tensors, key = [], []
 
         def ptr(t):

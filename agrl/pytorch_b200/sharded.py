@@ -31,6 +31,16 @@ def shard_bounds(n, world):
     return out
 
 
+def or_across_ranks(status, group=None):
+    """Bitwise OR of every rank's status word (bit flags: LABEL_RANGE, ZERO_DIVISION, TOPK_OVERFLOW, ...), in place.
+    NCCL has no BOR reduction: the word is expanded into one 0/1 lane per bit, all-reduced with MAX and re-packed."""
+    shifts = torch.arange(16, device=status.device, dtype=torch.int32)
+    bits = (status.to(torch.int32).view(-1, 1) >> shifts) & 1
+    dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
+    status.copy_((bits << shifts).sum(dim=1).to(status.dtype).view_as(status))
+    return status
+
+
 class CudaOps(object):
     """Per-rank compute on the rank's current CUDA device (libagrl_b200)."""
 
@@ -253,7 +263,7 @@ def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids
         dist.all_gather_into_tensor(cls_all, cls, group=group)
         keys_all, cls_all = keys_all.view(world, nq, max_rank), cls_all.view(world, nq, max_rank)
         dist.all_reduce(ngood, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(status, op=dist.ReduceOp.BOR, group=group)   # status words are bit flags
+        or_across_ranks(status, group)
     else:
         keys_all, cls_all = keys.unsqueeze(0), cls.unsqueeze(0)
     return ops.merge(keys_all, cls_all, ngood, max_rank, status)
@@ -302,7 +312,7 @@ def evaluate_market1501_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_
         dist.all_gather_into_tensor(keys_all, keys, group=group)
         keys_all = keys_all.view(world, nq, cap)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(status, op=dist.ReduceOp.BOR, group=group)   # status words are bit flags
+        or_across_ranks(status, group)
     else:
         keys_all = keys.unsqueeze(0)
     cnt, srt = ops.market_bin(d, offset, keys_all)

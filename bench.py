@@ -336,6 +336,8 @@ def run_b200(args):
         # ---- the same head pass with the opt-in single-plane fp16 graph-layer GEMM (reported beside, not as `value`) --
         fast = None
         if not args.no_fast_mode:
+            default_split = model.head_split
+
             def fast_mode():
                 model.head_split = _lib.SPLIT_FP16X1
                 try:
@@ -344,7 +346,7 @@ def run_b200(args):
                         head_pass()
                     return dict(head_ms=ms, kernels={k: round(t, 4) for k, (n, t) in fprof.totals().items()})
                 finally:
-                    model.head_split = _lib.SPLIT_BF16X2
+                    model.head_split = default_split
             fast = guarded(fast_mode)
             head_pass()                                  # features of the default mode again
             cx.barrier()
@@ -382,7 +384,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    lowrank_on = _lib.get_option('head_lowrank') != 0
+    lowrank_on = bool(getattr(model, 'head_lowrank', True))
     table, head_dram = kernel_table(timeline, pk, J, lowrank_on)
     top = max(timeline.items(), key=lambda kv: kv[1][1])[0]
     head_gbs = J * BYTES_PER_TRACKLET / (head_ms * 1e-3) / 1e9
@@ -403,9 +405,8 @@ def run_b200(args):
         'config': {'workload': WORKLOAD % args.dist_metric,
                    'tracklets_per_step_per_gpu': J, 'pool_tracklets': pool_n,
                    'head': 'bulk-copy pooling (TMA ring), graph layers on tcgen05 (graph_kernel_tc + bf16x2 split GEMM, 3 products; '
-                           'first layer on the 32 quarter-strip rows per tracklet); options %s' % (
-                       {k: _lib.get_option(k) for k in ('head_sub_batch', 'pool_tma', 'pool_stages', 'graph_variant', 'gemm_pair',
-                                                        'head_lowrank')},),
+                           'first layer on the 32 quarter-strip rows per tracklet); knobs %s' % (
+                       {k: getattr(model, k, None) for k in ('head_split', 'head_lowrank', 'pool_tma', 'pool_stages', 'pool_l2_hint')},),
                    'cache': 'input pool %.1f GB per GPU, larger than L2; cycled' % (pool_n * BYTES_PER_TRACKLET / 1e9),
                    'parallelism': 'independent head shards + gallery-sharded eval (NCCL merge)' if world > 1 else 'single GPU'},
         'head_ms': head_ms, 'eval_ms': eval_ms,
@@ -718,7 +719,7 @@ def sweep_measure(args, cx, steps, warm):
             ka = torch.empty(world * nq, K, dtype=keys.dtype, device=dev)
             ca = torch.empty(world * nq, K, dtype=cls.dtype, device=dev)
             dist.all_gather_into_tensor(ka, keys); dist.all_gather_into_tensor(ca, cls)
-            nall = ngood.clone(); dist.all_reduce(nall); dist.all_reduce(st, op=dist.ReduceOp.BOR)
+            nall = ngood.clone(); dist.all_reduce(nall); sharded.or_across_ranks(st)
             return ops.merge(ka.view(world, nq, K), ca.view(world, nq, K), nall, K, st)
         return ops.merge(keys.unsqueeze(0), cls.unsqueeze(0), ngood, K, st)
 

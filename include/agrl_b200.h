@@ -13,8 +13,9 @@
  *     host memory (pageable or pinned);
  *   - every *_dev entry point is asynchronous on `stream` (a cudaStream_t passed as void*), does
  *     no allocation and no synchronisation, and needs a caller-owned workspace whose size comes
- *     from the matching *_workspace_bytes(); it is re-entrant (no global mutable state), so one
- *     host thread per GPU may call concurrently (nn.DataParallel, train_vidreid_xent_htri.py:318);
+ *     from the matching *_workspace_bytes(); it is re-entrant -- the library keeps NO process-global mutable
+ *     state, every tuning knob is a field of the call's parameter struct -- so one host thread per GPU may
+ *     call concurrently (nn.DataParallel, train_vidreid_xent_htri.py:318);
  *   - every *_host entry point copies host->device, runs the same kernels, copies the result back
  *     and synchronises before returning (this is the end-to-end path bench.py reports as `e2e`);
  *   - return value: AGRL_OK (0) or a negative AGRL_E_* code; nothing throws across the boundary.
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define AGRL_B200_ABI_VERSION 1
+#define AGRL_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define AGRL_API __attribute__((visibility("default")))
@@ -76,6 +77,13 @@ extern "C" {
                                      instead of three.  Measured head error 1e-5 norm-relative, 3e-5
                                      max-scaled (bar 1e-4); not offered for the distance matrix            */
 
+#define AGRL_SPLIT_FP16_E4M3   4   /* graph layers only: the scaled fp16 plane of AGRL_SPLIT_FP16X1 plus the two first-order
+                                     corrections as ONE K-concatenated 8-bit product, y.w ~ fp16(y).fp16(w) + e4m3(r_y).e4m3(w)
+                                     + e4m3(y).e4m3(r_w) with r = x - fp16(x): the operand bits of AGRL_SPLIT_BF16X2 (11 + 4
+                                     vs 8 + 8) at two thirds of its tensor-core time (kind::f8f6f4 runs at twice the fp16 rate).
+                                     Measured head error ~1e-6 (bar 1e-4), like BF16X2.  Needs the tensor-core graph kernel
+                                     (<= 64 nodes per tracklet, C % 128 == 0); AGRL_E_UNSUPPORTED otherwise.                      */
+
 AGRL_API int         agrl_abi_version(void);
 AGRL_API const char *agrl_status_string(int code);
 AGRL_API const char *agrl_last_cuda_error(void);           /* thread-local text of the last CUDA failure   */
@@ -88,21 +96,6 @@ AGRL_API uint64_t    agrl_launch_count(void);
  * time from the previous event to this one, i.e. the kernel's duration on a busy stream). */
 AGRL_API int         agrl_profile_begin(void *stream);
 AGRL_API int         agrl_profile_end(char *text, size_t capacity);
-/* Process-wide tuning knobs (results change at most by summation order, i.e. far below the parity bars).
- * Names: "head_sub_batch" (tracklets per internal sub-batch of agrl_head_forward_dev; 0 = one pass, default),
- * "overlap_mode", "pool_tma" (1 = bulk-copy pooling kernel, default), "pool_stages" (16 KiB ring stages per
- * pooling CTA), "pool_ctas_per_sm", "pool_l2_hint", "graph_variant" (8 = tensor-core graph kernel, default;
- * 6 = CUDA-core graph_kernel_v2; 0-5 = graph_kernel flavours), "gemm_pair" (1 = cta_group::2 GEMMs; default 0),
- * "pool_sms" / "gemm_sms" (experimental spatial partition of the sub-batched pipeline with overlap_mode = 0: poolings
- * 1.. as one shared-memory-filling CTA per SM on pool_sms SMs, persistent GEMMs on gemm_sms CTAs, 0 = the rest; default 0 = off),
- * "head_lowrank" (1 = the first graph layer's X.W^T on the 4S quarter-strip rows per tracklet instead of the 7S node rows,
- * G.X.W^T = (G.T).(Q.W^T); needs more workspace, so set it before agrl_head_workspace_bytes; default 0).
- * Defaults can also come from the AGRL_HEAD_SUB / AGRL_OVERLAP_MODE / AGRL_POOL_TMA / AGRL_POOL_STAGES /
- * AGRL_POOL_CTAS / AGRL_POOL_HINT / AGRL_GRAPH_VARIANT / AGRL_GEMM_PAIR / AGRL_POOL_SMS / AGRL_GEMM_SMS / AGRL_HEAD_LOWRANK environment variables.  set returns AGRL_E_INVALID for an unknown name or a value
- * out of range; get returns -1 for an unknown name. */
-AGRL_API int         agrl_set_option(const char *name, int64_t value);
-AGRL_API int64_t     agrl_get_option(const char *name);
-
 /* =============================================================================================
  * (3) Ranking -- replaces rank_cy.evaluate_cy (torchreid/metrics/rank_cylib/rank_cy.pyx:24-32,
  *     eval_market1501_cy :154-241) and evaluate_mars / Compute_AP (torchreid/metrics/rank.py:160-212),
@@ -292,7 +285,7 @@ typedef struct agrl_head_params {
     float   gamma;                /* 0.1 (vmgn.py:74,172)                                          */
     float   leaky_slope;          /* 0.1 (vmgn.py:95)                                              */
     float   bn_eps;               /* 1e-5                                                          */
-    int32_t split;                /* AGRL_SPLIT_BF16X2 (default), AGRL_SPLIT_BF16X3 or AGRL_SPLIT_FP16X1 */
+    int32_t split;                /* AGRL_SPLIT_BF16X2, AGRL_SPLIT_BF16X3, AGRL_SPLIT_FP16X1 or AGRL_SPLIT_FP16_E4M3 */
     /* device pointers, fp32; BN vectors have C entries, linear weights are (C, C) row-major [out,in] */
     const float *linear_weight[AGRL_HEAD_MAX_LAYERS];      /* graph_layers.i.linear.weight          */
     const float *bn_weight[AGRL_HEAD_MAX_LAYERS];          /* graph_layers.i.bn.{weight,bias,...}    */
@@ -304,6 +297,15 @@ typedef struct agrl_head_params {
     int32_t maps_nhwc;            /* 0: x4_1 / x4_2 are (B*S, C, h, w) NCHW-contiguous (the reference);
                                      1: channels-last memory, (B*S, h, w, C) (torch.channels_last
                                      backbone): pooled directly, no layout conversion pass            */
+    /* tuning knobs; 0 = the library's default.  Results change at most by summation order (far below the parity bars). */
+    int32_t lowrank_off;          /* 1: run the FIRST layer's X.W^T on all 7S node rows.  Default: on the 4S quarter-strip
+                                     rows (the pooled nodes of a frame are linear combinations of its four quarter strips:
+                                     G.X.W^T = (G.T).(Q.W^T)), then a mixing kernel applies G.T and the layer's epilogue
+                                     (needs C % 512 == 0; else this is ignored).  Changes the workspace size.          */
+    int32_t pool_register_loads;  /* 1: the register-load pooling kernel even where the bulk-copy (TMA ring) kernel
+                                     applies (16x8 maps, 16-byte aligned)                                             */
+    int32_t pool_stages;          /* 16 KiB ring stages per pooling CTA, 2..12; 0 = 4                                  */
+    int32_t pool_no_l2_hint;      /* 1: no evict-first L2 hint on the pooling bulk copies                              */
 } agrl_head_params;
 
 /* bytes of the persistent, weight-derived buffer (bf16 planes of W, folded BN scale/shift) */

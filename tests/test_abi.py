@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(raw, name), name
     assert sorted(_lib.exported_names()) == declared_symbols()
-    assert lib.agrl_abi_version() == 1
+    assert lib.agrl_abi_version() == 2
     assert lib.agrl_status_string(0) == b'ok'
     assert b'no CPU fallback' in lib.agrl_status_string(_lib.E_NO_DEVICE)
 

@@ -45,11 +45,12 @@ class FakeProfile(object):
 class FakeModel(object):
     def __init__(self, fail_when=None):
         self.head_split = _lib.SPLIT_BF16X2
+        self.head_lowrank = True
         self.calls = []
         self.fail_when = fail_when
 
     def head(self, x1, x2, adj, S, out=None):
-        state = (self.head_split, _lib.get_option('head_lowrank'), _lib.get_option('pool_sms'))
+        state = (self.head_split, int(self.head_lowrank), 0)
         if self.fail_when is not None and self.fail_when(state):
             raise RuntimeError('injected failure')
         self.calls.append(state + (adj.shape[0],))
@@ -86,10 +87,7 @@ def fake_device(monkeypatch):
         def stop(self):
             return dict(sm_mhz=1700.0, sm_max_mhz=1965.0, reasons=['sw_power_cap'], samples=3, power_w=990.0)
     monkeypatch.setattr(bench, 'ClockSampler', Sampler)
-    saved = {k: _lib.get_option(k) for k in ('head_lowrank', 'head_sub_batch', 'pool_stages')}
     yield
-    for k, v in saved.items():
-        assert _lib.get_option(k) == v, 'bench must restore option %s' % k
 
 
 def run(monkeypatch, capsys, model, argv=()):

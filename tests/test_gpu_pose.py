@@ -79,16 +79,12 @@ def test_head_with_masks_equals_head_with_dense_adjacency(split):
     x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=6, scale=2.0)
     wts = synth.head_weights(2048, 2, seed=7, randomise_bn=True)
     model = make_model(wts, split=split)
-    saved = _lib.get_option('head_sub_batch')
-    try:
-        for sub in (0, 4):
-            _lib.set_option('head_sub_batch', sub)
-            with torch.no_grad():
-                dense = model.head(x1.cuda(), x2.cuda(), adj, S)
-                compact = model.head(x1.cuda(), x2.cuda(), masks, S)
-            assert torch.equal(dense, compact), sub
-    finally:
-        _lib.set_option('head_sub_batch', saved)
+    for lowrank in (True, False):
+        model.head_lowrank = lowrank
+        with torch.no_grad():
+            dense = model.head(x1.cuda(), x2.cuda(), adj, S)
+            compact = model.head(x1.cuda(), x2.cuda(), masks, S)
+        assert torch.equal(dense, compact), lowrank
     ref = ohead.head_forward(x1, x2, adj.cpu(), wts, dtype=torch.float64)
     emax, enrm = rel_err(compact.cpu(), ref)
     assert emax < TOL and enrm < TOL

@@ -4,7 +4,7 @@ small-batch tests never reach.  bench.py runs 882-tracklet head calls (3088 / 17
 1980 x 9330 x 4096 distance matrix (1168 tiles); here the same shapes are checked against the oracle:
 
   * head at B = 128 / 256 / 882 -- fp64 oracle on a 64-tracklet subsample spread over the batch incl. the first and the
-    last tracklet (vmgn.py:296-321); default, head_split = 3, fp16 plane, low-rank first layer on / off;
+    last tracklet (vmgn.py:296-321); bf16x2, bf16x3, fp16 plane, fp16 + e4m3 corrections, low-rank first layer on / off;
   * distance at (1980, 9330, 4096) and (1980, 9330, 2048), both metrics, fp64 oracle (distance.py:59-89);
   * one MARS-config chain head(2048 tracklets) -> distance -> evaluate_rank: features vs the oracle on a subsample, the
     distance matrix vs the fp64 oracle on the GPU features, CMC/mAP bit-exact vs the oracle on the GPU distance matrix
@@ -67,22 +67,13 @@ def _rel(got, ref):
     return float((got - ref).abs().max() / ref.abs().max()), float((got - ref).norm() / ref.norm())
 
 
-@pytest.fixture
-def lowrank_option():
-    from agrl.pytorch_b200 import _lib
-    saved = _lib.get_option('head_lowrank')
-    yield _lib
-    _lib.set_option('head_lowrank', saved)
-
-
-@pytest.mark.parametrize('B,split,lowrank', [(128, 2, None), (256, 2, None), (882, 2, None), (882, 3, None), (882, 1, None),
-                                             (882, 2, 0), (882, 3, 0), (882, 2, 1), (300, 1, 0)])
-def test_head_at_bench_scale(B, split, lowrank, lowrank_option):
-    lib = lowrank_option
-    if lowrank is not None:
-        lib.set_option('head_lowrank', lowrank)
+@pytest.mark.parametrize('B,split,lowrank', [(128, 2, True), (256, 2, True), (882, 2, True), (882, 3, True), (882, 1, True),
+                                             (882, 4, True), (128, 4, True), (882, 2, False), (882, 3, False), (882, 4, False),
+                                             (300, 1, False)])
+def test_head_at_bench_scale(B, split, lowrank):
     wts = synth.head_weights(C, 2, seed=200 + B, randomise_bn=True)
     model = _model(wts, split)
+    model.head_lowrank = lowrank
     x1, x2 = _device_maps(B, seed=201 + B)
     adj = synth.pose_adjacency(B, S, 7, seed=202 + B)
     with torch.no_grad():

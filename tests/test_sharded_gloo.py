@@ -229,3 +229,22 @@ def test_single_process_path_without_init():
     cmc, mAP = sharded.evaluate_mars_sharded(qf, gf, qp, gp, qc, gc, max_rank=10, ops=CpuOps())
     ref = orank.mars_port(odist.distance_matrix(qf, gf, 'euclidean').numpy(), qp, gp, qc, gc, 10)
     assert np.array_equal(cmc, ref[0]) and float(mAP) == float(ref[1])
+
+
+def _or_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        st = torch.tensor([[1, 4, 0][rank % 3] | (8 if rank == world - 1 else 0)], dtype=torch.int32)
+        sharded.or_across_ranks(st)
+        np.save(os.path.join(out_dir, 'or%d.npy' % rank), st.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_status_words_are_or_reduced_across_ranks(tmp_path):
+    """different flags on different ranks must all survive (a MAX reduction would keep only the largest word)"""
+    world = 3
+    mp.spawn(_or_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert int(np.load(os.path.join(str(tmp_path), 'or%d.npy' % r))[0]) == (1 | 4 | 8)

@@ -1,5 +1,5 @@
 """Head-pipeline variants on one resident input pool (one process, options switched at run time).
-usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: sub tma stages ctas graph mode hint split pair psms gsms lr nhwc call gb)
+usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: tma stages hint split lr nhwc call gb)
 `gb` = number of graph layers of the model (0: pooling + attention only -> the pooling kernels run practically alone).
 `call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
 import json
@@ -12,8 +12,8 @@ import torch
 import bench
 from agrl.pytorch_b200 import _lib
 
-KEYS = {'sub': 'head_sub_batch', 'tma': 'pool_tma', 'stages': 'pool_stages', 'ctas': 'pool_ctas_per_sm', 'graph': 'graph_variant',
-        'mode': 'overlap_mode', 'hint': 'pool_l2_hint', 'pair': 'gemm_pair', 'psms': 'pool_sms', 'gsms': 'gemm_sms', 'lr': 'head_lowrank'}
+KEYS = {'tma': 'pool_tma', 'stages': 'pool_stages', 'hint': 'pool_l2_hint', 'lr': 'head_lowrank'}      # module attributes
+DEFAULTS = {'tma': 1, 'stages': 0, 'hint': 1, 'lr': 1}
 
 
 def main():
@@ -41,7 +41,7 @@ def main():
     J, S = int(os.environ.get('HV_TRACKLETS', bench.NQ + bench.NG)), bench.S
     feats = torch.empty(J, 2 * bench.C, device=dev)
     stream = torch.cuda.current_stream(dev)
-    defaults = {k: _lib.get_option(v) for k, v in KEYS.items()}
+    defaults = dict(DEFAULTS)
     for spec in sys.argv[2:]:
         cfg = dict(defaults)
         cfg['call'] = pool_n
@@ -49,9 +49,9 @@ def main():
             if kv:
                 k, v = kv.split('=')
                 cfg[k] = int(v)
-        for k, name in KEYS.items():
-            _lib.set_option(name, cfg[k])
         model = model_for(cfg.get('gb', 2))
+        for k, name in KEYS.items():
+            setattr(model, name, cfg[k] if k == 'stages' else bool(cfg[k]))
         model.head_split = cfg.get('split', 2)
         call = min(cfg['call'], pool_n)
         chunks = [(o, min(call, J - o)) for o in range(0, J, call)]
@@ -83,11 +83,15 @@ def main():
                 with _lib.profile(stream.cuda_stream) as prof:
                     head_pass()
                 tot = {k: round(t, 3) for k, (n, t) in prof.totals().items()}
+                energy = None
+                if os.environ.get('HV_ENERGY'):                  # NVML energy counter over >= HV_ENERGY seconds of passes
+                    cx = type('Cx', (), {'local': 0, 'dev': dev})()
+                    energy = bench.energy_of(cx, head_pass, min_seconds=float(os.environ['HV_ENERGY']))
             best = min(ms)
             print(json.dumps({'spec': spec, 'head_ms': round(best, 3), 'all': [round(m, 3) for m in ms[:6]], 'clocks': clocks,
                               'ktracklets_s': round(J / best, 1),
                               'hbm_frac': round(J * bench.BYTES_PER_TRACKLET / (best * 1e-3) / 1e9 / 6545.9, 4),
-                              'checksum': float(feats.double().sum()), 'kernels': tot}), flush=True)
+                              'checksum': float(feats.double().sum()), 'kernels': tot, 'energy': energy}), flush=True)
         except Exception as ex:  # noqa
             print(json.dumps({'spec': spec, 'error': repr(ex)}), flush=True)
 

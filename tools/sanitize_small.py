@@ -15,21 +15,20 @@ kp, hts, valid = synth.pose_keypoints(B, S, seed=3)
 masks = pose.part_masks(kp, hts, valid)
 adj = pose.expand_adjacency(masks, S)
 outs = []
-for split in (2, 1, 3):
+for split in (2, 1, 3, 4):
     m = models.init_model('vmgn', num_classes=8, loss={'xent', 'htri'}, last_stride=1, num_split=4, num_gb=2, num_scale=1,
                           pyramid_part=True, use_pose=True, learn_graph=True, pretrained=False, head_split=split)
     sd = m.state_dict()
     for k, v in wts.items():
         sd[k].copy_(v)
     m = m.cuda().eval()
-    for variant in (8, 6, 0):
-        _lib.set_option('graph_variant', variant)
-        for sub in (0, 2):
-            _lib.set_option('head_sub_batch', sub)
+    for lowrank in (True, False):
+        for tma in (True, False):
+            m.head_lowrank, m.pool_tma = lowrank, tma
             with torch.no_grad():
                 outs.append(m.head(x1.cuda(), x2.cuda(), adj, S))
                 outs.append(m.head(x1.cuda(), x2.cuda(), masks, S))
-    _lib.set_option('graph_variant', 8); _lib.set_option('head_sub_batch', 0)
+    m.head_lowrank, m.pool_tma = True, True
     with torch.no_grad():
         outs.append(m.head(x1.cuda().contiguous(memory_format=torch.channels_last),
                            x2.cuda().contiguous(memory_format=torch.channels_last), adj, S))
