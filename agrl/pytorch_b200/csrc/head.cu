@@ -975,7 +975,8 @@ struct MixArgs {
 
 // Two channels per thread -- every shared-memory broadcast of four G.T weights feeds eight FMAs -- and the residual rows
 // of eight nodes loaded ahead of their use, so that the row loop is not bound by the latency of one load per 36 FMAs.
-// grid (C / 512, tracklets).
+// grid (C / 512, tracklets).  (Packed fma.rn.f32x2 with the weights duplicated in shared memory was measured: 4.67 vs
+// 4.40 ms per pass -- FFMA2 issues at half rate on sm_100, the extra LDS traffic is pure cost.)
 constexpr int kMixRows = 8;
 __global__ void __launch_bounds__(kHeadThreads, 2)
 graph_mix_kernel(MixArgs a) {
@@ -1075,11 +1076,15 @@ attn_kernel(AttnArgs a) {
         s_att[tid] = __fdiv_rn(s_norm[tid], fmaxf(t, 1e-12f));
     }
     __syncthreads();
-    // fused[p] = sum_s f * att ; mean over p ; BN
-    for (int c4 = tid; c4 < C / 4; c4 += kHeadThreads) {
+    // fused[p] = sum_s f * att ; mean over p ; BN.  gridDim.y CTAs share a tracklet's channels (small calls: more CTAs
+    // than tracklets, so that the machine is filled; the per-element arithmetic does not depend on the split)
+    const int per_slab = (C / 4 + gridDim.y - 1) / gridDim.y;
+    const int c4_lo = blockIdx.y * per_slab, c4_hi = min(C / 4, c4_lo + per_slab);
+    for (int c4 = c4_lo + tid; c4 < c4_hi; c4 += kHeadThreads) {
         float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int p = 0; p < kParts; ++p) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
             for (int s = 0; s < a.S; ++s) {
                 const int r = s * kParts + p;
                 const float w = s_att[r];
@@ -1325,7 +1330,10 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
         AGRL_CUDA_TRY(cudaMemcpyAsync(nodes_out, x[0], sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
     AttnArgs aa{x[cur], out + static_cast<size_t>(b0) * ld_out, ld_out, pr.scale[L + 1], pr.shift[L + 1], S, C, attn_sumsq, attn_slots};
     AGRL_LAUNCH_BEGIN(st);
-    attn_kernel<<<static_cast<unsigned>(n), kHeadThreads, 0, st>>>(aa);
+    // channel slabs per tracklet: 1 iteration per thread at C = 2048 with two slabs; more when the call is small
+    int slabs = 1;
+    if (attn_sumsq) { slabs = n >= 600 ? 2 : (n >= 300 ? 4 : 8); while (slabs > 1 && (C / 4) % slabs != 0) slabs >>= 1; }
+    attn_kernel<<<dim3(static_cast<unsigned>(n), slabs), kHeadThreads, 0, st>>>(aa);
     AGRL_LAUNCH_CHECK(st, "attn");
     return AGRL_OK;
 }

@@ -385,7 +385,8 @@ def run_b200(args):
         return
 
     lowrank_on = bool(getattr(model, 'head_lowrank', True))
-    table, head_dram = kernel_table(timeline, pk, J, lowrank_on)
+    passes = {1: 1.0, 2: 3.0, 3: 6.0, 4: 2.0}.get(int(getattr(model, 'head_split', 4)), 2.0)
+    table, head_dram = kernel_table(timeline, pk, J, lowrank_on, passes)
     top = max(timeline.items(), key=lambda kv: kv[1][1])[0]
     head_gbs = J * BYTES_PER_TRACKLET / (head_ms * 1e-3) / 1e9
     # `roofline`: the WHOLE head as SURVEY 8(d) defines it -- algorithmic bytes per tracklet (both maps, the pose graph,
@@ -400,11 +401,11 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'tracklets/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'fp32 (bf16x2/bf16x3 split operands on tcgen05, fp32 accumulate)',
+        'vs_baseline': None, 'dtype': 'fp32 (head GEMMs: fp16 + e4m3 correction planes, distance: bf16x3 planes, on tcgen05; fp32 accumulate)',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD % args.dist_metric,
                    'tracklets_per_step_per_gpu': J, 'pool_tracklets': pool_n,
-                   'head': 'bulk-copy pooling (TMA ring), graph layers on tcgen05 (graph_kernel_tc + bf16x2 split GEMM, 3 products; '
+                   'head': 'bulk-copy pooling (TMA ring), graph layers on tcgen05 (graph_kernel_tc + split GEMM: fp16 product + one K-concatenated e4m3 correction product; '
                            'first layer on the 32 quarter-strip rows per tracklet); knobs %s' % (
                        {k: getattr(model, k, None) for k in ('head_split', 'head_lowrank', 'pool_tma', 'pool_stages', 'pool_l2_hint')},),
                    'cache': 'input pool %.1f GB per GPU, larger than L2; cycled' % (pool_n * BYTES_PER_TRACKLET / 1e9),
@@ -476,7 +477,7 @@ def energy_of(cx, fn, min_seconds=1.0):
             'ms_per_pass_wall': r['seconds'] / reps * 1e3}
 
 
-def kernel_table(timeline, pk, J, lowrank_on):
+def kernel_table(timeline, pk, J, lowrank_on, gemm_passes=2.0):
     """Per kernel of one step: launches, ms, share, what bounds it, algorithmic bytes or flops per step, achieved rate,
     the peak it is held against and the fraction; `dram_bytes` per step from profiles/traffic.json (ncu --set full,
     dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled by units).  Returns (table, head DRAM bytes)."""
@@ -487,7 +488,9 @@ def kernel_table(timeline, pk, J, lowrank_on):
         'pool': ('hbm', J * (2 * S * C * H * W * 4 + node_b + C * 4)),
         # read X once, write the operand planes (2 planes x 2 B): layer 1 writes the 32 quarter rows when low-rank
         'graph': ('hbm', J * ((node_b + (q_b if lowrank_on else node_b)) + 2 * node_b)),
-        'gemm_graph_layer': ('tensor', 3 * 2.0 * J * (rows1 + V) * C * C),
+        # tensor time in bf16-pass equivalents: 3 for the bf16x2 split, 2 for fp16 + e4m3 (the 8-bit product covers both
+        # corrections at twice the rate), 1 for the fp16 plane, 6 for bf16x3
+        'gemm_graph_layer': ('tensor', gemm_passes * 2.0 * J * (rows1 + V) * C * C),
         'graph_mix': ('hbm', J * (2 * node_b + q_b)),
         'attn': ('hbm', J * node_b),
         'split_planes': ('hbm', (NQ + NG) * 2 * C * (4 + 6)),
