@@ -34,6 +34,7 @@ class HeadParams(ctypes.Structure):
         ('global_bn', c_vp * 4), ('att_bn', c_vp * 4),
         ('maps_nhwc', c_i32),
         ('lowrank_off', c_i32), ('pool_register_loads', c_i32), ('pool_stages', c_i32), ('pool_no_l2_hint', c_i32),
+        ('gemm_no_pair', c_i32),
     ]
 
 

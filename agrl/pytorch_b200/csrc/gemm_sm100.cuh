@@ -49,7 +49,7 @@ constexpr int kEpiBytes = 4 * 32 * kEpiPad * 4;       // transpose staging of th
 // and 2, with a relay warp and with direct cross-CTA barrier signalling: 22.7 / 21.9 ms per pass against 23.0 ms for one
 // CTA per tile, nothing in the fp16 mode (profiles/r2/first_call_variants.log).  The GEMM is bound by the board's power
 // limit, not by operand ingest; the pair flavours were removed.)
-template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0> struct Config {
+template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0, bool kPair = false> struct Config {
     // epilogue flavour: kDirect = registers -> 16-byte global accesses, 8 warps (two per TMEM lane
     // quarter, half the columns each), no smem; otherwise 4 warps and a padded smem transpose so
     // that stores are coalesced along rows of arbitrary alignment.
@@ -58,9 +58,10 @@ template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0> st
     static constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
     static_assert(BN == 128 || BN == 256, "tile width");
     static_assert(!kSplit || BN == 128, "two accumulators of 256 columns do not fit twice in TMEM");
-    static constexpr int kTileBytesB = BN * BK * 2;
+    static constexpr int kLoadN = kPair ? BN / 2 : BN;                  // rows of the B tile this CTA loads
+    static constexpr int kTileBytesB = kLoadN * BK * 2;
     static constexpr int kStageBytes = P * (kTileBytesA + kTileBytesB);
-    static constexpr int kTileM = BM;                                   // rows per scheduled tile
+    static constexpr int kTileM = kPair ? 2 * BM : BM;                  // rows per scheduled tile
     static constexpr int kStages = (200 * 1024) / kStageBytes;          // 96 KiB stages -> 2, 64 KiB -> 3
     static constexpr int kAccCols = kSplit ? 2 * BN : BN;               // columns per accumulator stage
     static constexpr int kNumPairs = (P == 3) ? 6 : (P == 2 ? 3 : 1);
@@ -151,6 +152,59 @@ __device__ __forceinline__ void tc_mma_e4m3(uint32_t d_tmem, uint64_t a_desc, ui
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// ---- CTA-pair (cta_group::2) flavours: one 256 x BN tile per pair of SMs, each CTA loads its 128 rows of A and HALF of B ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {      // same offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit: arrive on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_e4m3_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -358,10 +412,14 @@ using EpiGraphLayerF16 = EpiGraphLayerT<true>;
 using EpiGraphLayerF16E4 = EpiGraphLayerT<true, true>;
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int P, int BN, bool kSplit, class Epi>
+// kPair: the CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile.  Every CTA loads its own 128 rows of A
+// and its half of the B tile; both CTAs' loads complete on the LEADER's full barrier (which expects the bytes of both
+// stages), the leader issues the MMAs for the pair, its commits arrive on the empty / accumulator-full barriers of both
+// CTAs, and both CTAs' epilogue warps release the accumulator on the leader's barrier.
+template <int P, int BN, bool kSplit, class Epi, bool kPair = false>
 __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const CUtensorMap &map_b,
                                                 int M, int N, int k_pad, const Epi &epi) {
-    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>;
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, kPair>;
     constexpr int kAccCols = Cfg::kAccCols;
     extern __shared__ unsigned char smem_dyn[];
     // 128B-swizzled tiles need 1024-byte alignment
@@ -377,7 +435,9 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::kStages + 2 * kAccStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile0 = static_cast<int>(blockIdx.x), tile_step = static_cast<int>(gridDim.x);
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;             // 0 = the pair's leader (issues the MMAs)
+    const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int tiles_m = (M + Cfg::kTileM - 1) / Cfg::kTileM, tiles_n = (N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = k_pad / BK;
@@ -397,6 +457,7 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
             else { base_m = (tiles_m / grp_m) * grp_m; gm = tiles_m - base_m; r = tile - full_tiles; }
             m0 = (base_m + r % gm) * Cfg::kTileM; n0 = (r / gm) * BN;
         } else { n0 = (tile % tiles_n) * BN; m0 = (tile / tiles_n) * Cfg::kTileM; }
+        m0 += static_cast<int>(rank) * BM;                            // this CTA's 128 rows of the tile
     };
 
     if (warp == 0 && lane == 0) {
@@ -405,12 +466,15 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, Cfg::kEpiWarps * (kPair ? 2 : 1)); }
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
+    if (warp == 2) {
+        if (kPair) { tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols); tmem_relinquish_pair(); }
+        else { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
+    }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -426,18 +490,29 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                     const uint32_t sb = sa + P * kTileBytesA;
                     const uint32_t full = bar_full + 8 * stage;
-                    mbar_arrive_expect_tx(full, Cfg::kStageBytes);
+                    if (kPair && rank != 0) {
+                        // (the peer's bytes may land before the leader's expect_tx of the phase: the transaction count goes
+                        // negative until then, the phase cannot complete before the leader's arrive)
+                        const uint32_t lfull = mapa_shared(full, 0);
+                        const int nb = n0 + Cfg::kLoadN;
 #pragma unroll
-                    for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kTileBytesA, &map_a, full, kb * BK, m0, p);
+                        for (int p = 0; p < P; ++p) tma_load_3d_pair(sa + p * kTileBytesA, &map_a, lfull, kb * BK, m0, p);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::kTileBytesB, &map_b, full, kb * BK, n0, p);
+                        for (int p = 0; p < P; ++p) tma_load_3d_pair(sb + p * Cfg::kTileBytesB, &map_b, lfull, kb * BK, nb, p);
+                    } else {
+                        mbar_arrive_expect_tx(full, (kPair ? 2 : 1) * Cfg::kStageBytes);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) tma_load_3d(sa + p * kTileBytesA, &map_a, full, kb * BK, m0, p);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) tma_load_3d(sb + p * Cfg::kTileBytesB, &map_b, full, kb * BK, n0, p);
+                    }
                 }
                 __syncwarp();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 && rank == 0) {
+        // ================= MMA issuer (the pair's leader only) =================
         constexpr uint32_t idesc = make_idesc(Cfg::kTileM, BN, Epi::kF16);
         int stage = 0; uint32_t phase = 0;
         int cit = 0;                                               // accumulator-drain counter (chunks)
@@ -465,6 +540,15 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                             // fp16 product of the value planes, then ONE 8-bit product over the k-block's 128 bytes:
                             // [r_a | a8] . [b8 | r_b] = r_a.b8 + a8.r_b, the two first-order corrections of a.b
                             static_assert(P == 2 && !kSplit, "fp16 + e4m3 mode: two byte-identical planes, one accumulator");
+                            if constexpr (kPair) {
+                                const uint64_t pa0 = make_smem_desc(sa), pb0 = make_smem_desc(sb);
+                                const uint64_t pa1 = make_smem_desc(sa + kTileBytesA), pb1 = make_smem_desc(sb + Cfg::kTileBytesB);
+                                const uint32_t pd = tmem_base + acc * kAccCols;
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16_pair(pd, pa0 + 2 * k, pb0 + 2 * k, idesc, (first | k) != 0 ? 1u : 0u);
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_e4m3_pair(pd, pa1 + 2 * k, pb1 + 2 * k, idesc, 1u);
+                            } else {
                             const uint64_t da0 = make_smem_desc(sa), db0 = make_smem_desc(sb);
                             const uint64_t da1 = make_smem_desc(sa + kTileBytesA), db1 = make_smem_desc(sb + Cfg::kTileBytesB);
                             const uint32_t d = tmem_base + acc * kAccCols;
@@ -472,6 +556,7 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                             for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d, da0 + 2 * k, db0 + 2 * k, idesc, (first | k) != 0 ? 1u : 0u);
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_e4m3(d, da1 + 2 * k, db1 + 2 * k, idesc, 1u);
+                            }
                         } else
 #pragma unroll
                         for (int i = 0; i < Cfg::kNumPairs; ++i) {
@@ -485,12 +570,18 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                                 const bool main_acc = kSplit && i == Cfg::kNumPairs - 1;
                                 const uint32_t d = main_acc ? d_main : d_corr;
                                 const uint32_t accum = main_acc ? ((first | k) != 0 ? 1u : 0u) : ((first | i | k) != 0 ? 1u : 0u);
-                                tc_mma_bf16(d, da + 2 * k, db + 2 * k, idesc, accum);
+                                if (kPair) tc_mma_bf16_pair(d, da + 2 * k, db + 2 * k, idesc, accum);
+                                else tc_mma_bf16(d, da + 2 * k, db + 2 * k, idesc, accum);
                             }
                         }
                         // frees the smem stage when the MMAs retire; publishes the accumulator (chunk) when complete
-                        tc_commit(bar_empty + 8 * stage);
-                        if (kb == kb_end - 1) tc_commit(bar_tfull + 8 * acc);
+                        if (kPair) {
+                            tc_commit_pair(bar_empty + 8 * stage);
+                            if (kb == kb_end - 1) tc_commit_pair(bar_tfull + 8 * acc);
+                        } else {
+                            tc_commit(bar_empty + 8 * stage);
+                            if (kb == kb_end - 1) tc_commit(bar_tfull + 8 * acc);
+                        }
                     }
                     __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -501,7 +592,11 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
         // ================= epilogue =================
         const int ew = warp - kCtrlWarps;
         const int quarter = ew & 3;                                // == warp % 4: the TMEM lane quarter
-        auto release_acc = [&](int acc) { mbar_arrive(bar_tempty + 8 * acc); };
+        // "accumulator drained" goes to the barrier the MMA issuer waits on: the leader's
+        auto release_acc = [&](int acc) {
+            if (kPair) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));
+            else mbar_arrive(bar_tempty + 8 * acc);
+        };
         int cit = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int m0, n0;
@@ -637,8 +732,11 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
+    }
 }
 
 template <int P, int BN, bool kSplit, class Epi>
@@ -648,12 +746,46 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     split_gemm_body<P, BN, kSplit, Epi>(map_a, map_b, M, N, k_pad, epi);
 }
 
+template <int P, int BN, bool kSplit, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__((Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb>::kMaxRegs))
+pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 int M, int N, int k_pad, Epi epi) {
+    split_gemm_body<P, BN, kSplit, Epi, true>(map_a, map_b, M, N, k_pad, epi);
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 // 3-D tensor map over planes [P][rows][k_pad] of bf16: box = (BK, box_rows, 1), 128-byte swizzle.
 // box_rows = BM for the A operand, the kernel's BN for the B operand.
 // plane_rows = rows between consecutive planes (>= rows when the map covers a row slice of the planes).
 int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows,
                           int64_t plane_rows);
+
+// CTA-pair flavour; map_b must have been built with box_rows = BN / 2.
+template <int P, int BN, bool kSplit, class Epi>
+int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad, const Epi &epi, cudaStream_t st) {
+    using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, true>;
+    static_assert(!Epi::kDirect || !kSplit, "the direct epilogue reads a single accumulator");
+    auto kern = pair_gemm_kernel<P, BN, kSplit, Epi>;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    // persistent grid = the number of CTA pairs that can be resident at once (a GPC with an odd SM left over hosts no
+    // pair there), asked once per kernel
+    static const int max_pairs = [&] {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kNumSMs & ~1); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = kNumSMs / 2; }
+        return n < kNumSMs / 2 ? n : kNumSMs / 2;
+    }();
+    const int tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + BN - 1) / BN);
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
+    AGRL_LAUNCH_CHECK(st, Epi::kName);
+    return AGRL_OK;
+}
 
 template <int P, int BN, bool kSplit, class Epi>
 int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad,

@@ -1251,11 +1251,13 @@ static int launch_pool(const agrl_head_params *p, const Prepared &pr, const Head
 
 // one GEMM of a graph layer in the caller's operand mode; Epi is built by `make(fp8)` for the scaled modes
 template <class EpiBf16, class EpiF16, class EpiF16E4>
-static int launch_layer_gemm(int split, const CUtensorMap &map_a, const CUtensorMap &map_w, int rows, int C,
+static int launch_layer_gemm(int split, bool pair, const CUtensorMap &map_a, const CUtensorMap &map_w, int rows, int C,
                              const EpiBf16 &e2, const EpiF16 &e1, const EpiF16E4 &e4, cudaStream_t st) {
     switch (split) {
         case AGRL_SPLIT_FP16X1: return gemm::launch_split_gemm<1, 256, false>(map_a, map_w, rows, C, C, e1, st);
-        case AGRL_SPLIT_FP16_E4M3: return gemm::launch_split_gemm<2, 256, false>(map_a, map_w, rows, C, C, e4, st);
+        case AGRL_SPLIT_FP16_E4M3:
+            return pair ? gemm::launch_pair_gemm<2, 256, false>(map_a, map_w, rows, C, C, e4, st)
+                        : gemm::launch_split_gemm<2, 256, false>(map_a, map_w, rows, C, C, e4, st);
         case AGRL_SPLIT_BF16X3: return gemm::launch_split_gemm<3, 128, false>(map_a, map_w, rows, C, C, e2, st);
         default: return gemm::launch_split_gemm<2, 256, false>(map_a, map_w, rows, C, C, e2, st);
     }
@@ -1279,12 +1281,13 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
     if (L > 0 && (rc = gemm::make_plane_tensor_map(&map_y, y, rows, C, P, gemm::BM, all_rows))) return rc;
     const int scaled = scaled_mode(p->split), fp8 = p->split == AGRL_SPLIT_FP16_E4M3;
     const int bn = p->split == AGRL_SPLIT_BF16X3 ? 128 : 256;
+    const bool pair = fp8 && !p->gemm_no_pair;              // CTA pairs (cta_group::2): each CTA loads half of the W tile
     int cur = 0;
     for (int l = 0; l < L; ++l) {
         GraphArgs ga{x[cur], adj, masks, y, all_rows * C, V, C, P, p->use_pose, p->learn_graph, scaled, hwk.y_unscale + b0};
         ga.fp8 = fp8;
         float *dst = (l == L - 1 && nodes_out) ? nodes_out : x[cur ^ 1];
-        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, P, bn, C))) return rc;
+        if ((rc = gemm::make_plane_tensor_map(&map_w, pr.w_planes[l], C, C, P, pair ? bn / 2 : bn, C))) return rc;
         // Low-rank first layer: only layer 0 sees nodes that are T.(quarter strips)
         if (l == 0 && hwk.z) {
             const int S4 = S * 4;
@@ -1300,7 +1303,7 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
             gemm::EpiPlainT<false> z2{z, C, nullptr, nullptr, S4};
             gemm::EpiPlainT<true> z1{z, C, hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, S4};
             gemm::EpiPlainT<true, true> z4{z, C, hwk.y_unscale + b0, pr.w_scale + 4 * l + 1, S4};
-            if ((rc = launch_layer_gemm(p->split, map_q, map_w, static_cast<int>(qrows), C, z2, z1, z4, st))) return rc;
+            if ((rc = launch_layer_gemm(p->split, pair, map_q, map_w, static_cast<int>(qrows), C, z2, z1, z4, st))) return rc;
             MixArgs ma{x[cur], z, ga.gt, dst, pr.scale[l], pr.shift[l], V, S4, C, p->gamma, p->leaky_slope};
             AGRL_LAUNCH_BEGIN(st);
             graph_mix_kernel<<<dim3(C / (2 * kHeadThreads), static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
@@ -1322,7 +1325,7 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
         e2.row_sumsq = e1.row_sumsq = e4.row_sumsq = sumsq;
         e2.sumsq_slots = e1.sumsq_slots = e4.sumsq_slots = sumsq ? sumsq_slots : 0;
         AGRL_LAUNCH_BEGIN(st);
-        if ((rc = launch_layer_gemm(p->split, map_y, map_w, static_cast<int>(rows), C, e2, e1, e4, st))) return rc;
+        if ((rc = launch_layer_gemm(p->split, pair, map_y, map_w, static_cast<int>(rows), C, e2, e1, e4, st))) return rc;
         if (dst == nodes_out) x[cur ^ 1] = nodes_out;
         cur ^= 1;
     }

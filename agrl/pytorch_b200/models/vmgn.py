@@ -136,6 +136,7 @@ class VMGN(nn.Module):
         self.pool_tma = True             # bulk-copy (TMA ring) pooling kernel where it applies (False: register loads)
         self.pool_stages = 0             # ring stages per pooling CTA (0 = library default)
         self.pool_l2_hint = True         # evict-first hint on the pooling bulk copies
+        self.gemm_pair = True            # fp16 + e4m3 mode: layer GEMMs as CTA pairs (cta_group::2); False: one CTA per tile
         self._prep = {}                  # device -> (key, prepared buffer): what the cached buffer was built from
         self._ws = {}                    # (device, stream) -> workspace
 
@@ -168,6 +169,7 @@ class VMGN(nn.Module):
         P.leaky_slope, P.bn_eps, P.split = 0.1, 1e-5, self.head_split
         P.lowrank_off, P.pool_register_loads = int(not self.head_lowrank), int(not self.pool_tma)
         P.pool_stages, P.pool_no_l2_hint = int(self.pool_stages), int(not self.pool_l2_hint)
+        P.gemm_no_pair = int(not self.gemm_pair)
         tensors, key = [], []
 
         def ptr(t):

@@ -306,6 +306,10 @@ typedef struct agrl_head_params {
                                      applies (16x8 maps, 16-byte aligned)                                             */
     int32_t pool_stages;          /* 16 KiB ring stages per pooling CTA, 2..12; 0 = 4                                  */
     int32_t pool_no_l2_hint;      /* 1: no evict-first L2 hint on the pooling bulk copies                              */
+    int32_t gemm_no_pair;         /* AGRL_SPLIT_FP16_E4M3 only.  Default: the layer GEMMs run as CTA pairs (tcgen05
+                                     cta_group::2, 256 x 256 tiles, each CTA loads half of the W tile: a third less L2 -> SM
+                                     traffic, which is what bounds this mode; 16.0 -> 12.7 ms per 11310-tracklet pass).
+                                     1: one CTA per 128 x 256 tile.  Bit-identical results either way.                   */
 } agrl_head_params;
 
 /* bytes of the persistent, weight-derived buffer (bf16 planes of W, folded BN scale/shift) */

@@ -340,3 +340,29 @@ def test_channels_last_maps_are_pooled_without_a_layout_copy(w):
     assert emax < TOL and enrm < TOL, (w, emax, enrm)
     emax, _ = rel_err(nhwc.cpu(), nchw.cpu())
     assert emax < 5e-6
+
+
+@pytest.mark.parametrize('B', [3, 37])
+def test_cta_pair_gemms_agree(B):
+    """fp16 + e4m3 mode with the layer GEMMs as CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA loading half of
+    the W tile): the same MMAs in the same order per output element, so bit-identical to one CTA per tile; odd row-tile
+    counts (a pair whose second half lies past the last row), low-rank first layer on and off."""
+    S = 8
+    x1, x2 = synth.feature_maps(B, S, 2048, 16, 8, seed=130 + B, scale=2.0)
+    adj = synth.pose_adjacency(B, S, 7, seed=131 + B)
+    wts = synth.head_weights(2048, 2, seed=132, randomise_bn=True)
+    model = make_model(wts, split=4)
+    ref = ohead.head_forward(x1, x2, adj, wts, dtype=torch.float64)
+    x1, x2, adj = x1.cuda(), x2.cuda(), adj.cuda()
+    for lowrank in (True, False):
+        model.head_lowrank, model.gemm_pair = lowrank, False
+        with torch.no_grad():
+            single = model.head(x1, x2, adj, S).clone()
+        model.gemm_pair = True
+        for _ in range(2):
+            with torch.no_grad():
+                pair = model.head(x1, x2, adj, S)
+        torch.cuda.synchronize()
+        emax, enrm = rel_err(pair.cpu(), ref)
+        assert emax < TOL and enrm < TOL, (B, lowrank, emax, enrm)
+        assert torch.equal(pair, single), (B, lowrank)

@@ -1,5 +1,5 @@
 """Head-pipeline variants on one resident input pool (one process, options switched at run time).
-usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: tma stages hint split lr nhwc call gb)
+usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: tma stages hint split lr pair nhwc call gb)
 `gb` = number of graph layers of the model (0: pooling + attention only -> the pooling kernels run practically alone).
 `call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
 import json
@@ -12,8 +12,8 @@ import torch
 import bench
 from agrl.pytorch_b200 import _lib
 
-KEYS = {'tma': 'pool_tma', 'stages': 'pool_stages', 'hint': 'pool_l2_hint', 'lr': 'head_lowrank'}      # module attributes
-DEFAULTS = {'tma': 1, 'stages': 0, 'hint': 1, 'lr': 1}
+KEYS = {'tma': 'pool_tma', 'stages': 'pool_stages', 'hint': 'pool_l2_hint', 'lr': 'head_lowrank', 'pair': 'gemm_pair'}      # module attributes
+DEFAULTS = {'tma': 1, 'stages': 0, 'hint': 1, 'lr': 1, 'pair': 1}
 
 
 def main():
