@@ -123,3 +123,19 @@ def test_sharded_evaluator_fused_equals_unfused_and_the_oracle(metric):
     dn = metrics.compute_distance_matrix(qf, gf, metric).cpu().numpy()
     rcmc, rmap = orank.mars_port(dn, qp, gp, qc, gc, 50)
     assert np.array_equal(a[0], rcmc) and a[1] == rmap
+
+
+def test_fused_topk_with_the_two_plane_split():
+    """AGRL_SPLIT_BF16X2 operands (3 products): the fused route and the matrix route still agree key for key"""
+    from agrl.pytorch_b200 import _lib, sharded
+    from agrl.pytorch_b200.metrics.distance import PreparedOperand, distance_prepared
+    g = torch.Generator(device='cuda').manual_seed(77)
+    qf = torch.randn(150, 320, generator=g, device='cuda')
+    gf = torch.randn(7000, 320, generator=g, device='cuda')
+    ops = sharded.CudaOps(split=_lib.SPLIT_BF16X2)
+    qop, gop = PreparedOperand(qf, 'euclidean', _lib.SPLIT_BF16X2), PreparedOperand(gf, 'euclidean', _lib.SPLIT_BF16X2)
+    qp, qc, gp, gc = _labels(150, 7000, seed=78)
+    keys, cls, ngood, st = ops.topk_fused(qop, gop, qp, gp, qc, gc, 50, 0, allow_fallback=False)
+    rkeys, rcls, rngood, _ = ops.partial(distance_prepared(qop, gop), qp, gp, qc, gc, 50, 0)
+    assert int(st.cpu()) == 0
+    assert torch.equal(keys, rkeys) and torch.equal(cls, rcls) and torch.equal(ngood, rngood)
