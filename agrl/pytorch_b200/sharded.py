@@ -212,13 +212,39 @@ def _as_dev_i64(x, dev):
 FUSED_MIN_GALLERY = 32768        # gallery rows per shard from which the fused distance -> top-k is the default
 
 
+def _shard_layout(n_local_rows, dev, world, group, gallery_counts):
+    """(rows of every shard, this rank): from ``gallery_counts`` when the caller knows them (no collective, no host
+    sync), else one all-gather of the local row count."""
+    if world == 1:
+        return [int(n_local_rows)], 0
+    rank = dist.get_rank(group)
+    if gallery_counts is not None:
+        counts = [int(c) for c in gallery_counts]
+        assert len(counts) == world and counts[rank] == int(n_local_rows), 'gallery_counts must list every rank\'s shard rows'
+        return counts, rank
+    n_local = torch.tensor([n_local_rows], dtype=torch.int64, device=dev)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, n_local, group=group)
+    return counts.cpu().tolist(), rank
+
+
+def _broadcast_queries(qf, qp, qc, group):
+    """rank 0's query features and labels to every rank: two collectives (features; both label vectors packed)"""
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(qf, src=src, group=group)
+    lab = torch.stack([qp, qc])
+    dist.broadcast(lab, src=src, group=group)
+    qp.copy_(lab[0]); qc.copy_(lab[1])
+
+
 def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids_local, metric='euclidean',
-                          max_rank=50, group=None, broadcast_queries=True, ops=None, fused=None):
+                          max_rank=50, group=None, broadcast_queries=True, ops=None, fused=None, gallery_counts=None):
     """MARS-metric CMC/mAP (rank.py:160-212) of ``qf`` against the union of every rank's gallery shard.
 
     qf (num_q, d) and the query labels must be the same on every rank (``broadcast_queries`` copies
     rank 0's); gf_local (num_g_r, d) and its labels are this rank's rows.  Gallery indices are global:
     shard r starts at sum(num_g_0..r-1), which is also how ties are broken (by global index).
+    ``gallery_counts``: rows of every rank's shard when the caller knows them (skips one all-gather and its host sync).
     ``fused``: distance -> top-k in the GEMM epilogue, no (num_q x num_g_r) matrix (default: from FUSED_MIN_GALLERY
     gallery rows per shard on; same result either way).
     Returns (numpy.float64[max_rank], numpy.float64) on every rank.
@@ -230,17 +256,9 @@ def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids
     gp, gc = _as_dev_i64(g_pids_local, dev), _as_dev_i64(g_camids_local, dev)
     qf = qf.contiguous()
     if world > 1 and broadcast_queries:
-        for t in (qf, qp, qc):
-            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        _broadcast_queries(qf, qp, qc, group)
     # global index of this shard's first row
-    n_local = torch.tensor([gf_local.shape[0]], dtype=torch.int64, device=dev)
-    if world > 1:
-        counts = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, n_local, group=group)
-        counts = counts.cpu().tolist()
-        rank = dist.get_rank(group)
-    else:
-        counts, rank = [int(n_local)], 0
+    counts, rank = _shard_layout(gf_local.shape[0], dev, world, group, gallery_counts)
     total = sum(counts)
     if total < max_rank:
         raise ValueError('could not broadcast input array from shape ({},) into shape ({},)'.format(total, max_rank))
@@ -270,7 +288,7 @@ def evaluate_mars_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids
 
 
 def evaluate_market1501_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_camids_local, metric='euclidean',
-                                max_rank=50, group=None, broadcast_queries=True, ops=None):
+                                max_rank=50, group=None, broadcast_queries=True, ops=None, gallery_counts=None):
     """market1501-metric CMC/mAP (rank_cy.pyx:154-241 semantics) of ``qf`` against the union of every
     rank's gallery shard: same arguments as evaluate_mars_sharded, returns (numpy.float32[rank_len], float)
     on every rank, bit-identical to the unsharded evaluator (ties by global gallery index).
@@ -284,16 +302,8 @@ def evaluate_market1501_sharded(qf, gf_local, q_pids, g_pids_local, q_camids, g_
     gp, gc = _as_dev_i64(g_pids_local, dev), _as_dev_i64(g_camids_local, dev)
     qf = qf.contiguous()
     if world > 1 and broadcast_queries:
-        for t in (qf, qp, qc):
-            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    n_local = torch.tensor([gf_local.shape[0]], dtype=torch.int64, device=dev)
-    if world > 1:
-        counts_g = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts_g, n_local, group=group)
-        counts_g = counts_g.cpu().tolist()
-        rank = dist.get_rank(group)
-    else:
-        counts_g, rank = [int(n_local)], 0
+        _broadcast_queries(qf, qp, qc, group)
+    counts_g, rank = _shard_layout(gf_local.shape[0], dev, world, group, gallery_counts)
     ng_total, offset = sum(counts_g), sum(counts_g[:rank])
     if ng_total < max_rank:
         print('Note: number of gallery samples is quite small, got {}'.format(ng_total))     # rank_cy.pyx:160-162

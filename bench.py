@@ -283,7 +283,7 @@ def run_b200(args):
             d = metrics.compute_distance_matrix(feats[:NQ], feats[NQ:], metric)
             return metrics.evaluate_rank(d, lab[0], lab[1], lab[2], lab[3], use_metric_mars=True)
         return sharded.evaluate_mars_sharded(feats[:NQ], feats[NQ:], lab[0], lab[1], lab[2], lab[3],
-                                             metric=metric, max_rank=50)
+                                             metric=metric, max_rank=50, gallery_counts=[NG] * world)
 
     with torch.no_grad():
         for _ in range(args.warmup):

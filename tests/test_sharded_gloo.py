@@ -180,8 +180,9 @@ def _worker(rank, world, port, case, out_dir):
         qc_r = qc if rank == 0 else np.zeros_like(qc)
         cmc, mAP = sharded.evaluate_mars_sharded(qf_r, gf[lo:hi], qp_r, gp[lo:hi], qc_r, gc[lo:hi],
                                                  metric=metric, max_rank=K, ops=CpuOps())
+        counts = [b - a for a, b in sharded.shard_bounds(len(gp), world)]      # known shard sizes: no count exchange
         mcmc, mmAP = sharded.evaluate_market1501_sharded(qf_r, gf[lo:hi], qp_r, gp[lo:hi], qc_r, gc[lo:hi],
-                                                         metric=metric, max_rank=K, ops=CpuOps())
+                                                         metric=metric, max_rank=K, ops=CpuOps(), gallery_counts=counts)
         np.savez(os.path.join(out_dir, 'r%d.npz' % rank), cmc=cmc, mAP=mAP, mcmc=mcmc, mmAP=mmAP)
     finally:
         dist.destroy_process_group()

@@ -24,7 +24,7 @@ for split in (2, 1, 3, 4):
     m = m.cuda().eval()
     for lowrank in (True, False):
         for tma in (True, False):
-            m.head_lowrank, m.pool_tma = lowrank, tma
+            m.head_lowrank, m.pool_tma, m.gemm_pair = lowrank, tma, tma
             with torch.no_grad():
                 outs.append(m.head(x1.cuda(), x2.cuda(), adj, S))
                 outs.append(m.head(x1.cuda(), x2.cuda(), masks, S))
@@ -42,5 +42,15 @@ for metric in ('euclidean', 'cosine'):
     rr = re_ranking_dev(qg, qq, gg)
     print(metric, metrics.evaluate_rank(rr, qp, gp, qc, gc, use_metric_mars=True)[1],
           metrics.evaluate_rank(qg, qp, gp, qc, gc, use_metric_market1501=True)[1])
+# fused distance -> top-k (EpiTopK, compaction, label hash tables) incl. the overflow flag
+from agrl.pytorch_b200 import sharded
+from agrl.pytorch_b200.metrics.distance import PreparedOperand
+ops = sharded.CudaOps()
+g = torch.Generator(device='cuda').manual_seed(9)
+q2, g2 = torch.randn(70, 200, generator=g, device='cuda'), torch.randn(3000, 200, generator=g, device='cuda')
+lab = [torch.randint(0, 9, (n,), generator=g, device='cuda') for n in (70, 3000, 70, 3000)]
+for metric in ('euclidean', 'cosine'):
+    k, c, n, st = ops.topk_fused(PreparedOperand(q2, metric), PreparedOperand(g2, metric), lab[0], lab[1], lab[2], lab[3], 50, 5)
+    outs.append(k.float())
 torch.cuda.synchronize()
 print('ok', float(sum(o.double().sum() for o in outs)))
