@@ -964,7 +964,7 @@ graph_kernel_tc(GraphArgs a) {
 // Z = Q.W^T (4S rows per tracklet, from the GEMM) and G.T (V x 4S, from graph_kernel_tc).  A thread keeps its columns of
 // Z in registers, the rows of G.T come as shared-memory broadcasts.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMixLd = 36;                             // 4S <= 36 for V <= 64, padded with zeros
+constexpr int kMixLdMax = 36;                          // 4S <= 36 for V <= 64; the kernel is instantiated for 32 (S <= 8) and 36
 struct MixArgs {
     const float *x, *z, *gt;           // (B, V, C), (B, 4S, C), (B, V, 4S)
     float *out;                        // (B, V, C)
@@ -978,6 +978,7 @@ struct MixArgs {
 // grid (C / 512, tracklets).  (Packed fma.rn.f32x2 with the weights duplicated in shared memory was measured: 4.67 vs
 // 4.40 ms per pass -- FFMA2 issues at half rate on sm_100, the extra LDS traffic is pure cost.)
 constexpr int kMixRows = 8;
+template <int kMixLd>                                  // row length of G.T in shared memory / registers: 4S padded with zeros
 __global__ void __launch_bounds__(kHeadThreads, 2)
 graph_mix_kernel(MixArgs a) {
     __shared__ __align__(16) float s_gt[kMaxNodes * kMixLd];
@@ -1306,7 +1307,8 @@ static int launch_layers(const agrl_head_params *p, const Prepared &pr, HeadWork
             if ((rc = launch_layer_gemm(p->split, pair, map_q, map_w, static_cast<int>(qrows), C, z2, z1, z4, st))) return rc;
             MixArgs ma{x[cur], z, ga.gt, dst, pr.scale[l], pr.shift[l], V, S4, C, p->gamma, p->leaky_slope};
             AGRL_LAUNCH_BEGIN(st);
-            graph_mix_kernel<<<dim3(C / (2 * kHeadThreads), static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
+            if (S4 <= 32) graph_mix_kernel<32><<<dim3(C / (2 * kHeadThreads), static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
+            else graph_mix_kernel<kMixLdMax><<<dim3(C / (2 * kHeadThreads), static_cast<unsigned>(n)), kHeadThreads, 0, st>>>(ma);
             AGRL_LAUNCH_CHECK(st, "graph_mix");
             if (dst == nodes_out) x[cur ^ 1] = nodes_out;
             cur ^= 1;
