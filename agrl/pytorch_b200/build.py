@@ -28,6 +28,11 @@ NVCC_FLAGS = [
 ]
 
 
+def extra_flags():
+    """AGRL_NVCC_EXTRA: extra nvcc flags for diagnostic builds (e.g. -DAGRL_TIMELINE, see tools/graph_timeline.py)."""
+    return os.environ.get('AGRL_NVCC_EXTRA', '').split()
+
+
 def nvcc():
     exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(exe):
@@ -63,7 +68,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
         if force or stale(obj, [src] + hdrs):
-            cmd = [exe] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            cmd = [exe] + NVCC_FLAGS + extra_flags() + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -760,6 +760,8 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows,
                           int64_t plane_rows);
 
+int make_rows_tensor_map_f32(CUtensorMap *map, const float *x, int64_t batch, int V, int C);       // split.cu
+
 // CTA-pair flavour; map_b must have been built with box_rows = BN / 2.
 template <int P, int BN, bool kSplit, class Epi>
 int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, int N, int k_pad, const Epi &epi, cudaStream_t st) {

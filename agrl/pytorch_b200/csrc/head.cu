@@ -474,25 +474,38 @@ struct PoseGraph {
 //   Y      per 128-channel block the TRANSPOSED tile [channel][node] (K = nodes) as two bf16 planes; D = G.X^T block,
 //          3 plane products (same 16-bit operand class as the planes Y is rounded to anyway), 128 x 128 x 16 MMAs,
 //          double-buffered accumulator.
-//   roles  13 warps: 0..11 workers, 12 issues the MMAs.  Gram: workers 0..7 convert.  Y: workers 2,3,6..11 convert,
-//          workers 0,1,4,5 (the ones that may read TMEM lanes 0..63) drain accumulators into operand planes.  Inside a
-//          phase the roles are coupled by mbarriers only (operands ready / MMAs retired / accumulator drained).
-//          clock64 per phase (one tracklet, 2 CTAs per SM): Gram 63 k cycles, graph build 28 k, Y 125-143 k, in which the
-//          four drain warps are busy 92 % of the time.  Tried without gain: staging the planes through padded shared
-//          memory for 64-byte-contiguous stores (11.3 vs 11.5 ms per pass), eight drain + six convert warps at 64
-//          registers (12.8 ms), UMMA M = 64 (other TMEM row layout, 8 % faster per MMA), 64-channel Y blocks, two or
-//          four accumulators per product class, three CTAs per SM.
-// Measured: the kernel is 30 % faster than graph_kernel_v2 (11.5 vs 16.3 ms per pass); a Gram on the CUDA cores with
-// only Y on tcgen05 was slower than either (17.1 ms).
-// One CTA per tracklet, 416 threads, 2 CTAs per SM (81 KiB smem, 256 TMEM columns each).
+//   input  a loader warp fetches the node rows as raw fp32 tiles [V][64 channels] with ONE bulk tensor copy per tile
+//          (3-D tensor map over (tracklet, node, channel), completion on an mbarrier); the converters read shared memory.
+//   roles  14 warps: 0..11 workers, 12 issues the MMAs, 13 loads.  Gram: workers 0..7 convert (three operand buffers,
+//          three tiles in flight).  Y: workers 2,3,6..11 convert, workers 0,1,4,5 (the ones that may read TMEM lanes
+//          0..63) drain accumulators into operand planes with 32-byte stores (st.global.v8.b32: whole sectors).  Inside
+//          a phase the roles are coupled by mbarriers only (tile landed / stage free / operands ready / MMAs retired /
+//          accumulator drained).
+//   clock64 timeline of one tracklet, 2 CTAs per SM (tools/graph_timeline.py, profiles/r2/graph_timeline.txt):
+//          with register loads Gram 63-70 k cycles, graph build 23-28 k, Y 125-143 k -- every Gram block and every 64
+//          channels of Y waited 2-4 k cycles on its own global loads.  With the staged tiles: Gram 75 k, build 23 k,
+//          Y 99 k.  The Gram phase receives one 14 KiB tile per ~2 k cycles whether two, three or four are in flight
+//          (request-to-landed grows from 2.2 k to 5 k cycles instead): that is the memory system's rate for this
+//          kernel's pattern -- 296 CTAs reading 256-byte pieces 8 KiB apart while their neighbours write 128-byte pieces
+//          4 KiB apart -- about 3-3.7 TB/s chip-wide, so the phase is memory-bound at that efficiency.  Y is bound by
+//          the four drain warps (TMEM -> conversion -> stores, ~6 k cycles per 128 channels).
+//          Tried without gain: staging the output planes through padded shared memory for 64-byte-contiguous stores,
+//          eight drain + six convert warps at 64 registers, UMMA M = 64 (other TMEM row layout), 64-channel Y blocks,
+//          two or four accumulators per product class, three CTAs per SM, 56 row copies per tile instead of the tensor
+//          map (4-5 k cycles of issue overhead per tile), four tile stages with two operand buffers, four operand
+//          buffers with two stages, walking the channels of Y in reverse (to reuse the Gram's tail from L2).
+// Measured: 30 % faster than the CUDA-core kernel of round 1 (11.5 vs 16.3 ms per pass), another 5-10 % from the staged
+// tiles and the 32-byte stores; a Gram on the CUDA cores with only Y on tcgen05 was slower than either (17.1 ms).
+// One CTA per tracklet, 448 threads, 2 CTAs per SM (109 KiB smem at V = 56, 256 TMEM columns each).
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcPlane = 64 * 128;                     // 8 KiB: 64 rows x 128 B
 constexpr int kTcGPlanes = 0;                          // two G planes; the 128-row A descriptor of plane 1 runs into the ring
-constexpr int kTcRingOff = 2 * kTcPlane;               // Gram: 2 buffers x 2 planes x 8 KiB (+ the last plane's 128-row tail);
+constexpr int kTcRingOff = 2 * kTcPlane;               // Gram: 3 buffers x 2 planes x 8 KiB, then the third tile stage;
 constexpr int kTcRingBytes = 8 * kTcPlane;             // Y: 2 buffers x 2 planes x 16 KiB; in between: g[64][68], sq[64]
 constexpr int kTcBars = kTcRingOff + kTcRingBytes;
-constexpr int kTcSmem = kTcBars + 128 + 1024;
-constexpr int kTcThreads = 416;
+constexpr int kTcRawOff = kTcBars + 256;                // message-passing phase: 2 stages of raw fp32 node rows, [V][64 channels] each
+constexpr int kTcSmem = kTcRawOff + 1024;              // + 2 * V * 256 bytes of raw stages (full layer only)
+constexpr int kTcThreads = 448;                        // 12 workers, the MMA issuer, the bulk-copy loader
 static_assert((kMaxNodes * kGLd + kMaxNodes) * 4 <= kTcRingBytes, "g[] fits the ring");
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -525,7 +538,8 @@ __device__ __forceinline__ void split8_f16e4(const float (&v)[8], uint4 &h16, ui
         const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
         hw[i] = *reinterpret_cast<const uint32_t *>(&h);
         const float2 hf = __half22float2(h);
-        r[i] = __nv_cvt_float2_to_fp8x2(make_float2(__fsub_rn(v[2 * i], hf.x) * 64.0f, __fsub_rn(v[2 * i + 1], hf.y) * 64.0f),
+        // (v - h) * 64 as ONE fma: v - h is exact in fp32 and 64 a power of two, so the result is the same number
+        r[i] = __nv_cvt_float2_to_fp8x2(make_float2(fmaf(v[2 * i], 64.0f, -64.0f * hf.x), fmaf(v[2 * i + 1], 64.0f, -64.0f * hf.y)),
                                         __NV_SATFINITE, __NV_E4M3);
         c[i] = __nv_cvt_float2_to_fp8x2(make_float2(v[2 * i] * 0.015625f, v[2 * i + 1] * 0.015625f), __NV_SATFINITE, __NV_E4M3);
     }
@@ -534,26 +548,51 @@ __device__ __forceinline__ void split8_f16e4(const float (&v)[8], uint4 &h16, ui
     val8 = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
 }
 
+// one 32-byte store per lane (STG.256): full 32-byte sectors instead of two half-written ones
+__device__ __forceinline__ void st256(void *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// clock64 timeline of the kernel's phases (tools/graph_timeline.py): compiled in only with -DAGRL_TIMELINE
+// (AGRL_NVCC_EXTRA=-DAGRL_TIMELINE python -m agrl.pytorch_b200.build --force), never in the product library
+#ifdef AGRL_TIMELINE
+__device__ long long *g_timeline = nullptr;
+#define AGRL_TL_DECL                                                                                         \
+    const bool tl_on = g_timeline != nullptr && (blockIdx.x % 97 == 5) && !a.lowrank;                        \
+    const long long tl_base = static_cast<long long>(blockIdx.x / 97) * 256
+#define AGRL_TL(slot) do { if (tl_on && (threadIdx.x & 31) == 0) g_timeline[tl_base + (slot)] = clock64(); } while (0)
+#else
+#define AGRL_TL_DECL
+#define AGRL_TL(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kTcThreads, 2)
-graph_kernel_tc(GraphArgs a) {
+graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
+    AGRL_TL_DECL;
     extern __shared__ __align__(16) unsigned char tc_smem_dyn[];
     unsigned char *smem = tc_smem_dyn + ((1024u - (gemm::smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
     unsigned char *ring_p = smem + kTcRingOff;
     float *g = reinterpret_cast<float *>(ring_p);                      // [64][68], between the two MMA phases
     float *sq = g + kMaxNodes * kGLd;                                  // [64]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcBars);     // done[2], gfull[2], yfull[2], accfree[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kTcBars);     // done[2], gfull[3], gdone[3], yfull[2], accfree[2], tmem slot, rfull[3], rempty[3]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
     const uint32_t gplanes = gemm::smem_u32(smem) + kTcGPlanes, ring = gemm::smem_u32(ring_p), bar0 = gemm::smem_u32(bars);
-    const uint32_t b_done = bar0, b_gfull = bar0 + 16, b_yfull = bar0 + 32, b_accfree = bar0 + 48;
+    const uint32_t b_done = bar0, b_gfull = bar0 + 16, b_gdone = bar0 + 48, b_yfull = bar0 + 80, b_accfree = bar0 + 96;
+    const uint32_t b_rfull = bar0 + 128, b_rempty = bar0 + 160;         // three stages each
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool worker = warp < 12, issuer = warp == 12, gram_worker = warp < 8;
+    const bool worker = warp < 12, issuer = warp == 12, loader = warp == 13, gram_worker = warp < 8;
     const int V = a.V, C = a.C, b = blockIdx.x;
     const float *x = a.x + static_cast<size_t>(b) * V * C;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            gemm::mbar_init(b_done + 8 * i, 1); gemm::mbar_init(b_gfull + 8 * i, 8);
+            gemm::mbar_init(b_done + 8 * i, 1);
             gemm::mbar_init(b_yfull + 8 * i, 8); gemm::mbar_init(b_accfree + 8 * i, 4);
+        }
+        for (int i = 0; i < 3; ++i) {
+            gemm::mbar_init(b_rfull + 8 * i, 1); gemm::mbar_init(b_rempty + 8 * i, 8);
+            gemm::mbar_init(b_gfull + 8 * i, 8); gemm::mbar_init(b_gdone + 8 * i, 1);
         }
         gemm::fence_barrier_init();
     }
@@ -569,70 +608,73 @@ graph_kernel_tc(GraphArgs a) {
     auto wait_bar = [&](uint32_t bar, int use) { gemm::mbar_wait(bar, static_cast<uint32_t>(use & 1)); };
     const int ref_row = (V > 6) ? 6 : V - 1;                           // centre of the Gram: the whole-frame strip of frame 0
     const int n_gblocks = C / 64;                                      // even (C % 128 == 0)
-    const int g_uses = a.learn_graph ? n_gblocks / 2 : 0;              // commits on each done[] barrier by the Gram phase
+    if (warp == 0) AGRL_TL(0);
+    // Input staging: the node rows reach both tensor-core phases as raw fp32 tiles, [V][64 channels] each, fetched by ONE
+    // bulk tensor copy per tile (completion on an mbarrier) by the loader warp -- the converters read shared memory
+    // instead of waiting on global loads (clock64 timeline of the register-load version: 2 k cycles per Gram block and
+    // 3-4 k per 64 channels of the message-passing phase, all of it exposed load latency).  A tile takes ~2.2 k cycles to
+    // arrive, so the Gram phase keeps THREE in flight (the third stage sits in the operand ring's last quarter, next to
+    // its three operand buffers); the message-passing phase, bound by its accumulator drain, uses stages 0 and 1.
+    const int raw_stage = V * 256;
+    auto stage_off = [&](int st) { return st < 2 ? kTcRawOff + st * raw_stage : kTcRingOff + 6 * kTcPlane; };
+    auto load_raw = [&](int piece, int st) {                           // loader: tile of channels [64 piece, +64) -> stage st
+        if (lane == 0) {
+            const uint32_t full = b_rfull + 8 * st;
+            gemm::mbar_arrive_expect_tx(full, static_cast<uint32_t>(raw_stage));
+            gemm::tma_load_3d(gemm::smem_u32(smem) + stage_off(st), &map_x, full, piece * 64, 0, b);
+        }
+    };
+    auto prefetch_l2 = [&](int piece, int n_pieces) {                  // loader: DRAM -> L2, two 128-byte lines per node row
+        if (piece < n_pieces)
+            for (int v = lane; v < 2 * V; v += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(x + static_cast<size_t>(v >> 1) * C + piece * 64 + (v & 1) * 32));
+    };
+    // uses of stage st by the Gram phase (tiles st, st + 3, ...): the message passing continues each barrier's phase count
+    auto gram_uses_of = [&](int st) { return a.learn_graph ? (n_gblocks + 2 - st) / 3 : 0; };
+    if (loader && lane == 0) gemm::prefetch_tensormap(&map_x);
 
     if (a.learn_graph) {
         // ================= Gram =================
         if (gram_worker) {
-            // item = (row, 8-channel slot): 64 rows x 8 slots, two items per thread; blocks kb and kb + 1 in flight
-            float nxt[2][8], nx2[2][8];
-            const float *xref = x + static_cast<size_t>(ref_row) * C;
-            auto load_block = [&](int kb, float (&dstv)[2][8]) {
-                const float4 *rsrc = reinterpret_cast<const float4 *>(xref + kb * 64 + (tid & 7) * 8);      // slot is the same for both items
-                const float4 rlo = __ldg(rsrc), rhi = __ldg(rsrc + 1);
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
-                    if (row < V) {
-                        const float4 *src = reinterpret_cast<const float4 *>(x + static_cast<size_t>(row) * C + kb * 64 + slot * 8);
-                        const float4 lo = __ldg(src), hi = __ldg(src + 1);
-                        dstv[t][0] = __fsub_rn(lo.x, rlo.x); dstv[t][1] = __fsub_rn(lo.y, rlo.y);
-                        dstv[t][2] = __fsub_rn(lo.z, rlo.z); dstv[t][3] = __fsub_rn(lo.w, rlo.w);
-                        dstv[t][4] = __fsub_rn(hi.x, rhi.x); dstv[t][5] = __fsub_rn(hi.y, rhi.y);
-                        dstv[t][6] = __fsub_rn(hi.z, rhi.z); dstv[t][7] = __fsub_rn(hi.w, rhi.w);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dstv[t][i] = 0.f;
-                    }
-                }
-            };
-            auto prefetch_block = [&](int kb) {                         // DRAM -> L2 a few blocks ahead
-                if (kb < n_gblocks && (tid & 3) == 0) {
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const int row = (tid >> 3) + 32 * t;
-                        if (row < V) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + static_cast<size_t>(row) * C + kb * 64 + (tid & 4) * 8));
-                    }
-                }
-            };
-            prefetch_block(2); prefetch_block(3); prefetch_block(4); prefetch_block(5);
-            load_block(0, nxt);
-            load_block(1, nx2);
-            auto gram_step = [&](int kb, float (&cur)[2][8]) {          // convert block kb (in `cur`), refill `cur` with kb + 2
-                const int buf = kb & 1;
-                prefetch_block(kb + 6);
-                if (kb >= 2) wait_bar(b_done + 8 * buf, (kb >> 1) - 1);  // the MMAs that read this buffer have retired
+            // item = (row, 8-channel slot): 64 rows x 8 slots, two items per thread, read from the staged tile
+            for (int kb = 0; kb < n_gblocks; ++kb) {
+                const int buf = kb % 3, use = kb / 3;                  // three operand buffers, three tile stages
+                wait_bar(b_rfull + 8 * buf, use);                      // the tile has landed
+                if (warp == 0) AGRL_TL(96 + kb);
+                if (kb >= 3) wait_bar(b_gdone + 8 * buf, use - 1);     // the MMAs that read this operand buffer have retired
+                if (warp == 0) AGRL_TL(192 + kb);
+                const float *rs = reinterpret_cast<const float *>(smem + stage_off(buf));
+                const float4 *rsrc = reinterpret_cast<const float4 *>(rs + ref_row * 64 + (tid & 7) * 8);   // slot is the same for both items
+                const float4 rlo = rsrc[0], rhi = rsrc[1];
                 unsigned char *dst = ring_p + buf * 2 * kTcPlane;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int item = tid + kHeadThreads * t, row = item >> 3, slot = item & 7;
+                    float c[8];
+                    if (row < V) {
+                        const float4 *src = reinterpret_cast<const float4 *>(rs + row * 64 + slot * 8);
+                        const float4 lo = src[0], hi = src[1];
+                        c[0] = __fsub_rn(lo.x, rlo.x); c[1] = __fsub_rn(lo.y, rlo.y); c[2] = __fsub_rn(lo.z, rlo.z); c[3] = __fsub_rn(lo.w, rlo.w);
+                        c[4] = __fsub_rn(hi.x, rhi.x); c[5] = __fsub_rn(hi.y, rhi.y); c[6] = __fsub_rn(hi.z, rhi.z); c[7] = __fsub_rn(hi.w, rhi.w);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) c[i] = 0.f;
+                    }
                     uint4 pl[2];
-                    split8<2>(cur[t], pl);
+                    split8<2>(c, pl);
                     const int off = row * 128 + ((slot ^ (row & 7)) << 4);
 #pragma unroll
                     for (int p = 0; p < 2; ++p) *reinterpret_cast<uint4 *>(dst + p * kTcPlane + off) = pl[p];
                 }
-                fence_proxy_async_smem();                               // (a MEMBAR: issue it BEFORE the next loads, or it waits for them)
+                fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) gemm::mbar_arrive(b_gfull + 8 * buf);
-                if (kb + 2 < n_gblocks) load_block(kb + 2, cur);
-            };
-            for (int kb = 0; kb < n_gblocks; kb += 2) {
-                gram_step(kb, nxt);
-                gram_step(kb + 1, nx2);
+                // (the stage is released only after its values have been converted and stored: an arrive right after the
+                // shared-memory loads would let the next bulk copy -- another proxy -- overtake them)
+                if (lane == 0) { gemm::mbar_arrive(b_gfull + 8 * buf); gemm::mbar_arrive(b_rempty + 8 * buf); }
+                if (warp == 0) AGRL_TL(128 + kb);
             }
-            wait_bar(b_done, g_uses - 1);                              // every Gram MMA has retired
-            wait_bar(b_done + 8, g_uses - 1);
+            for (int i = 0; i < 3; ++i)                                // every Gram MMA has retired
+                if (i < n_gblocks) wait_bar(b_gdone + 8 * i, (n_gblocks + 2 - i) / 3 - 1);
             gemm::tc_fence_after();
             if (epi_warp) {
                 uint32_t m[32], c[32];
@@ -648,8 +690,8 @@ graph_kernel_tc(GraphArgs a) {
         } else if (issuer && lane == 0) {
             constexpr uint32_t idesc = gemm::make_idesc(128, 64);
             for (int kb = 0; kb < n_gblocks; ++kb) {
-                const int buf = kb & 1;
-                wait_bar(b_gfull + 8 * buf, kb >> 1);
+                const int buf = kb % 3;
+                wait_bar(b_gfull + 8 * buf, kb / 3);
                 gemm::tc_fence_after();
                 const uint32_t base = ring + buf * 2 * kTcPlane;
 #pragma unroll
@@ -663,10 +705,23 @@ graph_kernel_tc(GraphArgs a) {
                         gemm::tc_mma_bf16(tmem + (main_acc ? 0 : 64), da + 2 * k, db + 2 * k, idesc,
                                           main_acc ? ((kb | k) != 0) : ((kb | i | k) != 0));
                 }
-                gemm::tc_commit(b_done + 8 * buf);
+                gemm::tc_commit(b_gdone + 8 * buf);
+                AGRL_TL(160 + kb);
             }
+        } else if (loader) {
+            for (int kb = 0; kb < n_gblocks; ++kb) {
+                prefetch_l2(kb + 8, n_gblocks);
+                if (kb >= 3) wait_bar(b_rempty + 8 * (kb % 3), kb / 3 - 1);
+                load_raw(kb, kb % 3);
+            }
+            if (!a.lowrank)                                            // the first two tiles of the message-passing phase
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (gram_uses_of(hh) > 0) wait_bar(b_rempty + 8 * hh, gram_uses_of(hh) - 1);
+                    load_raw(hh, hh);
+                }
         }
         __syncthreads();
+        if (warp == 0) AGRL_TL(1);
         if (gram_worker && tid < V) sq[tid] = g[tid * kGLd + tid];
         __syncthreads();
         if (worker) {
@@ -818,6 +873,7 @@ graph_kernel_tc(GraphArgs a) {
 
     // ================= Y = G . X, 128 channels per block =================
     const int n_blocks = C / 128;
+    if (warp == 0) AGRL_TL(2);
     if (issuer) {
         if (lane == 0) {
             constexpr uint32_t idesc = gemm::make_idesc(128, 128);
@@ -836,36 +892,42 @@ graph_kernel_tc(GraphArgs a) {
                     for (int k = 0; k < 4; ++k) gemm::tc_mma_bf16(tmem + buf * 128, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
                 }
                 gemm::tc_commit(b_done + 8 * buf);
+                AGRL_TL(16 + cb);
             }
+        }
+    } else if (loader) {
+        // tile hh as soon as every converter warp has released the stage of tile hh - 2 (tiles 0 and 1 were requested at the end
+        // of the Gram phase when there is one)
+        const int n_halves = 2 * n_blocks;
+        for (int hh = a.learn_graph ? 2 : 0; hh < n_halves; ++hh) {
+            prefetch_l2(hh + 4, n_halves);
+            const int use = gram_uses_of(hh & 1) + (hh >> 1);
+            if (use > 0) wait_bar(b_rempty + 8 * (hh & 1), use - 1);
+            load_raw(hh, hh & 1);
         }
     } else if (!epi_warp) {
         // converters (workers 2,3,6..11 -> 256 threads), 64 channels at a time: item = (channel, 8-node group), lane =
-        // channel, so every load instruction is one coalesced 128-byte piece of a node row; two items per thread, the
-        // next 64 channels in flight; two such halves fill one operand buffer
+        // channel, so every shared-memory read is conflict-free (32 consecutive floats of one node row); two items per
+        // thread; two such pieces fill one operand buffer
         const int cw = warp < 8 ? ((warp >> 2) * 2 + (warp & 1)) : warp - 4;   // 0..7
         const int ctid = cw * 32 + lane, ch = ctid & 63, g0 = ctid >> 6, n_halves = 2 * n_blocks;
         float nx[2][8];
-        auto load_half = [&](int hh) {
+        for (int hh = 0; hh < n_halves; ++hh) {
+            wait_bar(b_rfull + 8 * (hh & 1), gram_uses_of(hh & 1) + (hh >> 1));   // the tile has landed
+            {
+                const float *rs = reinterpret_cast<const float *>(smem + stage_off(hh & 1)) + ch;
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
+                for (int t = 0; t < 2; ++t) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int v = (g0 + 4 * t) * 8 + i;
-                    nx[t][i] = (v < V) ? __ldg(x + static_cast<size_t>(v) * C + hh * 64 + ch) : 0.f;
+                    for (int i = 0; i < 8; ++i) {
+                        const int v = (g0 + 4 * t) * 8 + i;
+                        nx[t][i] = (v < V) ? rs[v * 64] : 0.f;
+                    }
                 }
             }
-        };
-        auto prefetch_half = [&](int hh) {                              // DRAM -> L2 ahead: one 128-byte line per thread
-            const int row = ctid & 63;
-            if (ctid < 128 && hh < n_halves && row < V)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(x + static_cast<size_t>(row) * C + hh * 64 + (ctid >> 6) * 32));
-        };
-        for (int hh = 1; hh < 6; ++hh) prefetch_half(hh);
-        load_half(0);
-        for (int hh = 0; hh < n_halves; ++hh) {
-            prefetch_half(hh + 6);
-            const int cb = hh >> 1, buf = cb & 1, prev = g_uses + (cb >> 1) - 1;
+            const int cb = hh >> 1, buf = cb & 1, prev = (cb >> 1) - 1;
             if ((hh & 1) == 0 && prev >= 0) wait_bar(b_done + 8 * buf, prev);   // the MMAs that read this buffer have retired
+            if ((hh & 1) == 0 && cw == 0) AGRL_TL(48 + cb);
             unsigned char *dst = ring_p + buf * 4 * kTcPlane;
             const int row = (hh & 1) * 64 + ch;
 #pragma unroll
@@ -876,18 +938,23 @@ graph_kernel_tc(GraphArgs a) {
                 *reinterpret_cast<uint4 *>(dst + off) = pl[0];
                 *reinterpret_cast<uint4 *>(dst + 2 * kTcPlane + off) = pl[1];
             }
+            // the stage may be refilled only now: the shared-memory reads above have certainly completed once their values
+            // have been converted and stored (an arrive right after the loads lets the bulk copy -- another proxy -- overtake them)
+            __syncwarp();
+            if (lane == 0) gemm::mbar_arrive(b_rempty + 8 * (hh & 1));
             if (hh & 1) {
-                fence_proxy_async_smem();                               // (a MEMBAR: before the next loads are issued)
+                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) gemm::mbar_arrive(b_yfull + 8 * buf);
+                if (cw == 0) AGRL_TL(32 + cb);
             }
-            if (hh + 1 < n_halves) load_half(hh + 1);
         }
     } else {
         // epilogue (workers 0,1,4,5): accumulator -> registers (frees it for block cb + 2) -> planes -> global
         for (int cb = 0; cb < n_blocks; ++cb) {
             const int acc = cb & 1;
-            wait_bar(b_done + 8 * acc, g_uses + (cb >> 1));
+            wait_bar(b_done + 8 * acc, cb >> 1);
+            if (warp == 0) AGRL_TL(64 + cb);
             gemm::tc_fence_after();
             uint32_t r[2][32];
             gemm::tmem_ld_32x32(tlane + acc * 128 + ehalf * 64, r[0]);
@@ -896,6 +963,7 @@ graph_kernel_tc(GraphArgs a) {
             gemm::tc_fence_before();
             __syncwarp();
             if (lane == 0) gemm::mbar_arrive(b_accfree + 8 * acc);
+            if (warp == 0) AGRL_TL(80 + cb);
             if (erow < V) {
 #pragma unroll
                 for (int hq = 0; hq < 2; ++hq) {
@@ -904,21 +972,19 @@ graph_kernel_tc(GraphArgs a) {
                         // this thread's 64 channels are exactly k-block 2 cb + ehalf of the row
                         unsigned char *row8 = reinterpret_cast<unsigned char *>(a.y_planes + a.plane_stride + (static_cast<size_t>(b) * V + erow) * C) +
                                               (cb * 2 + ehalf) * 128 + hq * 32;
+                        // 32 channels: 64 bytes of fp16, 32 bytes of residuals, 32 bytes of value copies -> four 32-byte stores
+                        uint4 h16[4]; uint2 r8[4], c8[4];
 #pragma unroll
-                        for (int qq = 0; qq < 2; ++qq) {
-                            uint4 h16[2]; uint2 r8[2], c8[2];
+                        for (int e = 0; e < 4; ++e) {
+                            float v[8];
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                float v[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[hq][16 * qq + 8 * e + i]) * y_scale;
-                                split8_f16e4(v, h16[e], r8[e], c8[e]);
-                            }
-                            reinterpret_cast<uint4 *>(dst)[2 * qq] = h16[0];
-                            reinterpret_cast<uint4 *>(dst)[2 * qq + 1] = h16[1];
-                            *reinterpret_cast<uint4 *>(row8 + qq * 16) = make_uint4(r8[0].x, r8[0].y, r8[1].x, r8[1].y);
-                            *reinterpret_cast<uint4 *>(row8 + 64 + qq * 16) = make_uint4(c8[0].x, c8[0].y, c8[1].x, c8[1].y);
+                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[hq][8 * e + i]) * y_scale;
+                            split8_f16e4(v, h16[e], r8[e], c8[e]);
                         }
+                        st256(dst, h16[0], h16[1]);
+                        st256(dst + 16, h16[2], h16[3]);
+                        st256(row8, make_uint4(r8[0].x, r8[0].y, r8[1].x, r8[1].y), make_uint4(r8[2].x, r8[2].y, r8[3].x, r8[3].y));
+                        st256(row8 + 64, make_uint4(c8[0].x, c8[0].y, c8[1].x, c8[1].y), make_uint4(c8[2].x, c8[2].y, c8[3].x, c8[3].y));
                     } else if (a.fp16) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -954,6 +1020,7 @@ graph_kernel_tc(GraphArgs a) {
             }
         }
     }
+    if (warp == 0) AGRL_TL(3);
     gemm::tc_fence_before();
     __syncthreads();
     if (warp == 0) gemm::tmem_dealloc(tmem, 256);
@@ -1151,8 +1218,13 @@ static int check_params(const agrl_head_params *p) {
 }
 
 static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
-    AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-    graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, kTcSmem, st>>>(ga);
+    // + two stages of raw node tiles: 109 KiB at V = 56, two CTAs per SM
+    const int smem = kTcSmem + 2 * ga.V * 256;
+    AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem + 2 * kMaxNodes * 256));
+    CUtensorMap map_x;
+    int rc = gemm::make_rows_tensor_map_f32(&map_x, ga.x, batch, ga.V, ga.C);
+    if (rc) return rc;
+    graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, smem, st>>>(map_x, ga);
     AGRL_LAUNCH_CHECK(st, "graph");
     return AGRL_OK;
 }
@@ -1160,6 +1232,12 @@ static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
 }  // namespace agrl
 
 using namespace agrl;
+
+#ifdef AGRL_TIMELINE
+extern "C" __attribute__((visibility("default"))) int agrl_timeline_set(long long *buf) {
+    return cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 extern "C" size_t agrl_head_prepared_bytes(const agrl_head_params *p) {
     if (check_params(p)) return 0;
