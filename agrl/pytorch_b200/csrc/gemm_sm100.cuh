@@ -760,7 +760,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, int64_t k_pad, int P, int box_rows,
                           int64_t plane_rows);
 
-int make_rows_tensor_map_f32(CUtensorMap *map, const float *x, int64_t batch, int V, int C);       // split.cu
+int make_rows_tensor_map_f32(CUtensorMap *map, const float *x, int64_t batch, int V, int C, int box_channels);       // split.cu
 
 // CTA-pair flavour; map_b must have been built with box_rows = BN / 2.
 template <int P, int BN, bool kSplit, class Epi>

@@ -568,7 +568,7 @@ __device__ long long *g_timeline = nullptr;
 #endif
 
 __global__ void __launch_bounds__(kTcThreads, 2)
-graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
+graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_pf, GraphArgs a) {
     AGRL_TL_DECL;
     extern __shared__ __align__(16) unsigned char tc_smem_dyn[];
     unsigned char *smem = tc_smem_dyn + ((1024u - (gemm::smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
@@ -624,14 +624,16 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
             gemm::tma_load_3d(gemm::smem_u32(smem) + stage_off(st), &map_x, full, piece * 64, 0, b);
         }
     };
-    auto prefetch_l2 = [&](int piece, int n_pieces) {                  // loader: DRAM -> L2, two 128-byte lines per node row
-        if (piece < n_pieces)
-            for (int v = lane; v < 2 * V; v += 32)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(x + static_cast<size_t>(v >> 1) * C + piece * 64 + (v & 1) * 32));
+    // loader: DRAM -> L2 ahead of the tile copies, one request per FOUR tiles (1 KiB of every node row).  (Measured: the
+    // same kernel time as 112 per-line prefetches per tile, i.e. the size of the DRAM pieces is not what limits the phase.)
+    auto prefetch_l2 = [&](int piece, int n_pieces) {
+        if (lane == 0 && piece >= 0 && (piece & 3) == 0 && piece < n_pieces)
+            asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                         ::"l"(reinterpret_cast<uint64_t>(&map_pf)), "r"(piece * 64), "r"(0), "r"(b) : "memory");
     };
     // uses of stage st by the Gram phase (tiles st, st + 3, ...): the message passing continues each barrier's phase count
     auto gram_uses_of = [&](int st) { return a.learn_graph ? (n_gblocks + 2 - st) / 3 : 0; };
-    if (loader && lane == 0) gemm::prefetch_tensormap(&map_x);
+    if (loader && lane == 0) { gemm::prefetch_tensormap(&map_x); gemm::prefetch_tensormap(&map_pf); }
 
     if (a.learn_graph) {
         // ================= Gram =================
@@ -709,8 +711,11 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
                 AGRL_TL(160 + kb);
             }
         } else if (loader) {
+            prefetch_l2(0, n_gblocks);
+            prefetch_l2(4, n_gblocks);
             for (int kb = 0; kb < n_gblocks; ++kb) {
                 prefetch_l2(kb + 8, n_gblocks);
+                if (!a.lowrank) prefetch_l2(kb + 8 - n_gblocks, 8);       // ... and the first tiles of the message passing
                 if (kb >= 3) wait_bar(b_rempty + 8 * (kb % 3), kb / 3 - 1);
                 load_raw(kb, kb % 3);
             }
@@ -899,8 +904,9 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
         // tile hh as soon as every converter warp has released the stage of tile hh - 2 (tiles 0 and 1 were requested at the end
         // of the Gram phase when there is one)
         const int n_halves = 2 * n_blocks;
+        if (!a.learn_graph) { prefetch_l2(0, n_halves); prefetch_l2(4, n_halves); }
         for (int hh = a.learn_graph ? 2 : 0; hh < n_halves; ++hh) {
-            prefetch_l2(hh + 4, n_halves);
+            prefetch_l2(hh + 8, n_halves);
             const int use = gram_uses_of(hh & 1) + (hh >> 1);
             if (use > 0) wait_bar(b_rempty + 8 * (hh & 1), use - 1);
             load_raw(hh, hh & 1);
@@ -1221,10 +1227,11 @@ static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
     // + two stages of raw node tiles: 109 KiB at V = 56, two CTAs per SM
     const int smem = kTcSmem + 2 * ga.V * 256;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem + 2 * kMaxNodes * 256));
-    CUtensorMap map_x;
-    int rc = gemm::make_rows_tensor_map_f32(&map_x, ga.x, batch, ga.V, ga.C);
+    CUtensorMap map_x, map_pf;
+    int rc = gemm::make_rows_tensor_map_f32(&map_x, ga.x, batch, ga.V, ga.C, 64);
+    if (rc == AGRL_OK) rc = gemm::make_rows_tensor_map_f32(&map_pf, ga.x, batch, ga.V, ga.C, 256);
     if (rc) return rc;
-    graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, smem, st>>>(map_x, ga);
+    graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, smem, st>>>(map_x, map_pf, ga);
     AGRL_LAUNCH_CHECK(st, "graph");
     return AGRL_OK;
 }

@@ -133,14 +133,14 @@ int make_plane_tensor_map(CUtensorMap *map, const void *planes, int64_t rows, in
     return AGRL_OK;
 }
 
-// 3-D tensor map over fp32 node rows (batch, V, C): box = (64 channels, V rows, 1 tracklet), no swizzle -- one bulk
-// tensor copy lands a [V][64] fp32 tile (256-byte rows) of one tracklet in shared memory (graph_kernel_tc, head.cu).
-int make_rows_tensor_map_f32(CUtensorMap *map, const float *x, int64_t batch, int V, int C) {
+// 3-D tensor map over fp32 node rows (batch, V, C): box = (box_channels <= 256, V rows, 1 tracklet), no swizzle -- one
+// bulk tensor copy lands a [V][64] fp32 tile (256-byte rows) of one tracklet in shared memory (graph_kernel_tc, head.cu).
+int make_rows_tensor_map_f32(CUtensorMap *map, const float *x, int64_t batch, int V, int C, int box_channels) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return AGRL_E_NO_DEVICE;
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(V), static_cast<cuuint64_t>(batch)};
     const cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(V) * C * 4};
-    const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(V), 1};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_channels), static_cast<cuuint32_t>(V), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
