@@ -15,7 +15,7 @@ E_INVALID, E_NO_DEVICE, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = -1, -2, -3, -4, -5
 E_NO_VALID_QUERY, E_ZERO_DIVISION, E_LABEL_RANGE = -6, -7, -8
 ST_NO_VALID_QUERY, ST_ZERO_DIVISION, ST_LABEL_RANGE, ST_TOPK_OVERFLOW = 1, 2, 4, 8
 METRIC_EUCLIDEAN, METRIC_COSINE = 0, 1
-SPLIT_BF16X3, SPLIT_BF16X2, SPLIT_FP16X1, SPLIT_FP16_E4M3 = 3, 2, 1, 4
+SPLIT_BF16X3, SPLIT_BF16X2, SPLIT_FP16X1, SPLIT_FP16_E4M3, SPLIT_FP16X2 = 3, 2, 1, 4, 5
 CLIP_POOL_AVG, CLIP_POOL_MAX = 0, 1
 HEAD_MAX_LAYERS = 4
 
@@ -121,6 +121,11 @@ def load(build_if_missing=True):
         raise ImportError('libagrl_b200.so ABI version mismatch')
     _lib = lib
     return lib
+
+
+def planes_of_distance_split(split):
+    """16-bit planes per row of a prepared distance operand (csrc/distance.cu planes_of)."""
+    return 2 if split == SPLIT_FP16X2 else int(split)
 
 
 def exported_names():

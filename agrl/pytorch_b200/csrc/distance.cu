@@ -10,23 +10,40 @@
 
 namespace agrl {
 
-// One prepared operand: bf16 planes [P][rows][K_pad] followed by the per-row squared norms.
+// One prepared operand: 16-bit planes [P][rows][K_pad], the per-row squared norms, the per-row 1 / scale (fp16 x 2).
 struct Operand {
     __nv_bfloat16 *planes;
-    float *sumsq;
+    float *sumsq, *unscale;
     size_t bytes;
 };
 
-static Operand carve_operand(void *buf, int64_t rows, int64_t dim, int P) {
+static int planes_of(int split) { return split == AGRL_SPLIT_FP16X2 ? 2 : split; }
+
+static Operand carve_operand(void *buf, int64_t rows, int64_t dim, int split) {
     Carver c(buf);
     Operand o;
-    o.planes = c.take<__nv_bfloat16>(static_cast<size_t>(P) * rows * gemm::pad_k(dim));
+    o.planes = c.take<__nv_bfloat16>(static_cast<size_t>(planes_of(split)) * rows * gemm::pad_k(dim));
     o.sumsq = c.take<float>(rows);
+    o.unscale = c.take<float>(rows);
     o.bytes = c.total();
     return o;
 }
 
-static bool split_ok(int split) { return split == AGRL_SPLIT_BF16X2 || split == AGRL_SPLIT_BF16X3; }
+static bool split_ok(int split) { return split == AGRL_SPLIT_BF16X2 || split == AGRL_SPLIT_BF16X3 || split == AGRL_SPLIT_FP16X2; }
+
+// fp16 x 2: a CTA pair per 256 x 128 tile (three products per 48 KiB of operands and SM); a single CTA per tile when there
+// is one row tile only
+template <class Epi>
+static int launch_f16x2(const void *q_planes, int64_t num_q, const void *g_planes, int64_t g_rows, int64_t g_plane_rows,
+                        int kp, const Epi &epi, cudaStream_t st) {
+    CUtensorMap map_q, map_g;
+    int rc;
+    if ((rc = gemm::make_plane_tensor_map(&map_q, q_planes, num_q, kp, 2, gemm::BM, num_q))) return rc;
+    const bool pair = num_q > gemm::BM;
+    if ((rc = gemm::make_plane_tensor_map(&map_g, g_planes, g_rows, kp, 2, pair ? 64 : 128, g_plane_rows))) return rc;
+    if (pair) return gemm::launch_pair_gemm<2, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(g_rows), kp, epi, st);
+    return gemm::launch_split_gemm<2, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(g_rows), kp, epi, st);
+}
 static bool metric_ok(int metric) { return metric == AGRL_METRIC_EUCLIDEAN || metric == AGRL_METRIC_COSINE; }
 
 }  // namespace agrl
@@ -49,7 +66,8 @@ extern "C" int agrl_distance_prepare_operand_dev(const float *x, int64_t ld, int
     if (!operand || operand_bytes < o.bytes) return AGRL_E_WORKSPACE;
     const int normalize = (metric == AGRL_METRIC_COSINE);
     gemm::SplitArgs sa{x, ld, o.planes, normalize ? nullptr : o.sumsq, rows, static_cast<int>(dim),
-                       static_cast<int>(gemm::pad_k(dim)), split, normalize};
+                       static_cast<int>(gemm::pad_k(dim)), planes_of(split), normalize};
+    if (split == AGRL_SPLIT_FP16X2) { sa.fp16x2 = 1; sa.unscale = o.unscale; }
     return gemm::launch_split_planes(sa, static_cast<cudaStream_t>(stream));
 }
 
@@ -64,11 +82,15 @@ extern "C" int agrl_distance_prepared_dev(const void *q_operand, int64_t num_q, 
     Operand q = carve_operand(const_cast<void *>(q_operand), num_q, dim, split);
     Operand g = carve_operand(const_cast<void *>(g_operand), num_g, dim, split);
     const int kp = static_cast<int>(gemm::pad_k(dim));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (split == AGRL_SPLIT_FP16X2) {
+        gemm::EpiDistanceF16x2 epi{q.sumsq, g.sumsq, out, ld_out, metric, q.unscale, g.unscale};
+        return launch_f16x2(q.planes, num_q, g.planes, num_g, num_g, kp, epi, st);
+    }
     CUtensorMap map_q, map_g;
     if ((rc = gemm::make_plane_tensor_map(&map_q, q.planes, num_q, kp, split, gemm::BM, num_q))) return rc;
     if ((rc = gemm::make_plane_tensor_map(&map_g, g.planes, num_g, kp, split, 128, num_g))) return rc;
-    gemm::EpiDistance epi{q.sumsq, g.sumsq, out, ld_out, metric};
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    gemm::EpiDistance epi{q.sumsq, g.sumsq, out, ld_out, metric, nullptr, nullptr};
     const int nq = static_cast<int>(num_q), ng = static_cast<int>(num_g);
     if (split == AGRL_SPLIT_BF16X3) return gemm::launch_split_gemm<3, 128, true>(map_q, map_g, nq, ng, kp, epi, st);
     return gemm::launch_split_gemm<2, 128, true>(map_q, map_g, nq, ng, kp, epi, st);
@@ -182,7 +204,7 @@ extern "C" int agrl_distance_topk_dev(const void *q_operand, int64_t num_q, cons
     Operand g = carve_operand(const_cast<void *>(g_operand), num_g, dim, split);
     const int kp = static_cast<int>(gemm::pad_k(dim));
     CUtensorMap map_q, map_g;
-    if ((rc = gemm::make_plane_tensor_map(&map_q, q.planes, num_q, kp, split, gemm::BM, num_q))) return rc;
+    if (split != AGRL_SPLIT_FP16X2 && (rc = gemm::make_plane_tensor_map(&map_q, q.planes, num_q, kp, split, gemm::BM, num_q))) return rc;
     int64_t c0 = 0;
     // expected candidates per row and launch: growth * K (+ the K kept ones); leave 30 % of the list for the spread
     int growth = static_cast<int>(0.7 * (kTopkCap - K) / K);
@@ -196,10 +218,17 @@ extern "C" int agrl_distance_topk_dev(const void *q_operand, int64_t num_q, cons
         // the first launch may keep everything it sees (kTopkFirst <= capacity); later ones add ~growth * K per row
         int64_t width = c0 == 0 ? kTopkFirst : growth * c0;
         if (c0 + width > num_g || num_g - (c0 + width) < width / 8) width = num_g - c0;      // no tiny tail launch
-        if ((rc = gemm::make_plane_tensor_map(&map_g, g.planes + c0 * kp, width, kp, split, 128, num_g))) return rc;
-        gemm::EpiTopK epi{q.sumsq, g.sumsq + c0, metric, w.tau, w.cnt, w.cand, kTopkCap, static_cast<uint32_t>(index_offset + c0)};
-        rc = split == AGRL_SPLIT_BF16X3 ? gemm::launch_split_gemm<3, 128, true>(map_q, map_g, nq, static_cast<int>(width), kp, epi, st)
-                                        : gemm::launch_split_gemm<2, 128, true>(map_q, map_g, nq, static_cast<int>(width), kp, epi, st);
+        if (split == AGRL_SPLIT_FP16X2) {
+            gemm::EpiTopKF16x2 epi{q.sumsq, g.sumsq + c0, metric, w.tau, w.cnt, w.cand, kTopkCap, static_cast<uint32_t>(index_offset + c0),
+                                   q.unscale, g.unscale + c0};
+            rc = launch_f16x2(q.planes, num_q, g.planes + c0 * kp, width, num_g, kp, epi, st);
+        } else {
+            if ((rc = gemm::make_plane_tensor_map(&map_g, g.planes + c0 * kp, width, kp, split, 128, num_g))) return rc;
+            gemm::EpiTopK epi{q.sumsq, g.sumsq + c0, metric, w.tau, w.cnt, w.cand, kTopkCap, static_cast<uint32_t>(index_offset + c0),
+                              nullptr, nullptr};
+            rc = split == AGRL_SPLIT_BF16X3 ? gemm::launch_split_gemm<3, 128, true>(map_q, map_g, nq, static_cast<int>(width), kp, epi, st)
+                                            : gemm::launch_split_gemm<2, 128, true>(map_q, map_g, nq, static_cast<int>(width), kp, epi, st);
+        }
         if (rc) return rc;
         c0 += width;
         topk_compact_kernel<<<nq, kCompactThreads, 0, st>>>(w, K, c0 >= num_g ? 1 : 0, keys, status);

@@ -45,10 +45,10 @@ constexpr int kEpiBytes = 4 * 32 * kEpiPad * 4;       // transpose staging of th
 // kChunkKb > 0: the accumulator is drained every kChunkKb k-blocks and summed in registers with
 //        round-to-nearest fp32 adds (the tensor core truncates on accumulate; short chains keep that
 //        bias below the fp32 rounding of the result).  Needs 8 epilogue warps (64 sums per thread).
-// (CTA pairs -- cta_group::2, 256-row tiles, each CTA loading half of the B tile -- were built and measured in rounds 1
-// and 2, with a relay warp and with direct cross-CTA barrier signalling: 22.7 / 21.9 ms per pass against 23.0 ms for one
-// CTA per tile, nothing in the fp16 mode (profiles/r2/first_call_variants.log).  The GEMM is bound by the board's power
-// limit, not by operand ingest; the pair flavours were removed.)
+// kPair  CTA pairs (cta_group::2): a 256 x BN tile per pair of SMs, each CTA loading its 128 rows of A and HALF of the B
+//        tile.  Nothing for the bf16 modes (three / six products per loaded byte: MMA- or power-bound), but the modes
+//        with FEWER products per byte -- fp16 + e4m3 graph layers, fp16 x 2 distances -- are bound by the L2 -> SM
+//        operand fill (~46 B/clk/SM) with one CTA per tile, which the halved B traffic removes.
 template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0, bool kPair = false> struct Config {
     // epilogue flavour: kDirect = registers -> 16-byte global accesses, 8 warps (two per TMEM lane
     // quarter, half the columns each), no smem; otherwise 4 warps and a padded smem transpose so
@@ -237,9 +237,13 @@ constexpr uint32_t make_idesc(int m, int n, bool f16 = false) {
 }
 
 // ---- epilogue functors: value for output element (row, col) given the accumulator -------------
-struct EpiDistance {            // distance.py:59-73 / :76-89
+// kF16x2: AGRL_SPLIT_FP16X2 operands -- fp16 planes h = fp16(x s), l = fp16((x s - h) 2^11) with a power-of-two scale s
+// per row: the correction accumulator (h.l + l.h) enters with 2^-11, the result is un-scaled by 2^-kq 2^-kg (exact).
+template <bool kF16x2>
+struct EpiDistanceT {           // distance.py:59-73 / :76-89
     static constexpr const char *kName = "gemm_distance";
-    static constexpr bool kF16 = false;
+    static constexpr bool kF16 = kF16x2;
+    static constexpr float kCorrScale = kF16x2 ? 0.00048828125f : 1.0f;
     static constexpr bool kDirect = false;      // rows of arbitrary alignment: coalesce through smem
     static constexpr int kChunkKb = 4;          // drain the accumulator every 256 k (fp32-accurate sums)
     static constexpr bool kRowwise = false;
@@ -248,12 +252,15 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
     float *out;
     int64_t ld;
     int metric;
-    struct Col { float gn; };
+    const float *qu, *gu;       // kF16x2: 1 / s per row of either operand
+    struct Col { float gn, gu; };
     __device__ __forceinline__ Col col_state(int col) const {
-        Col c; c.gn = (metric == AGRL_METRIC_EUCLIDEAN) ? __ldg(gn + col) : 0.f; return c;
+        Col c; c.gn = (metric == AGRL_METRIC_EUCLIDEAN) ? __ldg(gn + col) : 0.f;
+        c.gu = kF16x2 ? __ldg(gu + col) : 1.0f; return c;
     }
     __device__ __forceinline__ void store(int row, int col, float acc, const Col &c) const {
         float v;
+        if (kF16x2) acc = acc * __ldg(qu + row) * c.gu;
         if (metric == AGRL_METRIC_EUCLIDEAN) v = fmaf(-2.0f, acc, __fadd_rn(__ldg(qn + row), c.gn));
         else v = 1.0f - acc;
         out[static_cast<size_t>(row) * ld + col] = v;
@@ -267,9 +274,11 @@ struct EpiDistance {            // distance.py:59-73 / :76-89
 // launches -- to the row's candidate list.  Launches cover growing column ranges; topk_compact_kernel (distance.cu) cuts
 // each list back to its K smallest keys and tightens the threshold in between, so after the first few thousand columns
 // only ~K ln(growth) candidates per row and launch pass the filter.
-struct EpiTopK {
+template <bool kF16x2>
+struct EpiTopKT {
     static constexpr const char *kName = "gemm_distance_topk";
-    static constexpr bool kF16 = false;
+    static constexpr bool kF16 = kF16x2;
+    static constexpr float kCorrScale = kF16x2 ? 0.00048828125f : 1.0f;
     static constexpr bool kDirect = false;
     static constexpr int kChunkKb = 4;
     static constexpr bool kRowwise = true;
@@ -281,17 +290,20 @@ struct EpiTopK {
     unsigned long long *cand;           // [M][cap]
     int cap;
     uint32_t idx_base;                  // global gallery index of this launch's column 0
+    const float *qu, *gu;               // kF16x2: 1 / s per row of either operand (gu offset like gn)
     __device__ __forceinline__ void consume(int row, int col0, int n_cols, const float (&sum)[64]) const {
         const unsigned long long t = tau[row];
         const float q = (metric == AGRL_METRIC_EUCLIDEAN) ? __ldg(qn + row) : 0.f;
+        const float uq = kF16x2 ? __ldg(qu + row) : 1.0f;
         unsigned long long *list = cand + static_cast<size_t>(row) * cap;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
             const int col = col0 + j;
             if (col < n_cols) {
                 float v;
-                if (metric == AGRL_METRIC_EUCLIDEAN) v = fmaf(-2.0f, sum[j], __fadd_rn(q, __ldg(gn + col)));
-                else v = 1.0f - sum[j];
+                const float acc = kF16x2 ? sum[j] * uq * __ldg(gu + col) : sum[j];      // the expression EpiDistanceT::store uses
+                if (metric == AGRL_METRIC_EUCLIDEAN) v = fmaf(-2.0f, acc, __fadd_rn(q, __ldg(gn + col)));
+                else v = 1.0f - acc;
                 const unsigned long long key = rank_key(v, idx_base + static_cast<uint32_t>(col));
                 if (key < t) {
                     const unsigned int slot = atomicAdd(cnt + row, 1u);
@@ -301,6 +313,10 @@ struct EpiTopK {
         }
     }
 };
+using EpiDistance = EpiDistanceT<false>;
+using EpiDistanceF16x2 = EpiDistanceT<true>;
+using EpiTopK = EpiTopKT<false>;
+using EpiTopKF16x2 = EpiTopKT<true>;
 
 // kScaled: single-plane fp16 operands (AGRL_SPLIT_FP16X1).  Both operands were multiplied by powers of two to sit
 // in the middle of the fp16 range (per tracklet for Y, per layer for W); the epilogue undoes that exactly.
@@ -310,6 +326,7 @@ template <bool kScaled, bool kFp8_ = false>
 struct EpiGraphLayerT {         // vmgn.py:169-172: gamma * LeakyReLU(BN(acc)) + (1-gamma) * x
     static constexpr const char *kName = "gemm_graph_layer";
     static constexpr bool kF16 = kScaled;
+    static constexpr float kCorrScale = 1.0f;
     static constexpr bool kFp8 = kFp8_;
     static constexpr bool kDirect = true;       // C % 4 == 0 and 16-byte aligned rows: vector accesses
     static constexpr int kChunkKb = 0;          // one accumulation over all of K
@@ -381,6 +398,7 @@ template <bool kScaled, bool kFp8_ = false>
 struct EpiPlainT {
     static constexpr const char *kName = "gemm_graph_layer";
     static constexpr bool kF16 = kScaled;
+    static constexpr float kCorrScale = 1.0f;
     static constexpr bool kFp8 = kFp8_;
     static constexpr bool kDirect = true;
     static constexpr int kChunkKb = 0;
@@ -659,8 +677,9 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float part = kSplit ? __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]))
-                                                      : __uint_as_float(r[j]);
+                            const float part = !kSplit ? __uint_as_float(r[j])
+                                               : (Epi::kCorrScale == 1.0f ? __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]))
+                                                                          : fmaf(__uint_as_float(rc[j]), Epi::kCorrScale, __uint_as_float(r[j])));
                             sum[c + j] = __fadd_rn(sum[c + j], part);
                         }
                     }
@@ -706,7 +725,8 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            buf[lane * kEpiPad + j] = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]));
+                            buf[lane * kEpiPad + j] = Epi::kCorrScale == 1.0f ? __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]))
+                                                                              : fmaf(__uint_as_float(rc[j]), Epi::kCorrScale, __uint_as_float(r[j]));
                     } else {
                         tmem_ld_wait();
 #pragma unroll
@@ -814,6 +834,8 @@ struct SplitArgs {
     int normalize;                     // 1: split x / max(||x||, 1e-12) instead of x (cosine_distance)
     int fp16 = 0;                      // 1: ONE fp16 plane of x * (*prescale) instead of bf16 planes
     const float *prescale = nullptr;   // device, a power of two (fp16 mode)
+    int fp16x2 = 0;                    // 1: AGRL_SPLIT_FP16X2 -- planes fp16(x s), fp16((x s - fp16(x s)) 2^11), s = 2^k per row, 1 / s -> unscale[row]
+    float *unscale = nullptr;
     int fp8 = 0;                       // with fp16: a second plane of E4M3 pairs for the B operand of the fp16 + e4m3 GEMM --
                                        // per 64-element k-block 64 bytes e4m3(x s 2^-6), then 64 bytes e4m3((x s - fp16(x s)) 2^6)
 };

@@ -19,37 +19,52 @@ constexpr int kSplitThreads = 256;
 // one CTA per row; two passes over the row (the second one hits L1/L2)
 __global__ void __launch_bounds__(kSplitThreads)
 split_planes_kernel(SplitArgs a) {
-    __shared__ float s_part[kSplitThreads / 32];
-    __shared__ float s_inv;
+    __shared__ float s_part[kSplitThreads / 32], s_maxp[kSplitThreads / 32];
+    __shared__ float s_inv, s_ps;
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x;
     const float *src = a.src + row * a.ld;
     const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (a.dim % 4 == 0);
 
-    float inv = 1.0f;
-    if (a.sumsq != nullptr || a.normalize) {
-        float s = 0.f;
+    float inv = 1.0f, ps = 1.0f;
+    if (a.sumsq != nullptr || a.normalize || a.fp16x2) {
+        float s = 0.f, m = 0.f;
         if (vec) {
             const float4 *s4 = reinterpret_cast<const float4 *>(src);
             for (int i = tid; i < a.dim / 4; i += kSplitThreads) {
                 const float4 v = __ldg(s4 + i);
                 s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+                m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
             }
         } else {
-            for (int i = tid; i < a.dim; i += kSplitThreads) { const float v = src[i]; s = fmaf(v, v, s); }
+            for (int i = tid; i < a.dim; i += kSplitThreads) { const float v = src[i]; s = fmaf(v, v, s); m = fmaxf(m, fabsf(v)); }
         }
         s = warp_sum(s);
-        if ((tid & 31) == 0) s_part[tid >> 5] = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((tid & 31) == 0) { s_part[tid >> 5] = s; s_maxp[tid >> 5] = m; }
         __syncthreads();
         if (tid == 0) {
-            float t = 0.f;
+            float t = 0.f, mx = 0.f;
 #pragma unroll
-            for (int w = 0; w < kSplitThreads / 32; ++w) t += s_part[w];
+            for (int w = 0; w < kSplitThreads / 32; ++w) { t += s_part[w]; mx = fmaxf(mx, s_maxp[w]); }
             if (a.sumsq) a.sumsq[row] = t;
-            s_inv = fmaxf(sqrtf(t), 1e-12f);       // F.normalize: x / max(||x||_2, eps)
+            const float nrm = fmaxf(sqrtf(t), 1e-12f);       // F.normalize: x / max(||x||_2, eps)
+            s_inv = nrm;
+            if (a.fp16x2) {
+                // power of two that puts the row's largest (normalised) magnitude in [2^7, 2^8); rows that are all zero,
+                // or hold Inf / NaN (fmaxf drops NaNs, the sum of squares keeps them), stay unscaled
+                if (a.normalize) mx = __fdiv_rn(mx, nrm);
+                int e = 7;
+                if (mx > 0.f && mx < 3.0e38f && t == t) e = ilogbf(mx);
+                e = max(-110, min(120, e));
+                s_ps = ldexpf(1.0f, 7 - e);
+                a.unscale[row] = ldexpf(1.0f, e - 7);
+            }
         }
         __syncthreads();
         inv = s_inv;
+        if (a.fp16x2) ps = s_ps;
     }
 
     const size_t plane_stride = static_cast<size_t>(a.rows) * a.k_pad;
@@ -59,6 +74,16 @@ split_planes_kernel(SplitArgs a) {
         float x0 = (i < a.dim) ? src[i] : 0.f;
         float x1 = (i + 1 < a.dim) ? src[i + 1] : 0.f;
         if (a.normalize) { x0 = __fdiv_rn(x0, inv); x1 = __fdiv_rn(x1, inv); }
+        if (a.fp16x2) {
+            x0 *= ps; x1 *= ps;                                   // exact
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            // (x - h is exact in fp32; 2^11 lifts the residual into fp16's normal range)
+            const __half2 l = __floats2half2_rn(__fsub_rn(x0, hf.x) * 2048.0f, __fsub_rn(x1, hf.y) * 2048.0f);
+            *reinterpret_cast<__half2 *>(dst + i) = h;
+            *reinterpret_cast<__half2 *>(dst + plane_stride + i) = l;
+            continue;
+        }
         if (a.fp16) {
             const float ps = __ldg(a.prescale);
             const __half2 h = __floats2half2_rn(x0 * ps, x1 * ps);

@@ -25,7 +25,7 @@ def _workspace(dev, nbytes):
     return ws
 
 
-def compute_distance_matrix(input1, input2, metric='euclidean', split=_lib.SPLIT_BF16X3):
+def compute_distance_matrix(input1, input2, metric='euclidean', split=_lib.SPLIT_FP16X2):
     """A wrapper function for computing distance matrix (distance.py:11).
 
     Args:
@@ -83,7 +83,7 @@ class PreparedOperand(object):
     Retrieval against a fixed gallery prepares the gallery once and reuses it for every query batch
     (``agrl_distance_prepare_operand_dev`` / ``agrl_distance_prepared_dev``)."""
 
-    def __init__(self, x, metric='euclidean', split=_lib.SPLIT_BF16X3):
+    def __init__(self, x, metric='euclidean', split=_lib.SPLIT_FP16X2):
         assert isinstance(x, torch.Tensor) and x.dim() == 2 and x.is_cuda
         if metric not in _METRICS:
             raise ValueError('Unknown distance metric: {}. '
@@ -111,12 +111,17 @@ class PreparedOperand(object):
         v.rows, v.dim, v.metric, v.split, v.device = n, self.dim, self.metric, self.split, self.device
         nbytes = lib.agrl_distance_operand_bytes(n, self.dim, self.split)
         v.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        P = _lib.planes_of_distance_split(self.split)
         plane_b = self.rows * k_pad * 2
-        src = self.buf[:self.split * plane_b].view(self.split, self.rows, k_pad * 2)
-        v.buf[:self.split * n * k_pad * 2].view(self.split, n, k_pad * 2).copy_(src[:, r0:r1])
-        off_src = (self.split * plane_b + 255) // 256 * 256
-        off_dst = (self.split * n * k_pad * 2 + 255) // 256 * 256
-        v.buf[off_dst:off_dst + 4 * n].copy_(self.buf[off_src + 4 * r0:off_src + 4 * r1])
+        src = self.buf[:P * plane_b].view(P, self.rows, k_pad * 2)
+        v.buf[:P * n * k_pad * 2].view(P, n, k_pad * 2).copy_(src[:, r0:r1])
+        # after the planes: squared norms, then the per-row 1 / scale of the fp16 x 2 split (256-byte aligned arrays)
+        off_src = (P * plane_b + 255) // 256 * 256
+        off_dst = (P * n * k_pad * 2 + 255) // 256 * 256
+        for _ in range(2):
+            v.buf[off_dst:off_dst + 4 * n].copy_(self.buf[off_src + 4 * r0:off_src + 4 * r1])
+            off_src = (off_src + 4 * self.rows + 255) // 256 * 256
+            off_dst = (off_dst + 4 * n + 255) // 256 * 256
         return v
 
 

@@ -44,7 +44,7 @@ def or_across_ranks(status, group=None):
 class CudaOps(object):
     """Per-rank compute on the rank's current CUDA device (libagrl_b200)."""
 
-    def __init__(self, split=_lib.SPLIT_BF16X3):
+    def __init__(self, split=_lib.SPLIT_FP16X2):
         self.lib = _lib.require_device()
         self.split = split
         self._ws = {}

@@ -66,8 +66,8 @@ extern "C" {
 #define AGRL_METRIC_COSINE    1   /* 1 - cos, rows L2-normalised with eps 1e-12 (distance.py:76-89) */
 
 /* ---- operand split of the tensor-core GEMMs ------------------------------------------------- */
-#define AGRL_SPLIT_BF16X3     3   /* fp32 = 3 bf16 planes, 6 products: fp32-accurate (default for
-                                     the distance matrix)                                          */
+#define AGRL_SPLIT_BF16X3     3   /* fp32 = 3 bf16 planes, 6 products: all 24 significand bits (the distance
+                                     matrix's default in rounds 1-2a; re-ranking; selectable)      */
 #define AGRL_SPLIT_BF16X2     2   /* 2 planes, 3 products: ~2^-17 relative per product (default for
                                      the graph layers, whose output enters with gamma = 0.1)       */
 
@@ -83,6 +83,14 @@ extern "C" {
                                      vs 8 + 8) at two thirds of its tensor-core time (kind::f8f6f4 runs at twice the fp16 rate).
                                      Measured head error ~1e-6 (bar 1e-4), like BF16X2.  Needs the tensor-core graph kernel
                                      (<= 64 nodes per tracklet, C % 128 == 0); AGRL_E_UNSUPPORTED otherwise.                      */
+
+#define AGRL_SPLIT_FP16X2      5   /* distance matrix only (its default): fp32 = fp16(x s) + 2^-11 fp16((x s - fp16(x s)) 2^11), s a power
+                                     of two PER ROW that puts the row's largest element in [2^7, 2^8): 22 operand bits in two planes,
+                                     THREE products (h.h in one accumulator, h.l + l.h in another, joined as main + 2^-11 corr)
+                                     instead of the six of AGRL_SPLIT_BF16X3 -- the "3xTF32" scheme with fp16's 11-bit significand.
+                                     Operand error <= 2^-22 per element (4.5e-9 of |q||g| on a 4096-long dot product, below
+                                     fp32 accumulation noise); elements more than 2^22 below their row's maximum lose
+                                     relative (never absolute) precision.                                                      */
 
 AGRL_API int         agrl_abi_version(void);
 AGRL_API const char *agrl_status_string(int code);
@@ -213,8 +221,8 @@ AGRL_API int agrl_rank_mars_host(const float *distmat_host,
  * (2) Distance matrix -- replaces compute_distance_matrix (torchreid/metrics/distance.py:11-56):
  *     euclidean_squared_distance :59-73 and cosine_distance :76-89.
  *     out[i,j] = (|q_i|^2 + |g_j|^2) - 2 q_i.g_j     or     1 - q^_i.g^_j
- *     The contraction runs on tcgen05 tensor cores with bf16 operand planes (AGRL_SPLIT_*),
- *     fp32 accumulation in TMEM; norms and the epilogue are fp32.
+ *     The contraction runs on tcgen05 tensor cores with 16-bit operand planes (`split`: AGRL_SPLIT_FP16X2,
+ *     AGRL_SPLIT_BF16X3 or AGRL_SPLIT_BF16X2), fp32 accumulation in TMEM; norms and the epilogue are fp32.
  * ============================================================================================= */
 AGRL_API size_t agrl_distance_workspace_bytes(int64_t num_q, int64_t num_g, int64_t dim, int split);
 

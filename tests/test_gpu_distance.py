@@ -1,7 +1,8 @@
 """GPU parity of the tcgen05 distance matrix (csrc/distance.cu, gemm_sm100.cuh, split.cu) through
 compute_distance_matrix: reference golden vectors, oracle (fp32 and fp64) on larger seeded inputs,
-ragged shapes, argument checks.  Tolerance (north star): 1e-4 relative; the 3-plane split is held
-to fp32-level accuracy (2e-6 of the matrix scale) on top of that."""
+ragged shapes, argument checks.  Tolerance (north star): 1e-4 relative; the fp32-accurate splits (fp16 x 2 with
+three products -- the default -- and bf16 x 3 with six) are held to fp32-level accuracy (2e-6 of the matrix scale) on
+top of that."""
 import os
 
 import numpy as np
@@ -27,15 +28,19 @@ def _err(got, ref):
     return np.abs(got - ref).max() / scale, np.linalg.norm(got - ref) / np.linalg.norm(ref)
 
 
+ACCURATE_SPLITS = [5, 3]     # _lib.SPLIT_FP16X2 (default), _lib.SPLIT_BF16X3
+
+
 @pytest.mark.parametrize('fname', golden_files('distance_'))
 @pytest.mark.parametrize('metric', ['euclidean', 'cosine'])
 @pytest.mark.parametrize('where', ['cpu', 'cuda'])
-def test_distance_golden(cdm, fname, metric, where):
+@pytest.mark.parametrize('split', ACCURATE_SPLITS)
+def test_distance_golden(cdm, fname, metric, where, split):
     g = np.load(os.path.join(GOLDEN, fname))
     a, b = torch.from_numpy(g['a']), torch.from_numpy(g['b'])
     if where == 'cuda':
         a, b = a.cuda(), b.cuda()
-    out = cdm(a, b, metric)
+    out = cdm(a, b, metric, split=split)
     assert out.shape == (a.size(0), b.size(0)) and out.dtype == torch.float32
     assert out.device.type == where
     emax, enrm = _err(out.cpu().numpy(), g[metric])
@@ -45,12 +50,13 @@ def test_distance_golden(cdm, fname, metric, where):
 @pytest.mark.parametrize('m,n,d', [(300, 1000, 2048), (129, 257, 4096), (1, 1, 1), (7, 130, 63), (128, 128, 64),
                                    (255, 383, 200), (702, 2636, 4096)])
 @pytest.mark.parametrize('metric', ['euclidean', 'cosine'])
-def test_distance_vs_oracle(cdm, m, n, d, metric):
+@pytest.mark.parametrize('split', ACCURATE_SPLITS)
+def test_distance_vs_oracle(cdm, m, n, d, metric, split):
     g = torch.Generator().manual_seed(m * 7 + n)
     a, b = torch.randn(m, d, generator=g), torch.randn(n, d, generator=g)
     ref32 = odist.distance_matrix(a, b, metric).numpy()
     ref64 = odist.distance_matrix(a, b, metric, dtype=torch.float64).numpy()
-    out = cdm(a.cuda(), b.cuda(), metric).cpu().numpy()
+    out = cdm(a.cuda(), b.cuda(), metric, split=split).cpu().numpy()
     emax, enrm = _err(out, ref32)
     assert emax < REL_TOL and enrm < REL_TOL
     # against the exact value we must be about as good as the reference's own fp32 arithmetic
@@ -84,6 +90,34 @@ def test_clustered_small_distances(cdm):
     e_ours, e_ref = np.abs(out - ref64) / norms, np.abs(ref32 - ref64) / norms
     print('clustered: ours %.3e  reference fp32 %.3e (relative to the norms)' % (e_ours.max(), e_ref.max()))
     assert e_ours.max() < 1.5e-6
+
+
+@pytest.mark.parametrize('metric', ['euclidean', 'cosine'])
+def test_fp16x2_rows_of_any_magnitude(cdm, metric):
+    """the default split scales every row by its own power of two: rows 30 orders of magnitude apart, an all-zero row, a
+    row with one dominant element and elements far below it, a NaN row (poisons only itself)"""
+    g = torch.Generator().manual_seed(11)
+    a, b = torch.randn(70, 520, generator=g), torch.randn(150, 520, generator=g)
+    a *= torch.logspace(-15, 15, 70)[:, None]
+    b *= torch.logspace(-12, 12, 150)[:, None]
+    a[3] = 0
+    b[5] = 0
+    a[7, 1:] *= 1e-9                                      # one element dominates the row
+    b[9, 17] *= 1e7
+    ref64 = odist.distance_matrix(a, b, metric, dtype=torch.float64).numpy()
+    out = cdm(a.cuda(), b.cuda(), metric).cpu().numpy()
+    if metric == 'euclidean':
+        scale = (a.double() ** 2).sum(1).numpy()[:, None] + (b.double() ** 2).sum(1).numpy()[None, :]
+        scale[scale == 0] = 1.0
+    else:
+        scale = np.ones_like(ref64)
+    assert np.isfinite(out).all()
+    assert (np.abs(out - ref64) / scale).max() < FP32_TOL
+    a[11, 4] = float('nan')
+    out2 = cdm(a.cuda(), b.cuda(), metric).cpu().numpy()
+    assert np.isnan(out2[11]).all()
+    keep = np.arange(70) != 11
+    assert np.array_equal(out2[keep], out[keep])
 
 
 def test_non_contiguous_and_strided_inputs(cdm):
