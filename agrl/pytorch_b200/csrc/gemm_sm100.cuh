@@ -439,6 +439,7 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                                                 int M, int N, int k_pad, const Epi &epi) {
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, kPair>;
     constexpr int kAccCols = Cfg::kAccCols;
+    constexpr bool kCorrPersist = kSplit && Cfg::kChunk > 0;
     extern __shared__ unsigned char smem_dyn[];
     // 128B-swizzled tiles need 1024-byte alignment
     unsigned char *smem = reinterpret_cast<unsigned char *>(
@@ -534,7 +535,8 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
         constexpr uint32_t idesc = make_idesc(Cfg::kTileM, BN, Epi::kF16);
         int stage = 0; uint32_t phase = 0;
         int cit = 0;                                               // accumulator-drain counter (chunks)
-        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int tcount = 0;                                            // tiles of this CTA so far
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
             for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++cit) {
                 const int acc = cit & 1;
                 const uint32_t acc_phase = (cit >> 1) & 1;
@@ -545,8 +547,14 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 // on every accumulate, at the ulp of the running sum; keeping the small correction
                 // products out of the big a0.b0 sum spares it 5/6 (P=3) of those truncations, and the
                 // correction sum itself is ~2^-8 smaller, so its own truncation is negligible.
-                const uint32_t d_main = tmem_base + acc * kAccCols;
-                const uint32_t d_corr = kSplit ? d_main + BN : d_main;
+                // Chunked + split (kCorrPersist): the two MAIN accumulators alternate per chunk in columns [0, 2 BN); the
+                // correction sum -- 2^-8 (bf16) / 2^-11 (fp16 x 2) of the main one, its own truncation negligible -- stays
+                // in TMEM for the whole tile, columns [2 BN, 4 BN) alternating per TILE, and is drained once: half the
+                // TMEM reads of draining both every chunk (same kernel time: the 128-wide MMAs, not the drains, pace
+                // this GEMM -- tensor pipe 62 % under ncu; a 256 x 256 pair tile with ONE accumulator and no chunked
+                // drain ran 0.31 instead of 0.39 ms at MARS size but lost a digit and a half to accumulate truncation).
+                const uint32_t d_main = kCorrPersist ? tmem_base + acc * BN : tmem_base + acc * kAccCols;
+                const uint32_t d_corr = kCorrPersist ? tmem_base + 2 * BN + (tcount & 1) * BN : (kSplit ? d_main + BN : d_main);
                 for (int kb = kb0; kb < kb_end; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);        // TMA bytes have landed
                     tc_fence_after();
@@ -587,7 +595,8 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                                 // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
                                 const bool main_acc = kSplit && i == Cfg::kNumPairs - 1;
                                 const uint32_t d = main_acc ? d_main : d_corr;
-                                const uint32_t accum = main_acc ? ((first | k) != 0 ? 1u : 0u) : ((first | i | k) != 0 ? 1u : 0u);
+                                const uint32_t accum = main_acc ? ((first | k) != 0 ? 1u : 0u)
+                                                                : (((kCorrPersist ? kb : first) | i | k) != 0 ? 1u : 0u);
                                 if (kPair) tc_mma_bf16_pair(d, da + 2 * k, db + 2 * k, idesc, accum);
                                 else tc_mma_bf16(d, da + 2 * k, db + 2 * k, idesc, accum);
                             }
@@ -615,8 +624,8 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
             if (kPair) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));
             else mbar_arrive(bar_tempty + 8 * acc);
         };
-        int cit = 0;
-        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int cit = 0, tcount = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
             int m0, n0;
             tile_origin(tile, m0, n0);
             const int row_base = m0 + quarter * 32;
@@ -666,21 +675,24 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++cit) {
                     const int acc = cit & 1;
                     const uint32_t acc_phase = (cit >> 1) & 1;
-                    const uint32_t tq = tlane + acc * kAccCols + col_half;
+                    const uint32_t tq = tlane + (kSplit ? acc * BN : acc * kAccCols) + col_half;
+                    const bool last_chunk = kb0 + chunk_kb >= num_kb;
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < BN / 2; c += 32) {
-                        uint32_t r[32], rc[32];
+                        uint32_t r[32];
                         tmem_ld_32x32(tq + c, r);
-                        if (kSplit) tmem_ld_32x32(tq + BN + c, rc);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float part = !kSplit ? __uint_as_float(r[j])
-                                               : (Epi::kCorrScale == 1.0f ? __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]))
-                                                                          : fmaf(__uint_as_float(rc[j]), Epi::kCorrScale, __uint_as_float(r[j])));
-                            sum[c + j] = __fadd_rn(sum[c + j], part);
+                        for (int j = 0; j < 32; ++j) sum[c + j] = __fadd_rn(sum[c + j], __uint_as_float(r[j]));
+                        if (kSplit && last_chunk) {                    // the tile's correction sum, once
+                            tmem_ld_32x32(tlane + 2 * BN + (tcount & 1) * BN + col_half + c, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                sum[c + j] = Epi::kCorrScale == 1.0f ? __fadd_rn(sum[c + j], __uint_as_float(r[j]))
+                                                                     : fmaf(__uint_as_float(r[j]), Epi::kCorrScale, sum[c + j]);
                         }
                     }
                     tc_fence_before();

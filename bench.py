@@ -48,6 +48,7 @@ V = 56
 BYTES_PER_TRACKLET = 2 * S * C * H * W * 4 + 56 * 56 * 4 + 2 * C * 4        # 16 806 144
 FLOPS_PER_TRACKLET = 2 * (2 * 56 * C * C + 2 * 2 * 56 * 56 * C)            # ~0.99 GFLOP
 METRIC = 'MARS-shape tracklets/s (graph head) + query×gallery eval ms at 1/2/4/8 B200'
+DIST_PRODUCTS = 3          # tensor-core products per distance (AGRL_SPLIT_FP16X2, the default of compute_distance_matrix)
 WORKLOAD = ('MARS-shaped test pass: graph head over 11310 tracklets (8 frames, 2048x16x8 maps), 1980x9330 %s distance on '
             'the 4096-d features, MARS-metric CMC/mAP')
 
@@ -401,7 +402,7 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'tracklets/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'fp32 (head GEMMs: fp16 + e4m3 correction planes, distance: bf16x3 planes, on tcgen05; fp32 accumulate)',
+        'vs_baseline': None, 'dtype': 'fp32 (head GEMMs: fp16 + e4m3 correction planes, distance: fp16x2 planes / 3 products, on tcgen05; fp32 accumulate)',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD % args.dist_metric,
                    'tracklets_per_step_per_gpu': J, 'pool_tracklets': pool_n,
@@ -414,7 +415,8 @@ def run_b200(args):
         'head_tracklets_per_s_per_gpu': J / (head_ms * 1e-3),
         'roofline': roof, 'kernel_table': table, 'gpu_launches': int(launches),
         'distance': {'ms': gemm_d, 'algorithmic_tflops': 2 * NQ * NG * 2 * C / (gemm_d * 1e-3) / 1e12,
-                     'tensor_pipe_frac': 6 * 2 * NQ * NG * 2 * C / (gemm_d * 1e-3) / 1e12 / pk['bf16_sustained']},
+                     'products': DIST_PRODUCTS,
+                     'tensor_pipe_frac': DIST_PRODUCTS * 2 * NQ * NG * 2 * C / (gemm_d * 1e-3) / 1e12 / pk['bf16_sustained']},
         'clocks': clocks, 'result': {'mAP': float(result[1]), 'rank1': float(result[0][0])},
     }
     if joules is not None:
@@ -493,8 +495,8 @@ def kernel_table(timeline, pk, J, lowrank_on, gemm_passes=2.0):
         'gemm_graph_layer': ('tensor', gemm_passes * 2.0 * J * (rows1 + V) * C * C),
         'graph_mix': ('hbm', J * (2 * node_b + q_b)),
         'attn': ('hbm', J * node_b),
-        'split_planes': ('hbm', (NQ + NG) * 2 * C * (4 + 6)),
-        'gemm_distance': ('tensor', 6 * 2.0 * NQ * NG * 2 * C),
+        'split_planes': ('hbm', (NQ + NG) * 2 * C * (4 + 4)),
+        'gemm_distance': ('tensor', DIST_PRODUCTS * 2.0 * NQ * NG * 2 * C),
         'rank_mars': ('hbm', NQ * NG * 4),
         'rank_mars_partial': ('hbm', NQ * NG * 4),
     }
@@ -742,8 +744,8 @@ def sweep_measure(args, cx, steps, warm):
             'ms': ms, 'queries': nq, 'gallery': ng_total, 'dim': d, 'gallery_rows_per_gpu': ng, 'distance': args.dist_metric,
             'algorithmic_tflops_per_gpu': flops / world / (ms * 1e-3) / 1e12,
             'gemm_ms_rank0': gemm_ms, 'gemm_share': gemm_ms / max(sum(t for _, (n, t) in tl.items()), 1e-9),
-            'gemm_tensor_pipe_frac': 6 * flops / world / (max(gemm_ms, 1e-9) * 1e-3) / 1e12 / pk['bf16_sustained'],
-            'limiter': 'the tcgen05 distance GEMM (6 bf16 products); largest other kernel on rank 0: %s %.2f ms' % (
+            'gemm_tensor_pipe_frac': DIST_PRODUCTS * flops / world / (max(gemm_ms, 1e-9) * 1e-3) / 1e12 / pk['bf16_sustained'],
+            'limiter': 'the tcgen05 distance GEMM (fp16 x 2 operands, 3 products); largest other kernel on rank 0: %s %.2f ms' % (
                 other[0] if other else ('-', 0.0)),
             'kernels_rank0': kern, 'mAP': float(res[1]), 'rank1': float(res[0][0])}
 
@@ -759,7 +761,7 @@ def run_sweep(args):
             'metric': 'scaled retrieval sweep: %d queries x %d gallery eval ms' % (r['queries'], r['gallery']), 'value': r['ms'],
             'unit': 'ms', 'n_gpus': cx.world, 'steps': args.steps, 'warmup': max(1, args.warmup), 'ms_per_step': r['ms'],
             'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None, 'data': 'synthetic',
-            'dtype': 'fp32 (bf16x3 split operands on tcgen05, fp32 accumulate)',
+            'dtype': 'fp32 (fp16x2 split operands, 3 products, on tcgen05; fp32 accumulate)',
             'config': {'workload': r['what'], 'queries': r['queries'], 'gallery': r['gallery'], 'dim': r['dim'],
                        'gallery_rows_per_gpu': r['gallery_rows_per_gpu'], 'metric': r['distance']},
             'algorithmic_tflops_per_gpu': r['algorithmic_tflops_per_gpu'], 'gemm_ms_rank0': r['gemm_ms_rank0'],
