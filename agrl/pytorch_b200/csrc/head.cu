@@ -568,7 +568,7 @@ __device__ long long *g_timeline = nullptr;
 #endif
 
 __global__ void __launch_bounds__(kTcThreads, 2)
-graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_pf, GraphArgs a) {
+graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
     AGRL_TL_DECL;
     extern __shared__ __align__(16) unsigned char tc_smem_dyn[];
     unsigned char *smem = tc_smem_dyn + ((1024u - (gemm::smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
@@ -617,23 +617,21 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // its three operand buffers); the message-passing phase, bound by its accumulator drain, uses stages 0 and 1.
     const int raw_stage = V * 256;
     auto stage_off = [&](int st) { return st < 2 ? kTcRawOff + st * raw_stage : kTcRingOff + 6 * kTcPlane; };
-    auto load_raw = [&](int piece, int st) {                           // loader: tile of channels [64 piece, +64) -> stage st
+    // (L2 eviction hints on the tile copies -- keep the Gram phase's tiles, stream the message passing's -- cut the layer-2
+    // launch's DRAM reads from 0.82 to 0.72 GB and changed neither its time nor the head's: A/B on one box, tools/build_alt.sh.)
+    auto load_raw = [&](int piece, int st) {          // loader: tile of channels [64 piece, +64) -> stage st
         if (lane == 0) {
             const uint32_t full = b_rfull + 8 * st;
             gemm::mbar_arrive_expect_tx(full, static_cast<uint32_t>(raw_stage));
             gemm::tma_load_3d(gemm::smem_u32(smem) + stage_off(st), &map_x, full, piece * 64, 0, b);
         }
     };
-    // loader: DRAM -> L2 ahead of the tile copies, one request per FOUR tiles (1 KiB of every node row).  (Measured: the
-    // same kernel time as 112 per-line prefetches per tile, i.e. the size of the DRAM pieces is not what limits the phase.)
-    auto prefetch_l2 = [&](int piece, int n_pieces) {
-        if (lane == 0 && piece >= 0 && (piece & 3) == 0 && piece < n_pieces)
-            asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                         ::"l"(reinterpret_cast<uint64_t>(&map_pf)), "r"(piece * 64), "r"(0), "r"(b) : "memory");
-    };
+    // (No L2 prefetch ahead of the tile copies: per-line prefetches and one tensor-map prefetch per four tiles were both
+    // measured -- 0.341 instead of 0.313 ms for the layer-2 launch and 1.05 instead of 0.82 GB of DRAM reads, the prefetched
+    // lines being evicted again before their tile copy arrives.)
     // uses of stage st by the Gram phase (tiles st, st + 3, ...): the message passing continues each barrier's phase count
     auto gram_uses_of = [&](int st) { return a.learn_graph ? (n_gblocks + 2 - st) / 3 : 0; };
-    if (loader && lane == 0) { gemm::prefetch_tensormap(&map_x); gemm::prefetch_tensormap(&map_pf); }
+    if (loader && lane == 0) gemm::prefetch_tensormap(&map_x);
 
     if (a.learn_graph) {
         // ================= Gram =================
@@ -711,11 +709,7 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 AGRL_TL(160 + kb);
             }
         } else if (loader) {
-            prefetch_l2(0, n_gblocks);
-            prefetch_l2(4, n_gblocks);
             for (int kb = 0; kb < n_gblocks; ++kb) {
-                prefetch_l2(kb + 8, n_gblocks);
-                if (!a.lowrank) prefetch_l2(kb + 8 - n_gblocks, 8);       // ... and the first tiles of the message passing
                 if (kb >= 3) wait_bar(b_rempty + 8 * (kb % 3), kb / 3 - 1);
                 load_raw(kb, kb % 3);
             }
@@ -904,9 +898,7 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // tile hh as soon as every converter warp has released the stage of tile hh - 2 (tiles 0 and 1 were requested at the end
         // of the Gram phase when there is one)
         const int n_halves = 2 * n_blocks;
-        if (!a.learn_graph) { prefetch_l2(0, n_halves); prefetch_l2(4, n_halves); }
         for (int hh = a.learn_graph ? 2 : 0; hh < n_halves; ++hh) {
-            prefetch_l2(hh + 8, n_halves);
             const int use = gram_uses_of(hh & 1) + (hh >> 1);
             if (use > 0) wait_bar(b_rempty + 8 * (hh & 1), use - 1);
             load_raw(hh, hh & 1);
@@ -1227,11 +1219,10 @@ static int launch_graph(const GraphArgs &ga, int64_t batch, cudaStream_t st) {
     // + two stages of raw node tiles: 109 KiB at V = 56, two CTAs per SM
     const int smem = kTcSmem + 2 * ga.V * 256;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(graph_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem + 2 * kMaxNodes * 256));
-    CUtensorMap map_x, map_pf;
+    CUtensorMap map_x;
     int rc = gemm::make_rows_tensor_map_f32(&map_x, ga.x, batch, ga.V, ga.C, 64);
-    if (rc == AGRL_OK) rc = gemm::make_rows_tensor_map_f32(&map_pf, ga.x, batch, ga.V, ga.C, 256);
     if (rc) return rc;
-    graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, smem, st>>>(map_x, map_pf, ga);
+    graph_kernel_tc<<<static_cast<unsigned>(batch), kTcThreads, smem, st>>>(map_x, ga);
     AGRL_LAUNCH_CHECK(st, "graph");
     return AGRL_OK;
 }

@@ -1,7 +1,8 @@
 """Head-pipeline variants on one resident input pool (one process, options switched at run time).
 usage: python tools/head_variants.py POOL "k=v,k=v" ...   (keys: tma stages hint split lr pair nhwc call gb)
 `gb` = number of graph layers of the model (0: pooling + attention only -> the pooling kernels run practically alone).
-`call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets."""
+`call` = tracklets per agrl_head_forward_dev call (default POOL).  Prints head ms per 11310 tracklets.
+HV_LIB=path: load that build of the library (tools/build_alt.sh) -- A/B comparisons on ONE box, boxes differ by 3 %."""
 import json
 import os
 import sys
@@ -11,6 +12,8 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 from agrl.pytorch_b200 import _lib
+if os.environ.get('HV_LIB'):                      # diagnostic A/B build (tools/build_alt.sh) instead of the product library
+    _lib.LIB_PATH = os.path.abspath(os.environ['HV_LIB'])
 
 KEYS = {'tma': 'pool_tma', 'stages': 'pool_stages', 'hint': 'pool_l2_hint', 'lr': 'head_lowrank', 'pair': 'gemm_pair'}      # module attributes
 DEFAULTS = {'tma': 1, 'stages': 0, 'hint': 1, 'lr': 1, 'pair': 1}
