@@ -552,7 +552,9 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 // in TMEM for the whole tile, columns [2 BN, 4 BN) alternating per TILE, and is drained once: half the
                 // TMEM reads of draining both every chunk (same kernel time: the 128-wide MMAs, not the drains, pace
                 // this GEMM -- tensor pipe 62 % under ncu; a 256 x 256 pair tile with ONE accumulator and no chunked
-                // drain ran 0.31 instead of 0.39 ms at MARS size but lost a digit and a half to accumulate truncation).
+                // drain ran 0.31 instead of 0.39 ms at MARS size but lost a digit and a half to accumulate truncation;
+                // issuing the products as corr, main, corr per k-step -- consecutive MMAs on different accumulators --
+                // changed nothing either).
                 const uint32_t d_main = kCorrPersist ? tmem_base + acc * BN : tmem_base + acc * kAccCols;
                 const uint32_t d_corr = kCorrPersist ? tmem_base + 2 * BN + (tcount & 1) * BN : (kSplit ? d_main + BN : d_main);
                 for (int kb = kb0; kb < kb_end; ++kb) {
