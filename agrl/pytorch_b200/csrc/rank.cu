@@ -694,37 +694,67 @@ struct MarsMergeArgs {
 __global__ void __launch_bounds__(kRankThreads)
 rank_mars_merge_kernel(MarsMergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
-    uint8_t  *cls = reinterpret_cast<uint8_t *>(smem_raw + static_cast<size_t>(a.n2) * 8);
     const int q = blockIdx.x, tid = threadIdx.x, K = a.max_rank;
+    const int Kp = (K + 15) & ~15;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);                                  // n2
+    uint64_t *okeys = keys + a.n2;                                                            // Kp: the merged head
+    uint8_t  *cls = reinterpret_cast<uint8_t *>(smem_raw + static_cast<size_t>(a.n2 + Kp) * 8);   // n2
+    uint8_t  *ocls = cls + a.n2;                                                              // Kp
     const int total = a.parts * K;
+    int unsorted = 0;
     for (int i = tid; i < a.n2; i += kRankThreads) {
         if (i < total) {
             const size_t src = (static_cast<size_t>(i / K) * a.num_q + q) * K + (i % K);
             keys[i] = a.keys[src];
             cls[i] = a.cls[src];
+            if ((i % K) != 0 && a.keys[src - 1] > keys[i]) unsorted = 1;
         } else { keys[i] = kKeyMax; cls[i] = 0; }
     }
-    __syncthreads();
-    // bitonic sort of the keys carrying the class byte
-    for (int k = 2; k <= a.n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (a.n2 >> 1); t += kRankThreads) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi = lo | j;
-                const uint64_t x = keys[lo], y = keys[hi];
-                if ((x > y) == ((lo & k) == 0)) {
-                    keys[lo] = y; keys[hi] = x;
-                    const uint8_t c = cls[lo]; cls[lo] = cls[hi]; cls[hi] = c;
-                }
+    for (int i = tid; i < Kp; i += kRankThreads) { okeys[i] = kKeyMax; ocls[i] = 0; }
+    unsorted = __syncthreads_or(unsorted);
+    const uint64_t *hk = okeys;
+    const uint8_t *hc = ocls;
+    if (!unsorted) {
+        // every shard's list is ascending (what _partial / agrl_distance_topk_dev emit) and keys are unique: the merged
+        // position of a key is its position in its own list plus, for every other list, the number of smaller keys there
+        // (a binary search) -- one pass instead of the 45 barrier-separated steps of a 512-key bitonic sort
+        for (int i = tid; i < total; i += kRankThreads) {
+            const uint64_t key = keys[i];
+            if (key == kKeyMax) continue;
+            const int p = i / K;
+            int rank = i - p * K;
+            for (int o = 0; o < a.parts && rank < K; ++o) {
+                if (o == p) continue;
+                const uint64_t *lst = keys + o * K;
+                int lo = 0, hi = K;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] < key) lo = mid + 1; else hi = mid; }
+                rank += lo;
             }
-            __syncthreads();
+            if (rank < K) { okeys[rank] = key; ocls[rank] = cls[i]; }
         }
+        __syncthreads();
+    } else {
+        // lists in arbitrary order: bitonic sort of the keys carrying the class byte
+        for (int k = 2; k <= a.n2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (a.n2 >> 1); t += kRankThreads) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int hi = lo | j;
+                    const uint64_t x = keys[lo], y = keys[hi];
+                    if ((x > y) == ((lo & k) == 0)) {
+                        keys[lo] = y; keys[hi] = x;
+                        const uint8_t c = cls[lo]; cls[lo] = cls[hi]; cls[hi] = c;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        hk = keys; hc = cls;
     }
     if (tid != 0) return;
     int valid = 0;
-    while (valid < K && keys[valid] != kKeyMax) ++valid;
-    mars_compute_ap(cls, valid, a.ngood[q], &a.ap[q], &a.first_pos[q], a.status);
+    while (valid < K && hk[valid] != kKeyMax) ++valid;
+    mars_compute_ap(hc, valid, a.ngood[q], &a.ap[q], &a.first_pos[q], a.status);
 }
 
 // numpy's pairwise float64 summation (what np.mean runs on the ap vector, rank.py:176):
@@ -1075,7 +1105,7 @@ extern "C" int agrl_rank_mars_merge_dev(const uint64_t *keys, const uint8_t *cls
     m.ap = all_ap ? all_ap : w.ap_f64;
     m.first_pos = w.first;
     m.status = status;
-    const size_t smem = static_cast<size_t>(n2) * 9;
+    const size_t smem = (static_cast<size_t>(n2) + ((max_rank + 15) & ~static_cast<size_t>(15))) * 9;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     rank_mars_merge_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(m);

@@ -155,6 +155,10 @@ def test_sharded_partial_and_merge_kernels(shape, seed, kind, parts):
     cmc, mAP = ops.merge(torch.stack(keys), torch.stack(cls), ngood, K, st)
     assert np.array_equal(_bits64(cmc), _bits64(ref_cmc))
     assert _bits64(mAP) == _bits64(ref_map)
+    # lists that are NOT ascending (another producer): the merge notices and sorts instead of rank-merging
+    perm = torch.randperm(K, generator=torch.Generator().manual_seed(seed)).to(dev)
+    cmc2, mAP2 = ops.merge(torch.stack(keys)[:, :, perm].contiguous(), torch.stack(cls)[:, :, perm].contiguous(), ngood, K, st)
+    assert np.array_equal(_bits64(cmc2), _bits64(ref_cmc)) and _bits64(mAP2) == _bits64(ref_map)
 
 
 @pytest.mark.parametrize('shape,seed,kind,parts', [('dukev', 31, 'randn', 3), ((100, 2049, 40, 4), 32, 'ties', 2),
