@@ -125,16 +125,18 @@ def test_sharded_evaluator_fused_equals_unfused_and_the_oracle(metric):
     assert np.array_equal(a[0], rcmc) and a[1] == rmap
 
 
-def test_fused_topk_with_the_two_plane_split():
-    """AGRL_SPLIT_BF16X2 operands (3 products): the fused route and the matrix route still agree key for key"""
-    from agrl.pytorch_b200 import _lib, sharded
+@pytest.mark.parametrize('split,nq', [(2, 150), (3, 150), (3, 100), (5, 100), (5, 300)])
+def test_fused_topk_with_every_operand_split(split, nq):
+    """bf16 x 2 / bf16 x 3 / fp16 x 2 operands, one CTA per tile (nq <= 128) and CTA pairs: the fused route and the matrix
+    route agree key for key"""
+    from agrl.pytorch_b200 import sharded
     from agrl.pytorch_b200.metrics.distance import PreparedOperand, distance_prepared
     g = torch.Generator(device='cuda').manual_seed(77)
-    qf = torch.randn(150, 320, generator=g, device='cuda')
+    qf = torch.randn(nq, 320, generator=g, device='cuda')
     gf = torch.randn(7000, 320, generator=g, device='cuda')
-    ops = sharded.CudaOps(split=_lib.SPLIT_BF16X2)
-    qop, gop = PreparedOperand(qf, 'euclidean', _lib.SPLIT_BF16X2), PreparedOperand(gf, 'euclidean', _lib.SPLIT_BF16X2)
-    qp, qc, gp, gc = _labels(150, 7000, seed=78)
+    ops = sharded.CudaOps(split=split)
+    qop, gop = PreparedOperand(qf, 'euclidean', split), PreparedOperand(gf, 'euclidean', split)
+    qp, qc, gp, gc = _labels(nq, 7000, seed=78)
     keys, cls, ngood, st = ops.topk_fused(qop, gop, qp, gp, qc, gc, 50, 0, allow_fallback=False)
     rkeys, rcls, rngood, _ = ops.partial(distance_prepared(qop, gop), qp, gp, qc, gc, 50, 0)
     assert int(st.cpu()) == 0
