@@ -1042,7 +1042,7 @@ struct MixArgs {
 // of eight nodes loaded ahead of their use, so that the row loop is not bound by the latency of one load per 36 FMAs.
 // grid (C / 512, tracklets).  (Packed fma.rn.f32x2 with the weights duplicated in shared memory was measured: 4.67 vs
 // 4.40 ms per pass -- FFMA2 issues at half rate on sm_100, the extra LDS traffic is pure cost.)
-constexpr int kMixRows = 8;
+constexpr int kMixRows = 8;                             // (4: same time, 14: 4.6 instead of 4.0 ms per pass, A/B on one box)
 template <int kMixLd>                                  // row length of G.T in shared memory / registers: 4S padded with zeros
 __global__ void __launch_bounds__(kHeadThreads, 2)
 graph_mix_kernel(MixArgs a) {
