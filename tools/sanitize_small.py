@@ -52,5 +52,13 @@ lab = [torch.randint(0, 9, (n,), generator=g, device='cuda') for n in (70, 3000,
 for metric in ('euclidean', 'cosine'):
     k, c, n, st = ops.topk_fused(PreparedOperand(q2, metric), PreparedOperand(g2, metric), lab[0], lab[1], lab[2], lab[3], 50, 5)
     outs.append(k.float())
+# CTA-pair tiles (more than 128 queries) and the other operand splits, matrix and fused
+q3 = torch.randn(200, 200, generator=g, device='cuda')
+lab3 = [torch.randint(0, 9, (n,), generator=g, device='cuda') for n in (200, 3000, 200, 3000)]
+for split in (_lib.SPLIT_FP16X2, _lib.SPLIT_BF16X3, _lib.SPLIT_BF16X2):
+    outs.append(metrics.compute_distance_matrix(q3, g2, 'euclidean', split=split))
+    k, c, n, st = sharded.CudaOps(split=split).topk_fused(PreparedOperand(q3, 'euclidean', split), PreparedOperand(g2, 'euclidean', split),
+                                                          lab3[0], lab3[1], lab3[2], lab3[3], 50, 0)
+    outs.append(k.float())
 torch.cuda.synchronize()
 print('ok', float(sum(o.double().sum() for o in outs)))
