@@ -618,9 +618,9 @@ def run_configs(args, cx, model, pool_n):
     out = {}
     dev, world, rank = cx.dev, cx.world, cx.rank
 
-    def eval_config(name, nq, ng, nid, ncam, metric, rank_metric, seed, reps=5):
+    def eval_config(name, nq, ng, nid, ncam, metric, rank_metric, seed, reps=5, dim=2 * C):
         qp, qc, gp, gc = synth.eval_labels((nq, ng, nid, ncam), seed=seed)
-        qf, gf = synth.eval_features(qp, gp, 2 * C, seed=seed, clustered=True, num_ids=nid)
+        qf, gf = synth.eval_features(qp, gp, dim, seed=seed, clustered=True, num_ids=nid)
         lo, hi = sharded.shard_bounds(ng, world)[rank]
         qf, gfl = qf.to(dev), gf[lo:hi].to(dev)
         qpd, qcd = torch.as_tensor(qp).to(dev), torch.as_tensor(qc).to(dev)
@@ -633,7 +633,7 @@ def run_configs(args, cx, model, pool_n):
             fn = sharded.evaluate_mars_sharded if rank_metric == 'use_metric_mars' else sharded.evaluate_market1501_sharded
             return fn(qf, gfl, qpd, gpl, qcd, gcl, metric=metric, max_rank=50, broadcast_queries=False)
         ms, res = cx.timed(once, reps, warm=2)
-        return {'queries': nq, 'gallery': ng, 'dim': 2 * C, 'distance': metric, 'rank_metric': rank_metric[len('use_metric_'):],
+        return {'queries': nq, 'gallery': ng, 'dim': dim, 'distance': metric, 'rank_metric': rank_metric[len('use_metric_'):],
                 'eval_ms': ms, 'gallery_rows_this_rank': hi - lo, 'scaling': 'strong (gallery rows sharded, NCCL merge)' if world > 1 else 'single GPU',
                 'mAP': float(res[1]), 'rank1': float(res[0][0])}
 
@@ -670,6 +670,8 @@ def run_configs(args, cx, model, pool_n):
     out['dukev_cosine'] = eval_config('dukev', 702, 2636, 702, 8, 'cosine', 'use_metric_mars', seed=23)
     out['mars_cosine'] = eval_config('mars', NQ, NG, NIDS, NCAMS, 'cosine', 'use_metric_mars', seed=24)
     out['mars_euclidean_market1501_metric'] = eval_config('mars', NQ, NG, NIDS, NCAMS, 'euclidean', 'use_metric_market1501', seed=25)
+    # BASELINE.json quotes the MARS configuration at d = 2048 (VMGN's eval feature is 4096 wide: SURVEY 8a A8)
+    out['mars_euclidean_d2048'] = eval_config('mars', NQ, NG, NIDS, NCAMS, 'euclidean', 'use_metric_mars', seed=26, dim=C)
     if not args.no_sweep:
         torch.cuda.empty_cache()
         out['sweep'] = sweep_measure(args, cx, steps=3, warm=1)
