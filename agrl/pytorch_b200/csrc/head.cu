@@ -954,17 +954,21 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
             wait_bar(b_done + 8 * acc, cb >> 1);
             if (warp == 0) AGRL_TL(64 + cb);
             gemm::tc_fence_after();
-            uint32_t r[2][32];
-            gemm::tmem_ld_32x32(tlane + acc * 128 + ehalf * 64, r[0]);
-            gemm::tmem_ld_32x32(tlane + acc * 128 + ehalf * 64 + 32, r[1]);
-            gemm::tmem_ld_wait();
-            gemm::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) gemm::mbar_arrive(b_accfree + 8 * acc);
-            if (warp == 0) AGRL_TL(80 + cb);
-            if (erow < V) {
+            // 32 channels at a time (64 accumulator values at once do not fit the 72 registers of a thread next to the
+            // conversion's temporaries); the accumulator is released after the second read -- the drain, not the MMAs of
+            // the next block, paces this phase, so an earlier release would buy nothing
 #pragma unroll
-                for (int hq = 0; hq < 2; ++hq) {
+            for (int hq = 0; hq < 2; ++hq) {
+                uint32_t r[1][32];
+                gemm::tmem_ld_32x32(tlane + acc * 128 + ehalf * 64 + hq * 32, r[0]);
+                gemm::tmem_ld_wait();
+                if (hq == 1) {
+                    gemm::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) gemm::mbar_arrive(b_accfree + 8 * acc);
+                    if (warp == 0) AGRL_TL(80 + cb);
+                }
+                if (erow < V) {
                     __nv_bfloat16 *dst = a.y_planes + (static_cast<size_t>(b) * V + erow) * C + cb * 128 + ehalf * 64 + hq * 32;
                     if (a.fp8) {
                         // this thread's 64 channels are exactly k-block 2 cb + ehalf of the row
@@ -976,7 +980,7 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
                         for (int e = 0; e < 4; ++e) {
                             float v[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[hq][8 * e + i]) * y_scale;
+                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[0][8 * e + i]) * y_scale;
                             split8_f16e4(v, h16[e], r8[e], c8[e]);
                         }
                         st256(dst, h16[0], h16[1]);
@@ -989,8 +993,8 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
                             uint32_t w[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const __half2 h = __floats2half2_rn(__uint_as_float(r[hq][8 * q + 2 * i]) * y_scale,
-                                                                    __uint_as_float(r[hq][8 * q + 2 * i + 1]) * y_scale);
+                                const __half2 h = __floats2half2_rn(__uint_as_float(r[0][8 * q + 2 * i]) * y_scale,
+                                                                    __uint_as_float(r[0][8 * q + 2 * i + 1]) * y_scale);
                                 w[i] = *reinterpret_cast<const uint32_t *>(&h);
                             }
                             reinterpret_cast<uint4 *>(dst)[q] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -1000,7 +1004,7 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
                         for (int q = 0; q < 4; ++q) {
                             float v[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[hq][8 * q + i]);
+                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[0][8 * q + i]);
                             if (a.P == 3) {
                                 uint4 pl[3];
                                 split8<3>(v, pl);
