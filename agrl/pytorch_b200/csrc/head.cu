@@ -618,7 +618,8 @@ graph_kernel_tc(const __grid_constant__ CUtensorMap map_x, GraphArgs a) {
     const int raw_stage = V * 256;
     auto stage_off = [&](int st) { return st < 2 ? kTcRawOff + st * raw_stage : kTcRingOff + 6 * kTcPlane; };
     // (L2 eviction hints on the tile copies -- keep the Gram phase's tiles, stream the message passing's -- cut the layer-2
-    // launch's DRAM reads from 0.82 to 0.72 GB and changed neither its time nor the head's: A/B on one box, tools/build_alt.sh.)
+    // launch's DRAM reads from 0.82 to 0.72 GB and changed neither its time nor the head's: A/B on one box, tools/build_alt.sh,
+    // before and after the drain rework.)
     auto load_raw = [&](int piece, int st) {          // loader: tile of channels [64 piece, +64) -> stage st
         if (lane == 0) {
             const uint32_t full = b_rfull + 8 * st;
