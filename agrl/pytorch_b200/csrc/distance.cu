@@ -31,19 +31,18 @@ static Operand carve_operand(void *buf, int64_t rows, int64_t dim, int split) {
 
 static bool split_ok(int split) { return split == AGRL_SPLIT_BF16X2 || split == AGRL_SPLIT_BF16X3 || split == AGRL_SPLIT_FP16X2; }
 
-// fp16 x 2: a CTA pair per 256 x 128 tile (three products per 48 KiB of operands and SM); a single CTA per tile when there
-// is one row tile only
+// fp16 x 2: one CTA per 128 x 128 tile, the two-MMA k-step of gemm_sm100.cuh (kWideB).  (CTA pairs on 256 x 128 tiles were
+// measured as well: 0.397 against 0.383 ms at 1980 x 9330 x 4096 -- not kept.)
 template <class Epi>
 static int launch_f16x2(const void *q_planes, int64_t num_q, const void *g_planes, int64_t g_rows, int64_t g_plane_rows,
                         int kp, const Epi &epi, cudaStream_t st) {
     CUtensorMap map_q, map_g;
     int rc;
     if ((rc = gemm::make_plane_tensor_map(&map_q, q_planes, num_q, kp, 2, gemm::BM, num_q))) return rc;
-    const bool pair = num_q > gemm::BM;
-    if ((rc = gemm::make_plane_tensor_map(&map_g, g_planes, g_rows, kp, 2, pair ? 64 : 128, g_plane_rows))) return rc;
-    if (pair) return gemm::launch_pair_gemm<2, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(g_rows), kp, epi, st);
+    if ((rc = gemm::make_plane_tensor_map(&map_g, g_planes, g_rows, kp, 2, 128, g_plane_rows))) return rc;
     return gemm::launch_split_gemm<2, 128, true>(map_q, map_g, static_cast<int>(num_q), static_cast<int>(g_rows), kp, epi, st);
 }
+
 static bool metric_ok(int metric) { return metric == AGRL_METRIC_EUCLIDEAN || metric == AGRL_METRIC_COSINE; }
 
 }  // namespace agrl

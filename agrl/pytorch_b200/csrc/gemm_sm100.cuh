@@ -47,8 +47,9 @@ constexpr int kEpiBytes = 4 * 32 * kEpiPad * 4;       // transpose staging of th
 //        bias below the fp32 rounding of the result).  Needs 8 epilogue warps (64 sums per thread).
 // kPair  CTA pairs (cta_group::2): a 256 x BN tile per pair of SMs, each CTA loading its 128 rows of A and HALF of the B
 //        tile.  Nothing for the bf16 modes (three / six products per loaded byte: MMA- or power-bound), but the modes
-//        with FEWER products per byte -- fp16 + e4m3 graph layers, fp16 x 2 distances -- are bound by the L2 -> SM
-//        operand fill (~46 B/clk/SM) with one CTA per tile, which the halved B traffic removes.
+//        with FEWER products per byte -- the fp16 + e4m3 graph layers -- are bound by the operand fill with one CTA
+//        per tile, which the halved B traffic removes (16.0 -> 12.05 ms per pass).  The fp16 x 2 distance GEMM gained
+//        nothing from pairs; it is paced by its 128-wide MMAs (see kWideB).
 template <int P, int BN, bool kSplit, bool kDirect = false, int kChunkKb = 0, bool kPair = false> struct Config {
     // epilogue flavour: kDirect = registers -> 16-byte global accesses, 8 warps (two per TMEM lane
     // quarter, half the columns each), no smem; otherwise 4 warps and a padded smem transpose so
@@ -439,7 +440,11 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                                                 int M, int N, int k_pad, const Epi &epi) {
     using Cfg = Config<P, BN, kSplit, Epi::kDirect, Epi::kChunkKb, kPair>;
     constexpr int kAccCols = Cfg::kAccCols;
-    constexpr bool kCorrPersist = kSplit && Cfg::kChunk > 0;
+    // kWideB (two planes, two accumulators, one CTA per tile): the B tile's planes lie back to back in the stage, so ONE
+    // 128 x 256 MMA per k-step multiplies a0 with [b0 ; b1] into [main | corr] and a second, 128-wide one adds a1.b0 to corr:
+    // 20 instead of 24 KiB of operand reads per k-step on the shared-memory port that paces these GEMMs
+    constexpr bool kWideB = kSplit && P == 2 && !kPair && BN == 128;
+    constexpr bool kCorrPersist = kSplit && Cfg::kChunk > 0 && !kWideB;
     extern __shared__ unsigned char smem_dyn[];
     // 128B-swizzled tiles need 1024-byte alignment
     unsigned char *smem = reinterpret_cast<unsigned char *>(
@@ -585,6 +590,14 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_e4m3(d, da1 + 2 * k, db1 + 2 * k, idesc, 1u);
                             }
+                        } else if constexpr (kWideB) {
+                            constexpr uint32_t idesc_wide = make_idesc(BM, 2 * BN, Epi::kF16);
+                            const uint64_t a0 = make_smem_desc(sa), a1 = make_smem_desc(sa + kTileBytesA), b0 = make_smem_desc(sb);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                tc_mma_bf16(d_main, a0 + 2 * k, b0 + 2 * k, idesc_wide, (first | k) != 0 ? 1u : 0u);   // a0.[b0 ; b1]
+                                tc_mma_bf16(d_corr, a1 + 2 * k, b0 + 2 * k, idesc, 1u);                                // + a1.b0
+                            }
                         } else
 #pragma unroll
                         for (int i = 0; i < Cfg::kNumPairs; ++i) {
@@ -677,7 +690,7 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                 for (int kb0 = 0; kb0 < num_kb; kb0 += chunk_kb, ++cit) {
                     const int acc = cit & 1;
                     const uint32_t acc_phase = (cit >> 1) & 1;
-                    const uint32_t tq = tlane + (kSplit ? acc * BN : acc * kAccCols) + col_half;
+                    const uint32_t tq = tlane + (kCorrPersist ? acc * BN : acc * kAccCols) + col_half;
                     const bool last_chunk = kb0 + chunk_kb >= num_kb;
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
                     tc_fence_after();
@@ -685,10 +698,22 @@ __device__ __forceinline__ void split_gemm_body(const CUtensorMap &map_a, const 
                     for (int c = 0; c < BN / 2; c += 32) {
                         uint32_t r[32];
                         tmem_ld_32x32(tq + c, r);
+                        if constexpr (kSplit && !kCorrPersist) {       // this chunk's correction sum sits next to the main one
+                            uint32_t rc[32];
+                            tmem_ld_32x32(tq + BN + c, rc);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float part = Epi::kCorrScale == 1.0f ? __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rc[j]))
+                                                                           : fmaf(__uint_as_float(rc[j]), Epi::kCorrScale, __uint_as_float(r[j]));
+                                sum[c + j] = __fadd_rn(sum[c + j], part);
+                            }
+                            continue;
+                        }
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) sum[c + j] = __fadd_rn(sum[c + j], __uint_as_float(r[j]));
-                        if (kSplit && last_chunk) {                    // the tile's correction sum, once
+                        if (kCorrPersist && last_chunk) {              // the tile's correction sum, once
                             tmem_ld_32x32(tlane + 2 * BN + (tcount & 1) * BN + col_half + c, r);
                             tmem_ld_wait();
 #pragma unroll

@@ -4,6 +4,8 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from agrl.pytorch_b200 import _lib
+if os.environ.get('HV_LIB'):                      # diagnostic A/B build (tools/build_alt.sh)
+    _lib.LIB_PATH = os.path.abspath(os.environ['HV_LIB'])
 from agrl.pytorch_b200.metrics.distance import compute_distance_matrix, PreparedOperand, distance_prepared
 
 nq, ng, d = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (1980, 9330, 4096)
