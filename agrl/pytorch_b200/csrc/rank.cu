@@ -711,6 +711,9 @@ rank_mars_merge_kernel(MarsMergeArgs a) {
         } else { keys[i] = kKeyMax; cls[i] = 0; }
     }
     for (int i = tid; i < Kp; i += kRankThreads) { okeys[i] = kKeyMax; ocls[i] = 0; }
+#ifdef AGRL_MERGE_SORT
+    unsorted = 1;
+#endif
     unsorted = __syncthreads_or(unsorted);
     const uint64_t *hk = okeys;
     const uint8_t *hc = ocls;
@@ -1108,6 +1111,7 @@ extern "C" int agrl_rank_mars_merge_dev(const uint64_t *keys, const uint8_t *cls
     const size_t smem = (static_cast<size_t>(n2) + ((max_rank + 15) & ~static_cast<size_t>(15))) * 9;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
+    AGRL_LAUNCH_BEGIN(st);          // (profiling: do not charge the collectives queued ahead on this stream to the merge)
     rank_mars_merge_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(m);
     AGRL_LAUNCH_CHECK(st, "rank_mars_merge");
     MarsArgs a;
