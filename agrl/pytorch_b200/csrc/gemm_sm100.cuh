@@ -843,6 +843,7 @@ int launch_pair_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M, 
     }();
     const int tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + BN - 1) / BN);
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    AGRL_LAUNCH_BEGIN(st);
     kern<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
     AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;
@@ -859,6 +860,7 @@ int launch_split_gemm(const CUtensorMap &map_a, const CUtensorMap &map_b, int M,
     // persistent grid: one CTA per SM, or per SM of the partition the caller leaves to this kernel (max_ctas > 0)
     const int width = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
     const int grid = tiles < width ? tiles : width;
+    AGRL_LAUNCH_BEGIN(st);
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(map_a, map_b, M, N, k_pad, epi);
     AGRL_LAUNCH_CHECK(st, Epi::kName);
     return AGRL_OK;

@@ -942,6 +942,7 @@ static int narrow_labels(const RankWorkspace &w, const int64_t *qp, const int64_
     int blocks = static_cast<int>((nmax + 255) / 256);
     if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
     if (blocks < 1) blocks = 1;
+    AGRL_LAUNCH_BEGIN(st);
     narrow_labels_kernel<<<dim3(blocks, 4), 256, 0, st>>>(la, status);
     AGRL_LAUNCH_CHECK(st, "narrow_labels");
     return AGRL_OK;
@@ -1082,6 +1083,7 @@ extern "C" int agrl_rank_mars_partial_dev(const float *distmat, int64_t ld,
     const size_t smem = static_cast<size_t>(L) * 8 + align_up(static_cast<size_t>(max_rank), 16);
     AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_mars_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
+    AGRL_LAUNCH_BEGIN(st);
     rank_mars_kernel<true><<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
     AGRL_LAUNCH_CHECK(st, "rank_mars_partial");
     return AGRL_OK;
@@ -1150,6 +1152,7 @@ extern "C" int agrl_rank_market1501_count_dev(const int64_t *q_pids, const int64
     MarketShardArgs a;
     fill_shard_args(a, w, nullptr, 0, num_q, num_g, 0);
     a.max_count = max_count;
+    AGRL_LAUNCH_BEGIN(st);
     rank_market_gather_kernel<true><<<static_cast<unsigned>(num_q), kRankThreads, 0, st>>>(a);
     AGRL_LAUNCH_CHECK(st, "rank_market_count");
     return AGRL_OK;
@@ -1174,6 +1177,7 @@ extern "C" int agrl_rank_market1501_gather_dev(const float *distmat, int64_t ld,
     MarketShardArgs a;
     fill_shard_args(a, w, distmat, ld, num_q, num_g, index_offset);
     a.cap = static_cast<int>(cap); a.keys = keys; a.npos = npos; a.njunk = njunk;
+    AGRL_LAUNCH_BEGIN(st);
     rank_market_gather_kernel<false><<<static_cast<unsigned>(num_q), kRankThreads, 0, st>>>(a);
     AGRL_LAUNCH_CHECK(st, "rank_market_gather");
     return AGRL_OK;
@@ -1201,6 +1205,7 @@ extern "C" int agrl_rank_market1501_bin_dev(const float *distmat, int64_t ld, in
     a.keys = const_cast<uint64_t *>(keys_all); a.cnt = cnt; a.sorted = sorted;
     const size_t smem = static_cast<size_t>(a.n2) * 8 + (static_cast<size_t>(a.n2) + 1) * 4;
     AGRL_CUDA_TRY(cudaFuncSetAttribute(rank_market_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    AGRL_LAUNCH_BEGIN(st);
     rank_market_bin_kernel<<<static_cast<unsigned>(num_q), kRankThreads, smem, st>>>(a);
     AGRL_LAUNCH_CHECK(st, "rank_market_bin");
     return AGRL_OK;
@@ -1237,6 +1242,7 @@ extern "C" int agrl_rank_market1501_finalize_dev(const int32_t *cnt_total, const
     f.flags = reinterpret_cast<uint32_t *>(w.counters + 1);
     f.terms = terms;
     const int wpb = kRankThreads / 32;
+    AGRL_LAUNCH_BEGIN(st);
     rank_market_finalize_kernel<<<static_cast<unsigned>((num_q + wpb - 1) / wpb), kRankThreads, 0, st>>>(f);
     AGRL_LAUNCH_CHECK(st, "rank_market_finalize");
     MarketArgs a;
@@ -1389,6 +1395,7 @@ extern "C" int agrl_rank_mars_classify_dev(const uint64_t *keys, const int64_t *
     const int64_t nmax = num_q > num_g ? num_q : num_g;
     int blocks = static_cast<int>((nmax + 255) / 256);
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    AGRL_LAUNCH_BEGIN(st);
     narrow_labels_kernel<<<dim3(blocks, 4), 256, 0, st>>>(la, status);
     AGRL_LAUNCH_CHECK(st, "narrow_labels");
     AGRL_CUDA_TRY(cudaMemsetAsync(w.tab_p, 0xFF, sizeof(int32_t) * 2 * w.slots, st));       // both tables: empty (-1)

@@ -114,6 +114,7 @@ split_planes_kernel(SplitArgs a) {
 
 int launch_split_planes(const SplitArgs &a, cudaStream_t st) {
     if (a.rows <= 0) return AGRL_OK;
+    AGRL_LAUNCH_BEGIN(st);
     split_planes_kernel<<<static_cast<unsigned>(a.rows), kSplitThreads, 0, st>>>(a);
     AGRL_LAUNCH_CHECK(st, "split_planes");
     return AGRL_OK;
