@@ -246,7 +246,8 @@ struct EpiDistanceT {           // distance.py:59-73 / :76-89
     static constexpr bool kF16 = kF16x2;
     static constexpr float kCorrScale = kF16x2 ? 0.00048828125f : 1.0f;
     static constexpr bool kDirect = false;      // rows of arbitrary alignment: coalesce through smem
-    static constexpr int kChunkKb = 4;          // drain the accumulator every 256 k (fp32-accurate sums)
+    static constexpr int kChunkKb = 4;          // drain the accumulator every 256 k (fp32-accurate sums).  Measured at 1980 x 9330 x 4096,
+                                                // fp16 x 2: 4 -> 0.383 ms, 1.5e-6 on clustered data; 16 -> 0.347 ms, 6.0e-6; never -> 0.345 ms, 2.5e-5
     static constexpr bool kRowwise = false;
     static constexpr bool kFp8 = false;
     const float *qn, *gn;       // squared norms (euclidean); unused for cosine
