@@ -34,12 +34,24 @@ def test_library_exports_every_declared_symbol():
     assert b'no CPU fallback' in lib.agrl_status_string(_lib.E_NO_DEVICE)
 
 
+def test_library_exports_nothing_but_the_header():
+    """no diagnostic entry points (e.g. the -DAGRL_TIMELINE build's agrl_timeline_set) in the product library"""
+    import subprocess
+    from agrl.pytorch_b200 import _lib
+    _lib.load()
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(line.split()[-1] for line in out.splitlines() if ' T ' in line and line.split()[-1].startswith('agrl_'))
+    assert exported == declared_symbols()
+
+
 def test_workspace_queries_need_no_device():
     from agrl.pytorch_b200 import _lib
     lib = _lib.load()
     assert lib.agrl_rank_workspace_bytes(1980, 9330, 50) > 4 * (2 * 1980 + 2 * 9330)
     # 3 bf16 planes of both operands + norms
     assert lib.agrl_distance_workspace_bytes(1980, 9330, 2048, 3) >= 3 * 2 * 2048 * (1980 + 9330)
+    # the default split of the distance matrix: two fp16 planes + norms + per-row scales
+    assert lib.agrl_distance_workspace_bytes(1980, 9330, 2048, _lib.SPLIT_FP16X2) >= (2 * 2 * 2048 + 8) * (1980 + 9330)
     assert lib.agrl_distance_workspace_bytes(10, 10, 2048, 7) == 0
     P = _lib.HeadParams()
     P.channels, P.num_layers, P.use_pose, P.learn_graph, P.split = 2048, 2, 1, 1, 2
