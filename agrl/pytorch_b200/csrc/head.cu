@@ -370,6 +370,10 @@ pool_tma_kernel(PoolTmaArgs a) {
                         gsum[i] += (v.x + v.y) + (v.z + v.w);
                     }
                 }
+                // the stage is handed back only when its values have ARRIVED in registers: the next bulk copy into it comes
+                // from another proxy, and an arrive right behind the shared-memory loads does not wait for them (this
+                // ordering cost graph_kernel_tc a 1e-3 error once) -- the empty asm makes the sums, hence the loads, precede it
+                asm volatile("" ::"f"(gsum[0]), "f"(gsum[1]), "f"(gsum[2]), "f"(gsum[3]), "f"(gsum[4]), "f"(gsum[5]), "f"(gsum[6]), "f"(gsum[7]) : "memory");
                 __syncwarp();
                 if (lane == 0) gemm::mbar_arrive(bar_empty + 8 * stage);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -383,8 +387,9 @@ pool_tma_kernel(PoolTmaArgs a) {
                         const float4 v = p[i * 32];
                         q[i] = (v.x + v.y) + (v.z + v.w);
                     }
+                    asm volatile("" ::"f"(q[0]), "f"(q[1]), "f"(q[2]), "f"(q[3]), "f"(q[4]), "f"(q[5]), "f"(q[6]), "f"(q[7]) : "memory");
                     __syncwarp();
-                    if (lane == 0) gemm::mbar_arrive(bar_empty + 8 * stage);      // values are in registers
+                    if (lane == 0) gemm::mbar_arrive(bar_empty + 8 * stage);      // values are in registers (see above)
                     // lane (grp, sub) ends with channel `sub`'s sum over quarter strip `grp`
                     const float v2 = group8_transpose_sum(q, sub);
                     const float h2 = v2 + __shfl_xor_sync(0xffffffffu, v2, 8);       // half strips
