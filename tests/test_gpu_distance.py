@@ -140,3 +140,22 @@ def test_argument_checks(cdm):
     with pytest.raises(ValueError, match='Unknown distance metric'):
         cdm(a, a, 'manhattan')
     assert cdm(a[:0], a).shape == (0, 3)
+
+
+@pytest.mark.parametrize('metric', ['euclidean', 'cosine'])
+@pytest.mark.parametrize('split', ACCURATE_SPLITS)
+def test_distance_is_symmetric_at_the_mars_shape(cdm, metric, split):
+    """d(a, b) == d(b, a)^T to fp32 rounding -- a size-independent property, checked at the MARS shape where the two calls
+    run different tile grids (not bit for bit: the correction products a0.b1 + a1.b0 swap roles, and the tensor core's
+    accumulate truncation depends on the order)"""
+    g = torch.Generator(device='cuda').manual_seed(17)
+    a = torch.randn(1980, 2048, generator=g, device='cuda')
+    b = torch.randn(9330, 2048, generator=g, device='cuda')
+    ab = cdm(a, b, metric, split=split)
+    ba = cdm(b, a, metric, split=split)
+    scale = float((a ** 2).sum(1).max() + (b ** 2).sum(1).max()) if metric == 'euclidean' else 1.0
+    assert float((ab - ba.t()).abs().max()) < FP32_TOL * scale
+    # and the diagonal of d(a, a) is (numerically) zero: |a|^2 + |a|^2 - 2 a.a cancels to rounding, 1 - cos = 0 to 1e-6
+    aa = cdm(a[:300], a[:300], metric, split=split)
+    scale = float((a[:300] ** 2).sum(1).max()) * 2 if metric == 'euclidean' else 1.0
+    assert float(aa.diagonal().abs().max()) < FP32_TOL * scale
